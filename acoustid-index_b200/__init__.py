@@ -1,0 +1,12 @@
+"""fpx — B200-native `_search` path for acoustid-index (fpindex).
+
+The product is libfpx.so (csrc/: hand-written sm_100a kernels behind the C ABI in include/fpx.h).
+This Python package is the host-side mirror of the reference interface used by tests and bench.py.
+The directory name has a hyphen (it mirrors the reference repo name); import it through
+`__graft_entry__.load_package()` which registers it as `acoustid_index_b200`.
+"""
+from . import _ffi, index, synth  # noqa: F401
+from ._ffi import FpxError, build as build_library, lib  # noqa: F401
+from .index import (Context, FileSegment, IndexReader, MemorySegment, SearchOptions, SearchRequest,  # noqa: F401
+                    SearchResult, Snapshot, SnapshotBuilder, merge_shard_results, multi_index_search,
+                    swap_snapshot)

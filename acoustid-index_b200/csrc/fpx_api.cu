@@ -1,0 +1,724 @@
+// fpx_api.cu — the extern "C" boundary declared in include/fpx.h.
+//
+// Host-side responsibilities: context / workspace pool, snapshot lifetime (immutable, atomically
+// refcounted — mirrors SharedPtr(Segments), src/shared_ptr.zig + src/Index.zig:430-485), upload of the
+// compiled CSR, and the batched search driver (chunked H2D -> kernels -> D2H on rotating streams).
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/fpx.h"
+#include "fpx_kernels.cuh"
+#include "fpx_snapshot_host.h"
+
+using namespace fpx;
+
+static_assert(sizeof(fpx_search_opts) == sizeof(SearchOpts), "opts layout");
+static_assert(sizeof(TermEntry) == 16, "directory entry is one 128-bit load");
+static_assert(FPX_MAX_QUERY_TERMS == kMaxQueryTerms && FPX_MAX_RESULTS == kMaxResults, "limits");
+
+namespace {
+
+thread_local std::string g_error;
+
+fpx_status set_error(fpx_status st, const std::string &msg) {
+    g_error = msg;
+    return st;
+}
+fpx_status cuda_fail(cudaError_t e, const char *what) {
+    g_error = std::string(what) + ": " + cudaGetErrorString(e);
+    if (e == cudaErrorMemoryAllocation) return FPX_OUT_OF_MEMORY;
+    return FPX_CUDA_ERROR;
+}
+#define FPX_CUDA(call)                                           \
+    do {                                                         \
+        cudaError_t e__ = (call);                                \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);    \
+    } while (0)
+
+enum KernelKind { KK_PREPARE = 0, KK_SEARCH = 1, KK_WIDE = 2, KK_H2D = 3, KK_D2H = 4 };
+
+struct EventPair {
+    int kind;
+    cudaEvent_t a, b;
+};
+
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr; // last use (async device API)
+    bool done_pending = false;
+    DevBuf<uint2> rows;
+    DevBuf<QueryInfo> qinfo;
+    DevBuf<uint32_t> queues, long_queue;
+    DevBuf<unsigned long long> wide_tables;
+    BatchCounters *counters = nullptr;
+    // staging for host batches
+    DevBuf<uint32_t> d_terms, d_ids, d_scores, d_counts;
+    DevBuf<uint64_t> d_offsets;
+    DevBuf<SearchOpts> d_opts;
+    uint32_t *h_error = nullptr; // pinned
+
+    ~Workspace() {
+        rows.release();
+        qinfo.release();
+        queues.release();
+        long_queue.release();
+        wide_tables.release();
+        d_terms.release();
+        d_ids.release();
+        d_scores.release();
+        d_counts.release();
+        d_offsets.release();
+        d_opts.release();
+        if (counters) cudaFree(counters);
+        if (h_error) cudaFreeHost(h_error);
+        if (done) cudaEventDestroy(done);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+constexpr uint32_t kWideCapLog2 = 20;
+
+} // namespace
+
+struct fpx_ctx {
+    int device = 0;
+    int n_sms = 148;
+    unsigned host_threads = 1;
+    uint32_t chunk_queries = 32768;
+    uint32_t flags = 0;
+    bool host_only = false;
+    std::mutex mu;
+    std::vector<Workspace *> free_ws;
+    DeviceStats *d_stats = nullptr;
+    std::vector<EventPair> pending;
+    fpx_profile prof{};
+    std::atomic<uint32_t> sticky_error{0};
+};
+
+struct fpx_snapshot_builder {
+    fpx_ctx *ctx;
+    SnapshotCompiler compiler;
+    explicit fpx_snapshot_builder(fpx_ctx *c) : ctx(c), compiler(c->host_threads) {}
+};
+
+struct fpx_snapshot {
+    fpx_ctx *ctx = nullptr;
+    std::atomic<int64_t> refs{1};
+    SnapshotDev dev{};
+    TermEntry *d_table = nullptr;
+    uint32_t *d_docids = nullptr;
+    fpx_snapshot_info info{};
+    std::vector<uint32_t> h_terms, h_row_len; // host copy of the term directory
+};
+
+namespace {
+
+fpx_status acquire_workspace(fpx_ctx *ctx, Workspace **out) {
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (!ctx->free_ws.empty()) {
+            *out = ctx->free_ws.back();
+            ctx->free_ws.pop_back();
+            return FPX_OK;
+        }
+    }
+    Workspace *w = new (std::nothrow) Workspace();
+    if (!w) return set_error(FPX_OUT_OF_MEMORY, "workspace");
+    cudaError_t e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&w->counters, sizeof(BatchCounters));
+    if (e == cudaSuccess) e = cudaMallocHost(&w->h_error, sizeof(uint32_t));
+    if (e == cudaSuccess) e = w->wide_tables.reserve((size_t)wide_ctas(ctx->n_sms) << kWideCapLog2);
+    if (e != cudaSuccess) {
+        delete w;
+        return cuda_fail(e, "workspace allocation");
+    }
+    *w->h_error = 0;
+    *out = w;
+    return FPX_OK;
+}
+
+void release_workspace(fpx_ctx *ctx, Workspace *w) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->free_ws.push_back(w);
+}
+
+struct Timed {
+    fpx_ctx *ctx;
+    cudaStream_t st;
+    int kind;
+    cudaEvent_t a = nullptr, b = nullptr;
+    Timed(fpx_ctx *c, cudaStream_t s, int k) : ctx(c), st(s), kind(k) {
+        if (ctx->flags & FPX_FLAG_PROFILE) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, st);
+        }
+    }
+    ~Timed() {
+        if (a) {
+            cudaEventRecord(b, st);
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            ctx->pending.push_back(EventPair{kind, a, b});
+        }
+    }
+};
+
+// Enqueue the kernels of one batch on `st`.  All pointers are device pointers.
+fpx_status enqueue_batch(fpx_snapshot *s, Workspace *w, cudaStream_t st, uint64_t n_queries, uint64_t n_terms_total,
+                         const uint32_t *d_terms, const uint64_t *d_offsets, uint64_t term_base,
+                         const SearchOpts *d_opts, uint32_t k_stride, uint32_t *d_ids, uint32_t *d_scores,
+                         uint32_t *d_counts) {
+    fpx_ctx *ctx = s->ctx;
+    if (n_queries == 0) return FPX_OK;
+    if (n_queries > 0x7FFFFFFFull) return set_error(FPX_INVALID_ARGUMENT, "batch too large (split it)");
+    cudaError_t e = w->rows.reserve(n_terms_total + 1);
+    if (e == cudaSuccess) e = w->qinfo.reserve(n_queries);
+    if (e == cudaSuccess) e = w->queues.reserve(n_queries * kNumClasses);
+    if (e == cudaSuccess) e = w->long_queue.reserve(n_queries);
+    if (e != cudaSuccess) return cuda_fail(e, "workspace growth");
+
+    BatchArgs a{};
+    a.snap = s->dev;
+    a.n_queries = (uint32_t)n_queries;
+    a.k_stride = k_stride;
+    a.terms = d_terms;
+    a.term_offsets = d_offsets;
+    a.term_base = term_base;
+    a.opts = d_opts;
+    a.out_ids = d_ids;
+    a.out_scores = d_scores;
+    a.out_counts = d_counts;
+    a.rows = w->rows.p;
+    a.qinfo = w->qinfo.p;
+    a.queues = w->queues.p;
+    a.long_queue = w->long_queue.p;
+    a.counters = w->counters;
+    a.stats = (ctx->flags & FPX_FLAG_PROFILE) ? ctx->d_stats : nullptr;
+    a.wide_tables = w->wide_tables.p;
+    a.wide_cap_log2 = kWideCapLog2;
+
+    FPX_CUDA(cudaMemsetAsync(w->counters, 0, sizeof(BatchCounters), st));
+    {
+        Timed t(ctx, st, KK_PREPARE);
+        launch_prepare(a, st);
+        launch_prepare_long(a, st, ctx->n_sms);
+    }
+    {
+        Timed t(ctx, st, KK_SEARCH);
+        for (int c = 0; c < 3; ++c) launch_search_class(a, c, st, ctx->n_sms);
+    }
+    {
+        Timed t(ctx, st, KK_WIDE);
+        launch_search_wide(a, st, wide_ctas(ctx->n_sms));
+    }
+    FPX_CUDA(cudaGetLastError());
+    FPX_CUDA(cudaMemcpyAsync(w->h_error, &w->counters->error, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    return FPX_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+uint32_t fpx_abi_version(void) { return FPX_ABI_VERSION; }
+
+const char *fpx_last_error_message(void) { return g_error.c_str(); }
+
+fpx_status fpx_init(const fpx_config *config, fpx_ctx **out) {
+    if (!out) return set_error(FPX_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    fpx_config cfg{};
+    cfg.device = -1;
+    if (config) cfg = *config;
+    fpx_ctx *ctx = new (std::nothrow) fpx_ctx();
+    if (!ctx) return set_error(FPX_OUT_OF_MEMORY, "ctx");
+    ctx->flags = cfg.flags;
+    ctx->host_threads = cfg.host_threads ? cfg.host_threads : std::max(1u, std::thread::hardware_concurrency());
+    if (cfg.chunk_queries) ctx->chunk_queries = cfg.chunk_queries;
+    ctx->host_only = (cfg.flags & FPX_FLAG_HOST_ONLY) != 0;
+    if (!ctx->host_only) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) {
+            delete ctx;
+            cudaGetLastError();
+            return set_error(FPX_BACKEND_UNAVAILABLE, "no CUDA device available; the fpx search path requires a GPU");
+        }
+        if (cfg.device >= 0) {
+            if (cfg.device >= n) {
+                delete ctx;
+                return set_error(FPX_INVALID_ARGUMENT, "device ordinal out of range");
+            }
+            e = cudaSetDevice(cfg.device);
+            ctx->device = cfg.device;
+        } else {
+            e = cudaGetDevice(&ctx->device);
+        }
+        cudaDeviceProp prop{};
+        if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, ctx->device);
+        if (e == cudaSuccess && prop.major < 10) {
+            delete ctx;
+            return set_error(FPX_BACKEND_UNAVAILABLE, "fpx kernels are built for sm_100a (Blackwell) only");
+        }
+        if (e == cudaSuccess) {
+            ctx->n_sms = prop.multiProcessorCount;
+            e = configure_kernels();
+        }
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->d_stats, sizeof(DeviceStats));
+        if (e == cudaSuccess) e = cudaMemset(ctx->d_stats, 0, sizeof(DeviceStats));
+        if (e != cudaSuccess) {
+            fpx_status st = cuda_fail(e, "fpx_init");
+            delete ctx;
+            return st;
+        }
+    }
+    *out = ctx;
+    return FPX_OK;
+}
+
+void fpx_shutdown(fpx_ctx *ctx) {
+    if (!ctx) return;
+    if (!ctx->host_only) {
+        cudaSetDevice(ctx->device);
+        cudaDeviceSynchronize();
+        for (Workspace *w : ctx->free_ws) delete w;
+        for (auto &p : ctx->pending) {
+            cudaEventDestroy(p.a);
+            cudaEventDestroy(p.b);
+        }
+        if (ctx->d_stats) cudaFree(ctx->d_stats);
+    }
+    delete ctx;
+}
+
+fpx_status fpx_snapshot_begin(fpx_ctx *ctx, fpx_snapshot_builder **out) {
+    if (!ctx || !out) return set_error(FPX_INVALID_ARGUMENT, "null argument");
+    *out = new (std::nothrow) fpx_snapshot_builder(ctx);
+    return *out ? FPX_OK : set_error(FPX_OUT_OF_MEMORY, "builder");
+}
+
+fpx_status fpx_snapshot_add_file_segment(fpx_snapshot_builder *b, const fpx_file_segment *seg) {
+    if (!b || !seg) return set_error(FPX_INVALID_ARGUMENT, "null argument");
+    if (seg->n_docs && !seg->doc_ids) return set_error(FPX_INVALID_ARGUMENT, "null doc_ids");
+    try {
+        if (!b->compiler.add_file_segment(seg->commit_id, seg->merges, seg->min_doc_id, seg->block_size, seg->blocks,
+                                          seg->num_blocks, seg->block_index, seg->doc_ids, seg->n_docs))
+            return set_error(FPX_INVALID_SEGMENT, b->compiler.error);
+    } catch (const std::bad_alloc &) {
+        return set_error(FPX_OUT_OF_MEMORY, "decoding file segment");
+    }
+    return FPX_OK;
+}
+
+fpx_status fpx_snapshot_add_memory_segment(fpx_snapshot_builder *b, const fpx_memory_segment *seg) {
+    if (!b || !seg) return set_error(FPX_INVALID_ARGUMENT, "null argument");
+    if (seg->n_docs && !seg->doc_ids) return set_error(FPX_INVALID_ARGUMENT, "null doc_ids");
+    try {
+        if (!b->compiler.add_memory_segment(seg->commit_id, seg->merges, seg->items, seg->n_items, seg->doc_ids,
+                                            seg->n_docs))
+            return set_error(FPX_INVALID_SEGMENT, b->compiler.error);
+    } catch (const std::bad_alloc &) {
+        return set_error(FPX_OUT_OF_MEMORY, "reading memory segment");
+    }
+    return FPX_OK;
+}
+
+fpx_status fpx_snapshot_set_doc_range(fpx_snapshot_builder *b, uint32_t lo, uint32_t hi) {
+    if (!b) return set_error(FPX_INVALID_ARGUMENT, "null argument");
+    if (hi < lo) return set_error(FPX_INVALID_ARGUMENT, "hi < lo");
+    b->compiler.set_doc_range(lo, hi);
+    return FPX_OK;
+}
+
+fpx_status fpx_snapshot_compile(fpx_snapshot_builder *b) {
+    if (!b) return set_error(FPX_INVALID_ARGUMENT, "null argument");
+    try {
+        if (!b->compiler.compile()) return set_error(FPX_INVALID_SEGMENT, b->compiler.error);
+    } catch (const std::bad_alloc &) {
+        return set_error(FPX_OUT_OF_MEMORY, "compiling snapshot");
+    }
+    return FPX_OK;
+}
+
+fpx_status fpx_snapshot_csr(fpx_snapshot_builder *b, fpx_csr_view *out) {
+    if (!b || !out) return set_error(FPX_INVALID_ARGUMENT, "null argument");
+    fpx_status st = fpx_snapshot_compile(b);
+    if (st != FPX_OK) return st;
+    CompiledCsr *c = b->compiler.compiled();
+    b->compiler.make_dense(*c);
+    out->n_terms = c->terms.size();
+    out->terms = c->terms.data();
+    out->row_offsets = c->dense_offsets.data();
+    out->docids = c->dense_docids.data();
+    return FPX_OK;
+}
+
+void fpx_snapshot_abort(fpx_snapshot_builder *b) { delete b; }
+
+fpx_status fpx_snapshot_commit(fpx_snapshot_builder *b, fpx_snapshot **out) {
+    if (!b || !out) return set_error(FPX_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    fpx_ctx *ctx = b->ctx;
+    if (ctx->host_only) return set_error(FPX_BACKEND_UNAVAILABLE, "context was created with FPX_FLAG_HOST_ONLY");
+    fpx_status st = fpx_snapshot_compile(b);
+    if (st != FPX_OK) return st;
+    CompiledCsr *c = b->compiler.compiled();
+    FPX_CUDA(cudaSetDevice(ctx->device));
+
+    fpx_snapshot *s = new (std::nothrow) fpx_snapshot();
+    if (!s) return set_error(FPX_OUT_OF_MEMORY, "snapshot");
+    s->ctx = ctx;
+    const size_t nt = c->terms.size();
+    uint32_t log2cap = 4;
+    while ((1ull << log2cap) < 2 * (uint64_t)nt) ++log2cap;
+    if (log2cap > 31) {
+        delete s;
+        return set_error(FPX_UNSUPPORTED, "too many distinct terms");
+    }
+    const size_t cap = (size_t)1 << log2cap;
+    const size_t n_doc_words = std::max<size_t>(c->docids.size(), 4);
+    uint32_t *d_t = nullptr, *d_l = nullptr, *d_s4 = nullptr;
+    cudaError_t e = cudaMalloc(&s->d_table, cap * sizeof(TermEntry));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_docids, n_doc_words * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(s->d_table, 0, cap * sizeof(TermEntry));
+    if (e == cudaSuccess && !c->docids.empty())
+        e = cudaMemcpy(s->d_docids, c->docids.data(), c->docids.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && nt) {
+        e = cudaMalloc(&d_t, nt * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&d_l, nt * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&d_s4, nt * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(d_t, c->terms.data(), nt * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_l, c->row_len.data(), nt * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_s4, c->row_start4.data(), nt * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            launch_build_table(s->d_table, log2cap, d_t, d_l, d_s4, nt, nullptr);
+            e = cudaDeviceSynchronize();
+        }
+    }
+    if (d_t) cudaFree(d_t);
+    if (d_l) cudaFree(d_l);
+    if (d_s4) cudaFree(d_s4);
+    if (e != cudaSuccess) {
+        if (s->d_table) cudaFree(s->d_table);
+        if (s->d_docids) cudaFree(s->d_docids);
+        delete s;
+        return cuda_fail(e, "snapshot upload");
+    }
+    s->dev.table = s->d_table;
+    s->dev.table_mask = (uint32_t)(cap - 1);
+    s->dev.table_shift = 32 - log2cap;
+    s->dev.docids = s->d_docids;
+    s->dev.pad_id = c->pad_id;
+    s->info.n_segments = b->compiler.n_segments();
+    s->info.n_terms = nt;
+    s->info.n_postings = c->n_postings;
+    s->info.n_postings_total = c->n_postings_total;
+    s->info.n_dropped_unreachable = c->n_unreachable;
+    s->info.n_dropped_superseded = c->n_superseded;
+    s->info.n_dropped_out_of_range = c->n_out_of_range;
+    s->info.device_bytes = cap * sizeof(TermEntry) + n_doc_words * sizeof(uint32_t);
+    s->info.max_row_len = c->max_row_len;
+    s->info.pad_id = c->pad_id;
+    s->info.table_log2 = log2cap;
+    s->info.doc_lo = b->compiler.doc_lo();
+    s->info.doc_hi = b->compiler.doc_hi();
+    s->h_terms = std::move(c->terms);
+    s->h_row_len = std::move(c->row_len);
+    delete b;
+    *out = s;
+    return FPX_OK;
+}
+
+fpx_status fpx_snapshot_acquire(fpx_snapshot *s) {
+    if (!s) return set_error(FPX_INVALID_ARGUMENT, "null snapshot");
+    s->refs.fetch_add(1, std::memory_order_relaxed);
+    return FPX_OK;
+}
+
+fpx_status fpx_snapshot_release(fpx_snapshot *s) {
+    if (!s) return set_error(FPX_INVALID_ARGUMENT, "null snapshot");
+    if (s->refs.fetch_sub(1, std::memory_order_acq_rel) == 1) { // shared_ptr.zig:23-34
+        cudaSetDevice(s->ctx->device);
+        cudaDeviceSynchronize(); // no search may still be reading the rows
+        if (s->d_table) cudaFree(s->d_table);
+        if (s->d_docids) cudaFree(s->d_docids);
+        delete s;
+    }
+    return FPX_OK;
+}
+
+fpx_status fpx_snapshot_get_info(const fpx_snapshot *s, fpx_snapshot_info *out) {
+    if (!s || !out) return set_error(FPX_INVALID_ARGUMENT, "null argument");
+    *out = s->info;
+    return FPX_OK;
+}
+
+fpx_status fpx_snapshot_row_lengths(const fpx_snapshot *s, const uint32_t *terms, uint64_t n, uint32_t *out_lengths) {
+    if (!s || (n && (!terms || !out_lengths))) return set_error(FPX_INVALID_ARGUMENT, "null argument");
+    const auto &t = s->h_terms;
+    parallel_for(n, s->ctx->host_threads, [&](size_t a, size_t b, unsigned) {
+        for (size_t i = a; i < b; ++i) {
+            auto it = std::lower_bound(t.begin(), t.end(), terms[i]);
+            out_lengths[i] = (it != t.end() && *it == terms[i]) ? s->h_row_len[(size_t)(it - t.begin())] : 0u;
+        }
+    });
+    return FPX_OK;
+}
+
+uint32_t fpx_default_min_score(uint64_t raw_query_len) { return (uint32_t)((raw_query_len + 19) / 20); }
+
+fpx_status fpx_search_batch_device(fpx_snapshot *s, uint64_t n_queries, const uint32_t *d_terms,
+                                   const uint64_t *d_term_offsets, const fpx_search_opts *d_opts, uint32_t k_stride,
+                                   uint32_t *d_out_ids, uint32_t *d_out_scores, uint32_t *d_out_counts,
+                                   void *cuda_stream);
+
+} // extern "C"
+
+namespace {
+
+// total number of terms is needed to size the row workspace; the device API reads it back once
+fpx_status device_total_terms(const uint64_t *d_offsets, uint64_t n_queries, cudaStream_t st, uint64_t *first,
+                              uint64_t *last) {
+    FPX_CUDA(cudaMemcpyAsync(first, d_offsets, 8, cudaMemcpyDeviceToHost, st));
+    FPX_CUDA(cudaMemcpyAsync(last, d_offsets + n_queries, 8, cudaMemcpyDeviceToHost, st));
+    FPX_CUDA(cudaStreamSynchronize(st));
+    return FPX_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+fpx_status fpx_search_batch_device(fpx_snapshot *s, uint64_t n_queries, const uint32_t *d_terms,
+                                   const uint64_t *d_term_offsets, const fpx_search_opts *d_opts, uint32_t k_stride,
+                                   uint32_t *d_out_ids, uint32_t *d_out_scores, uint32_t *d_out_counts,
+                                   void *cuda_stream) {
+    if (!s) return set_error(FPX_INVALID_ARGUMENT, "null snapshot");
+    if (n_queries == 0) return FPX_OK;
+    if (!d_term_offsets || !d_opts || !d_out_counts || (k_stride && (!d_out_ids || !d_out_scores)))
+        return set_error(FPX_INVALID_ARGUMENT, "null buffer");
+    if (k_stride > FPX_MAX_RESULTS) return set_error(FPX_UNSUPPORTED, "k_stride exceeds FPX_MAX_RESULTS");
+    fpx_ctx *ctx = s->ctx;
+    FPX_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    uint64_t first = 0, last = 0;
+    fpx_status rc = device_total_terms(d_term_offsets, n_queries, st, &first, &last);
+    if (rc != FPX_OK) return rc;
+    if (last < first) return set_error(FPX_INVALID_ARGUMENT, "term_offsets not ascending");
+    Workspace *w = nullptr;
+    rc = acquire_workspace(ctx, &w);
+    if (rc != FPX_OK) return rc;
+    if (w->done_pending) { // its previous batch may still be running on another stream
+        cudaStreamWaitEvent(st, w->done, 0);
+        w->done_pending = false;
+    }
+    // term_offsets index d_terms absolutely; the row workspace is indexed relative to the first offset
+    rc = enqueue_batch(s, w, st, n_queries, last - first, d_terms ? d_terms + first : nullptr, d_term_offsets, first,
+                       reinterpret_cast<const SearchOpts *>(d_opts), k_stride, d_out_ids, d_out_scores, d_out_counts);
+    if (rc == FPX_OK) {
+        cudaEventRecord(w->done, st);
+        w->done_pending = true;
+    }
+    release_workspace(ctx, w);
+    return rc;
+}
+
+fpx_status fpx_search_batch(fpx_snapshot *s, uint64_t n_queries, const uint32_t *terms, const uint64_t *term_offsets,
+                            const fpx_search_opts *opts, uint32_t k_stride, uint32_t *out_ids, uint32_t *out_scores,
+                            uint32_t *out_counts) {
+    if (!s) return set_error(FPX_INVALID_ARGUMENT, "null snapshot");
+    if (n_queries == 0) return FPX_OK;
+    if (!term_offsets || !opts || !out_counts || (k_stride && (!out_ids || !out_scores)))
+        return set_error(FPX_INVALID_ARGUMENT, "null buffer");
+    if (k_stride > FPX_MAX_RESULTS) return set_error(FPX_UNSUPPORTED, "k_stride exceeds FPX_MAX_RESULTS");
+    for (uint64_t q = 0; q < n_queries; ++q) {
+        if (term_offsets[q + 1] < term_offsets[q]) return set_error(FPX_INVALID_ARGUMENT, "term_offsets not ascending");
+        if (term_offsets[q + 1] - term_offsets[q] > FPX_MAX_QUERY_TERMS)
+            return set_error(FPX_UNSUPPORTED, "query has more than FPX_MAX_QUERY_TERMS terms");
+    }
+    if (term_offsets[n_queries] > term_offsets[0] && !terms) return set_error(FPX_INVALID_ARGUMENT, "null terms");
+    fpx_ctx *ctx = s->ctx;
+    FPX_CUDA(cudaSetDevice(ctx->device));
+
+    const uint64_t chunk = ctx->chunk_queries;
+    const uint64_t n_chunks = (n_queries + chunk - 1) / chunk;
+    const int n_ws = (int)std::min<uint64_t>(n_chunks, 3);
+    Workspace *ws[3] = {nullptr, nullptr, nullptr};
+    fpx_status rc = FPX_OK;
+    for (int i = 0; i < n_ws && rc == FPX_OK; ++i) rc = acquire_workspace(ctx, &ws[i]);
+    for (uint64_t c = 0; c < n_chunks && rc == FPX_OK; ++c) {
+        Workspace *w = ws[c % n_ws];
+        cudaStream_t st = w->stream;
+        if (w->done_pending) {
+            cudaStreamWaitEvent(st, w->done, 0);
+            w->done_pending = false;
+        }
+        const uint64_t q0 = c * chunk, q1 = std::min(n_queries, q0 + chunk), nq = q1 - q0;
+        const uint64_t t0 = term_offsets[q0], t1 = term_offsets[q1], nt = t1 - t0;
+        cudaError_t e = w->d_terms.reserve(nt + 1);
+        if (e == cudaSuccess) e = w->d_offsets.reserve(nq + 1);
+        if (e == cudaSuccess) e = w->d_opts.reserve(nq);
+        if (e == cudaSuccess) e = w->d_ids.reserve(nq * (uint64_t)k_stride + 1);
+        if (e == cudaSuccess) e = w->d_scores.reserve(nq * (uint64_t)k_stride + 1);
+        if (e == cudaSuccess) e = w->d_counts.reserve(nq);
+        if (e != cudaSuccess) {
+            rc = cuda_fail(e, "staging buffers");
+            break;
+        }
+        {
+            Timed t(ctx, st, KK_H2D);
+            if (nt) cudaMemcpyAsync(w->d_terms.p, terms + t0, nt * 4, cudaMemcpyHostToDevice, st);
+            cudaMemcpyAsync(w->d_offsets.p, term_offsets + q0, (nq + 1) * 8, cudaMemcpyHostToDevice, st);
+            cudaMemcpyAsync(w->d_opts.p, opts + q0, nq * sizeof(SearchOpts), cudaMemcpyHostToDevice, st);
+        }
+        rc = enqueue_batch(s, w, st, nq, nt, w->d_terms.p, w->d_offsets.p, t0, w->d_opts.p, k_stride, w->d_ids.p,
+                           w->d_scores.p, w->d_counts.p);
+        if (rc != FPX_OK) break;
+        {
+            Timed t(ctx, st, KK_D2H);
+            if (k_stride) {
+                cudaMemcpyAsync(out_ids + q0 * k_stride, w->d_ids.p, nq * (uint64_t)k_stride * 4, cudaMemcpyDeviceToHost, st);
+                cudaMemcpyAsync(out_scores + q0 * k_stride, w->d_scores.p, nq * (uint64_t)k_stride * 4, cudaMemcpyDeviceToHost, st);
+            }
+            cudaMemcpyAsync(out_counts + q0, w->d_counts.p, nq * 4, cudaMemcpyDeviceToHost, st);
+        }
+        if (ctx->flags & FPX_FLAG_PROFILE) {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            ctx->prof.h2d_bytes += nt * 4 + (nq + 1) * 8 + nq * sizeof(SearchOpts);
+            ctx->prof.d2h_bytes += nq * (uint64_t)k_stride * 8 + nq * 4;
+        }
+    }
+    uint32_t dev_err = 0;
+    for (int i = 0; i < n_ws; ++i)
+        if (ws[i]) {
+            cudaError_t e = cudaStreamSynchronize(ws[i]->stream);
+            if (e != cudaSuccess && rc == FPX_OK) rc = cuda_fail(e, "search batch");
+            dev_err |= *ws[i]->h_error;
+            release_workspace(ctx, ws[i]);
+        }
+    if (rc == FPX_OK && dev_err) rc = set_error((fpx_status)dev_err, "a query in the batch is outside the device path's limits");
+    return rc;
+}
+
+fpx_status fpx_search(fpx_snapshot *s, const uint32_t *terms, uint64_t n_terms, const fpx_search_opts *opts,
+                      uint32_t *out_ids, uint32_t *out_scores, uint32_t capacity, uint32_t *out_count) {
+    if (!opts || !out_count) return set_error(FPX_INVALID_ARGUMENT, "null argument");
+    uint64_t offs[2] = {0, n_terms};
+    uint32_t cap = std::min<uint32_t>(capacity, FPX_MAX_RESULTS);
+    if (opts->max_results > cap && capacity > FPX_MAX_RESULTS)
+        return set_error(FPX_UNSUPPORTED, "max_results exceeds FPX_MAX_RESULTS");
+    *out_count = 0;
+    return fpx_search_batch(s, 1, terms, offs, opts, cap, out_ids, out_scores, out_count);
+}
+
+fpx_status fpx_merge_shard_results(uint32_t n_shards, uint64_t n_queries, uint32_t k_stride, const uint32_t *ids,
+                                   const uint32_t *scores, const uint32_t *counts, const fpx_search_opts *opts,
+                                   uint32_t *out_ids, uint32_t *out_scores, uint32_t *out_counts) {
+    if (!n_shards || !counts || !opts || !out_counts) return set_error(FPX_INVALID_ARGUMENT, "null argument");
+    std::vector<unsigned long long> keys;
+    for (uint64_t q = 0; q < n_queries; ++q) {
+        keys.clear();
+        for (uint32_t g = 0; g < n_shards; ++g) {
+            const size_t base = ((size_t)g * n_queries + q) * k_stride;
+            const uint32_t n = std::min(counts[(size_t)g * n_queries + q], k_stride);
+            for (uint32_t i = 0; i < n; ++i)
+                keys.push_back(((unsigned long long)(0xFFFFFFFFu - scores[base + i]) << 32) | ids[base + i]);
+        }
+        std::sort(keys.begin(), keys.end());
+        const uint32_t k_eff = std::min(opts[q].max_results, k_stride);
+        uint32_t ms = opts[q].min_score, n_out = 0;
+        for (size_t i = 0; i < keys.size() && n_out < k_eff; ++i) {
+            const uint32_t score = 0xFFFFFFFFu - (uint32_t)(keys[i] >> 32);
+            if (score < ms) break;
+            if (n_out == 0) ms = std::max(ms, (uint32_t)(score * opts[q].min_score_pct) / 100u);
+            out_ids[q * k_stride + n_out] = (uint32_t)keys[i];
+            out_scores[q * k_stride + n_out] = score;
+            ++n_out;
+        }
+        out_counts[q] = n_out;
+    }
+    return FPX_OK;
+}
+
+fpx_status fpx_profile_reset(fpx_ctx *ctx) {
+    if (!ctx) return set_error(FPX_INVALID_ARGUMENT, "null ctx");
+    if (!ctx->host_only) {
+        FPX_CUDA(cudaSetDevice(ctx->device));
+        FPX_CUDA(cudaDeviceSynchronize());
+        FPX_CUDA(cudaMemset(ctx->d_stats, 0, sizeof(DeviceStats)));
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (auto &p : ctx->pending) {
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    ctx->pending.clear();
+    ctx->prof = fpx_profile{};
+    return FPX_OK;
+}
+
+fpx_status fpx_profile_read(fpx_ctx *ctx, fpx_profile *out) {
+    if (!ctx || !out) return set_error(FPX_INVALID_ARGUMENT, "null argument");
+    if (!ctx->host_only) {
+        FPX_CUDA(cudaSetDevice(ctx->device));
+        FPX_CUDA(cudaDeviceSynchronize());
+        std::vector<EventPair> ev;
+        {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            ev.swap(ctx->pending);
+        }
+        for (auto &p : ev) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, p.a, p.b);
+            switch (p.kind) {
+            case KK_PREPARE: ctx->prof.prepare_ms += ms; ctx->prof.prepare_launches += 2; break;
+            case KK_SEARCH: ctx->prof.search_ms += ms; ctx->prof.search_launches += 3; break;
+            case KK_WIDE: ctx->prof.wide_ms += ms; ctx->prof.wide_launches += 1; break;
+            case KK_H2D: ctx->prof.h2d_ms += ms; break;
+            case KK_D2H: ctx->prof.d2h_ms += ms; break;
+            }
+            cudaEventDestroy(p.a);
+            cudaEventDestroy(p.b);
+        }
+        DeviceStats ds{};
+        FPX_CUDA(cudaMemcpy(&ds, ctx->d_stats, sizeof ds, cudaMemcpyDeviceToHost));
+        ctx->prof.queries = ds.queries;
+        ctx->prof.unique_terms = ds.unique_terms;
+        ctx->prof.postings = ds.postings;
+        ctx->prof.results = ds.results;
+        ctx->prof.wide_queries = ds.wide_queries;
+    }
+    *out = ctx->prof;
+    return FPX_OK;
+}
+
+} // extern "C"

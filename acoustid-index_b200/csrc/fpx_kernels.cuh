@@ -1,0 +1,89 @@
+// fpx_kernels.cuh — device-side data structures shared by the kernels and the host API.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace fpx {
+
+// Term directory entry (open addressing, linear probing, 16 bytes = one 128-bit load).
+struct TermEntry {
+    uint32_t term;
+    uint32_t len;    // postings in the row (> 0)
+    uint32_t start4; // row start in units of 4 docids (16 bytes)
+    uint32_t used;   // 0 = empty slot
+};
+
+struct SnapshotDev {
+    const TermEntry *table;
+    uint32_t table_mask;
+    uint32_t table_shift; // 32 - log2(capacity)
+    const uint32_t *docids; // padded rows
+    uint32_t pad_id;
+};
+
+struct QueryInfo {
+    uint32_t n_rows;    // unique terms present in the snapshot
+    uint32_t postings;  // sum of row lengths (saturating)
+    uint32_t passes;    // hash partitions needed by the shared-memory path
+    uint32_t reserved;
+};
+
+struct SearchOpts { // == fpx_search_opts
+    uint32_t max_results, min_score, min_score_pct;
+};
+
+// Work classes: shared-memory count table of 2^13 / 2^14 / 2^15 slots, and the global-memory path.
+constexpr int kNumClasses = 4;
+constexpr int kWideClass = 3;
+constexpr uint32_t kClassLog[3] = {13, 14, 15};
+
+struct BatchCounters {
+    uint32_t qcount[kNumClasses];
+    uint32_t qhead[kNumClasses];
+    uint32_t long_count;
+    uint32_t long_head;
+    uint32_t error; // FPX_UNSUPPORTED etc. raised on device
+    uint32_t pad;
+};
+
+struct DeviceStats { // accumulated across batches (profiling)
+    unsigned long long queries, unique_terms, postings, results, wide_queries, overflow_requeues;
+};
+
+struct BatchArgs {
+    SnapshotDev snap;
+    uint32_t n_queries;
+    uint32_t k_stride;
+    const uint32_t *terms;
+    const uint64_t *term_offsets;
+    uint64_t term_base; // subtracted from term_offsets (chunked host batches)
+    const SearchOpts *opts;
+    uint32_t *out_ids, *out_scores, *out_counts;
+    // workspace
+    uint2 *rows;            // per query at [term_offsets[q]-term_base ...): {start4, len}
+    QueryInfo *qinfo;
+    uint32_t *queues;       // kNumClasses * n_queries
+    uint32_t *long_queue;   // n_queries
+    BatchCounters *counters;
+    DeviceStats *stats;
+    unsigned long long *wide_tables; // per wide CTA: wide_cap 64-bit slots
+    uint32_t wide_cap_log2;
+};
+
+constexpr uint32_t kWarpQueryTerms = 128; // queries up to this many raw terms are prepared by one warp
+constexpr uint32_t kMaxQueryTerms = 8192; // FPX_MAX_QUERY_TERMS
+constexpr uint32_t kFastKbuf = 512;       // candidate buffer of the shared-memory path
+constexpr uint32_t kWideKbuf = 2048;      // candidate buffer of the global-memory path
+constexpr uint32_t kMaxResults = 1024;    // FPX_MAX_RESULTS
+constexpr uint32_t kRowsChunk = 256;      // row descriptors staged per round
+
+void launch_build_table(TermEntry *table, uint32_t log2cap, const uint32_t *terms, const uint32_t *lens,
+                        const uint32_t *start4, uint64_t n_terms, cudaStream_t st);
+void launch_prepare(const BatchArgs &a, cudaStream_t st);
+void launch_prepare_long(const BatchArgs &a, cudaStream_t st, int n_sms);
+void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms);
+void launch_search_wide(const BatchArgs &a, cudaStream_t st, int n_ctas);
+cudaError_t configure_kernels();
+int wide_ctas(int n_sms);
+
+} // namespace fpx

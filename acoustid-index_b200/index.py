@@ -1,0 +1,307 @@
+"""Host-side mirror of the reference's interface for the `_search` path, over the C ABI.
+
+Names and argument meaning follow the reference (paths relative to the reference root):
+  SearchOptions / SearchResult      src/common.zig:45-54
+  SearchRequest                     src/api.zig:14-27
+  FileSegment / MemorySegment       src/FileSegment.zig:33-53, src/MemorySegment.zig:21-28 (data only)
+  Index.swap_snapshot               src/Index.zig:469-485   -> builds an immutable GPU snapshot
+  IndexReader.search                src/Index.zig:170-177 + src/common.zig:131-167 (finish)
+  multi_index_search                src/MultiIndex.zig:287-330 option mapping (+ server.zig:192 clamp)
+
+Everything here is plumbing around libfpx.so; no search arithmetic happens in Python.
+"""
+import ctypes as C
+from typing import List, NamedTuple, Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import FpxError, check, lib
+
+# src/api.zig:7-11
+default_search_timeout = 500
+max_search_timeout = 10000
+default_search_limit = 40
+min_search_limit = 1
+max_search_limit = 100
+
+
+class SearchResult(NamedTuple):
+    id: int
+    score: int
+
+
+class SearchOptions(NamedTuple):  # common.zig:50-54
+    max_results: int = 10
+    min_score: int = 1
+    min_score_pct: int = 10
+
+
+class SearchRequest:  # api.zig:14-27
+    def __init__(self, query, timeout=default_search_timeout, limit=default_search_limit, min_score=None,
+                 score_pct=10):
+        self.query = list(query)
+        self.timeout = timeout
+        self.limit = limit
+        self.min_score = min_score
+        self.score_pct = score_pct
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+class FileSegment:
+    """An immutable block-compressed segment resident in host memory (FileSegment.zig:33-53)."""
+
+    def __init__(self, commit_id, merges, min_doc_id, block_size, blocks, num_blocks, block_index, doc_ids, doc_alive,
+                 _owner=None):
+        self.commit_id, self.merges = int(commit_id), int(merges)
+        self.min_doc_id, self.block_size = int(min_doc_id), int(block_size)
+        self.blocks, self.num_blocks, self.block_index = blocks, int(num_blocks), block_index
+        self.doc_ids, self.doc_alive = _u32(doc_ids), np.ascontiguousarray(doc_alive, dtype=np.uint8)
+        self._owner = _owner
+
+    @staticmethod
+    def from_items(items, doc_ids, doc_alive, commit_id, merges=0, block_size=512, threads=0):
+        """Write sorted packed items ((hash<<32)|id) as blocks: filefmt.zig:94-138 via fpx_segment_write."""
+        items = np.ascontiguousarray(items, dtype=np.uint64)
+        doc_ids = _u32(doc_ids)
+        min_doc_id = int(doc_ids.min()) if len(doc_ids) else 0  # filefmt.zig:244-250
+        buf = C.c_void_p()
+        check(lib().fpx_segment_write(items.ctypes.data, len(items), min_doc_id, block_size, threads, C.byref(buf)))
+        owner = _SegmentBuf(buf)
+        nb = lib().fpx_segment_buf_num_blocks(buf)
+        bs = lib().fpx_segment_buf_block_size(buf)
+        blocks = np.ctypeslib.as_array(C.cast(lib().fpx_segment_buf_blocks(buf), _ffi.u8p), shape=((nb + 1) * bs,))
+        if nb:
+            index = np.ctypeslib.as_array(C.cast(lib().fpx_segment_buf_block_index(buf), _ffi.u32p), shape=(nb,))
+        else:
+            index = np.zeros(0, dtype=np.uint32)
+        assert lib().fpx_segment_buf_num_items(buf) == len(items)
+        return FileSegment(commit_id, merges, min_doc_id, bs, blocks, nb, index, doc_ids, doc_alive, _owner=owner)
+
+    def _desc(self):
+        d = _ffi.FileSegmentDesc()
+        d.commit_id, d.merges = self.commit_id, self.merges
+        d.min_doc_id, d.block_size = self.min_doc_id, self.block_size
+        d.blocks = self.blocks.ctypes.data if self.num_blocks else None
+        d.num_blocks = self.num_blocks
+        d.block_index = self.block_index.ctypes.data if self.num_blocks else None
+        d.doc_ids = self.doc_ids.ctypes.data if len(self.doc_ids) else None
+        d.doc_alive = self.doc_alive.ctypes.data if len(self.doc_alive) else None
+        d.n_docs = len(self.doc_ids)
+        return d
+
+
+class _SegmentBuf:
+    def __init__(self, h):
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().fpx_segment_buf_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class MemorySegment:
+    """Sorted packed items + docs map of an in-memory segment (MemorySegment.zig:21-28)."""
+
+    def __init__(self, commit_id, merges, items, doc_ids, doc_alive):
+        self.commit_id, self.merges = int(commit_id), int(merges)
+        self.items = np.ascontiguousarray(items, dtype=np.uint64)
+        self.doc_ids, self.doc_alive = _u32(doc_ids), np.ascontiguousarray(doc_alive, dtype=np.uint8)
+
+    def _desc(self):
+        d = _ffi.MemorySegmentDesc()
+        d.commit_id, d.merges = self.commit_id, self.merges
+        d.items = self.items.ctypes.data if len(self.items) else None
+        d.n_items = len(self.items)
+        d.doc_ids = self.doc_ids.ctypes.data if len(self.doc_ids) else None
+        d.doc_alive = self.doc_alive.ctypes.data if len(self.doc_alive) else None
+        d.n_docs = len(self.doc_ids)
+        return d
+
+
+class Context:
+    def __init__(self, device=-1, profile=False, host_only=False, host_threads=0, chunk_queries=0):
+        cfg = _ffi.Config(device, host_threads, chunk_queries,
+                          (_ffi.FPX_FLAG_PROFILE if profile else 0) | (_ffi.FPX_FLAG_HOST_ONLY if host_only else 0))
+        self.h = C.c_void_p()
+        check(lib().fpx_init(C.byref(cfg), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().fpx_shutdown(self.h)
+            self.h = None
+
+    def profile_reset(self):
+        check(lib().fpx_profile_reset(self.h))
+
+    def profile(self):
+        p = _ffi.Profile()
+        check(lib().fpx_profile_read(self.h, C.byref(p)))
+        return {k: getattr(p, k) for k, _ in _ffi.Profile._fields_}
+
+
+class SnapshotBuilder:
+    """Index.swapSnapshot hook: segments oldest -> newest, file before memory (Index.zig:33-41)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        check(lib().fpx_snapshot_begin(ctx.h, C.byref(self.h)))
+
+    def add_file_segment(self, seg: FileSegment):
+        d = seg._desc()
+        check(lib().fpx_snapshot_add_file_segment(self.h, C.byref(d)))
+
+    def add_memory_segment(self, seg: MemorySegment):
+        d = seg._desc()
+        check(lib().fpx_snapshot_add_memory_segment(self.h, C.byref(d)))
+
+    def set_doc_range(self, lo, hi):
+        check(lib().fpx_snapshot_set_doc_range(self.h, lo, hi))
+
+    def csr(self):
+        """Host view of the compiled CSR as numpy copies: (terms, row_offsets, docids)."""
+        v = _ffi.CsrView()
+        check(lib().fpx_snapshot_csr(self.h, C.byref(v)))
+        n = v.n_terms
+        if n == 0:
+            return np.zeros(0, np.uint32), np.zeros(1, np.uint64), np.zeros(0, np.uint32)
+        terms = np.ctypeslib.as_array(v.terms, shape=(n,)).copy()
+        offs = np.ctypeslib.as_array(v.row_offsets, shape=(n + 1,)).copy()
+        total = int(offs[-1])
+        docids = np.ctypeslib.as_array(v.docids, shape=(total,)).copy() if total else np.zeros(0, np.uint32)
+        return terms, offs, docids
+
+    def commit(self):
+        s = C.c_void_p()
+        check(lib().fpx_snapshot_commit(self.h, C.byref(s)))
+        self.h = None
+        return Snapshot(self.ctx, s)
+
+    def abort(self):
+        if self.h:
+            lib().fpx_snapshot_abort(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.abort()
+        except Exception:
+            pass
+
+
+class Snapshot:
+    """Immutable, refcounted GPU mirror of a Segments snapshot (Index.zig:36-63)."""
+
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    def info(self):
+        i = _ffi.SnapshotInfo()
+        check(lib().fpx_snapshot_get_info(self.h, C.byref(i)))
+        return {k: getattr(i, k) for k, _ in _ffi.SnapshotInfo._fields_}
+
+    def row_lengths(self, terms):
+        terms = _u32(terms)
+        out = np.zeros(len(terms), dtype=np.uint32)
+        if len(terms):
+            check(lib().fpx_snapshot_row_lengths(self.h, terms.ctypes.data, len(terms), out.ctypes.data))
+        return out
+
+    def acquire(self):
+        check(lib().fpx_snapshot_acquire(self.h))
+
+    def release(self):
+        if self.h:
+            check(lib().fpx_snapshot_release(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+def swap_snapshot(ctx: Context, file_segments: Sequence[FileSegment], memory_segments: Sequence[MemorySegment] = (),
+                  doc_range=None) -> Snapshot:
+    """What a host would do inside Index.swapSnapshot (Index.zig:469-485): mirror the new Segments in HBM."""
+    b = SnapshotBuilder(ctx)
+    for s in file_segments:
+        b.add_file_segment(s)
+    for s in memory_segments:
+        b.add_memory_segment(s)
+    if doc_range is not None:
+        b.set_doc_range(*doc_range)
+    return b.commit()
+
+
+class IndexReader:
+    """A held snapshot; search works on it without any lock (Index.zig:152-177)."""
+
+    def __init__(self, snapshot: Snapshot):
+        self.snapshot = snapshot
+
+    def search(self, hashes, options: SearchOptions = SearchOptions()) -> List[SearchResult]:
+        q = _u32([int(x) & 0xFFFFFFFF for x in hashes])
+        opts = np.array([options.max_results, options.min_score, options.min_score_pct], dtype=np.uint32)
+        cap = max(1, min(int(options.max_results), _ffi.FPX_MAX_RESULTS))
+        ids = np.zeros(cap, dtype=np.uint32)
+        sc = np.zeros(cap, dtype=np.uint32)
+        n = C.c_uint32(0)
+        check(lib().fpx_search(self.snapshot.h, q.ctypes.data if len(q) else None, len(q), opts.ctypes.data,
+                               ids.ctypes.data, sc.ctypes.data, cap, C.byref(n)))
+        return [SearchResult(int(ids[i]), int(sc[i])) for i in range(n.value)]
+
+    def search_batch(self, terms, term_offsets, opts, k_stride, out=None):
+        """Host buffers (numpy; pinned torch memory can be passed via .numpy()).  Returns (ids, scores, counts)."""
+        terms = _u32(terms)
+        term_offsets = np.ascontiguousarray(term_offsets, dtype=np.uint64)
+        opts = _u32(opts)
+        nq = len(term_offsets) - 1
+        assert opts.size == 3 * nq
+        if out is None:
+            out = (np.zeros((nq, k_stride), np.uint32), np.zeros((nq, k_stride), np.uint32), np.zeros(nq, np.uint32))
+        ids, sc, cnt = out
+        check(lib().fpx_search_batch(self.snapshot.h, nq, terms.ctypes.data if len(terms) else None,
+                                     term_offsets.ctypes.data, opts.ctypes.data, k_stride, ids.ctypes.data,
+                                     sc.ctypes.data, cnt.ctypes.data))
+        return ids, sc, cnt
+
+    def search_batch_ptr(self, nq, terms_ptr, offsets_ptr, opts_ptr, k_stride, ids_ptr, scores_ptr, counts_ptr):
+        """Raw host pointers (e.g. pinned torch tensors' data_ptr())."""
+        check(lib().fpx_search_batch(self.snapshot.h, nq, terms_ptr, offsets_ptr, opts_ptr, k_stride, ids_ptr,
+                                     scores_ptr, counts_ptr))
+
+    def search_batch_device(self, nq, d_terms, d_offsets, d_opts, k_stride, d_ids, d_scores, d_counts, stream=0):
+        """Device pointers (ints), asynchronous on `stream` (a cudaStream_t handle as int)."""
+        check(lib().fpx_search_batch_device(self.snapshot.h, nq, d_terms, d_offsets, d_opts, k_stride, d_ids, d_scores,
+                                            d_counts, stream))
+
+
+def multi_index_search(reader: IndexReader, request: SearchRequest, clamp_http=True) -> List[SearchResult]:
+    """MultiIndex.search option mapping (MultiIndex.zig:302-306); clamp_http applies server.zig:192-193."""
+    limit = request.limit
+    if clamp_http:
+        limit = max(min(limit, max_search_limit), min_search_limit)
+    min_score = request.min_score
+    if min_score is None:
+        min_score = lib().fpx_default_min_score(len(request.query))  # RAW length, before de-duplication
+    return reader.search(request.query, SearchOptions(limit, min_score, request.score_pct))
+
+
+def merge_shard_results(ids, scores, counts, opts, k_stride):
+    """ids/scores: [n_shards, nq, k_stride]; counts: [n_shards, nq]; opts: [nq, 3] -> merged (ids, scores, counts)."""
+    ids, scores, counts, opts = _u32(ids), _u32(scores), _u32(counts), _u32(opts)
+    g, nq = counts.shape
+    out = (np.zeros((nq, k_stride), np.uint32), np.zeros((nq, k_stride), np.uint32), np.zeros(nq, np.uint32))
+    check(lib().fpx_merge_shard_results(g, nq, k_stride, ids.ctypes.data, scores.ctypes.data, counts.ctypes.data,
+                                        opts.ctypes.data, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data))
+    return out

@@ -1,0 +1,198 @@
+/*
+ * fpx.h — C ABI of the B200-native `_search` path for acoustid-index (fpindex).
+ *
+ * This is the drop-in boundary.  The reference (Zig) has no FFI; the seams this ABI is
+ * designed to be bound at are (paths relative to the reference root):
+ *
+ *   - src/Index.zig:469-485  Index.swapSnapshot        -> fpx_snapshot_begin / add_..._segment / commit
+ *   - src/Index.zig:57-63    Segments.deinit           -> fpx_snapshot_release
+ *   - src/Index.zig:430-434  Index.acquireReader       -> fpx_snapshot_acquire
+ *   - src/Index.zig:170-177  IndexReader.search  }
+ *   - src/common.zig:131-167 SearchResults.finish }    -> fpx_search / fpx_search_batch
+ *   - src/MultiIndex.zig:302-306 option mapping        -> fpx_default_min_score
+ *
+ * INTEGRATION.md shows the Zig `extern fn` stub for each entry point.
+ *
+ * Conventions: plain pointers and sizes, no exceptions cross the boundary, every function
+ * returns an fpx_status; fpx_last_error_message() gives a thread-local description of the
+ * last failure on the calling thread.  All input buffers are borrowed for the duration of
+ * the call only.  Handles are opaque; snapshots are immutable and atomically refcounted, so
+ * fpx_search* may be called concurrently from many threads on one snapshot while another
+ * thread commits a newer one (mirrors the reference's lock-free readers, MultiIndex.zig:5-10).
+ */
+#ifndef FPX_H
+#define FPX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPX_ABI_VERSION 1u
+
+typedef int32_t fpx_status;
+enum {
+    FPX_OK = 0,
+    FPX_OUT_OF_MEMORY = 1,
+    FPX_INVALID_ARGUMENT = 2,
+    FPX_INVALID_SEGMENT = 3,     /* error.InvalidSegment / ChecksumMismatch, filefmt.zig:235-284 */
+    FPX_TIMEOUT = 4,             /* error.SearchTimeout, MultiIndex.zig:320 */
+    FPX_CUDA_ERROR = 5,
+    FPX_BACKEND_UNAVAILABLE = 6, /* no CUDA device / driver: the caller keeps its CPU path */
+    FPX_UNSUPPORTED = 7          /* query outside the documented limits below */
+};
+
+/* Documented limits of the device path (callers keep the CPU path beyond). */
+#define FPX_MAX_QUERY_TERMS 8192u /* raw terms per query */
+#define FPX_MAX_RESULTS 1024u     /* effective per-query limit = min(max_results, k_stride) */
+
+typedef struct fpx_ctx fpx_ctx;
+typedef struct fpx_snapshot_builder fpx_snapshot_builder;
+typedef struct fpx_snapshot fpx_snapshot;
+
+typedef struct fpx_config {
+    int32_t device;            /* CUDA device ordinal; -1 = current device */
+    uint32_t host_threads;     /* threads for snapshot compilation; 0 = hardware concurrency */
+    uint32_t chunk_queries;    /* queries per pipelined H2D/compute/D2H chunk in fpx_search_batch; 0 = default */
+    uint32_t flags;            /* FPX_FLAG_* */
+} fpx_config;
+#define FPX_FLAG_PROFILE 1u    /* record CUDA events around every kernel (fpx_profile_read) */
+#define FPX_FLAG_HOST_ONLY 2u  /* no device: only snapshot compilation / introspection work (CPU tests) */
+
+/* An immutable file segment exactly as FileSegment holds it in RAM (FileSegment.zig:33-53). */
+typedef struct fpx_file_segment {
+    uint64_t commit_id;          /* SegmentInfo.commit_id (segment.zig:23-26) */
+    uint64_t merges;             /* SegmentInfo.merges */
+    uint32_t min_doc_id;         /* FileSegment.min_doc_id: the docid delta base (block.zig:68) */
+    uint32_t block_size;         /* FileSegment.block_size, 64..4096 (block.zig:41-42) */
+    const uint8_t *blocks;       /* FileSegment.blocks: num_blocks*block_size bytes */
+    uint64_t num_blocks;         /* FileSegment.num_blocks (terminator block excluded) */
+    const uint32_t *block_index; /* FileSegment.block_index: max hash per block (filefmt.zig:117) */
+    const uint32_t *doc_ids;     /* keys of FileSegment.docs (any order) */
+    const uint8_t *doc_alive;    /* values of FileSegment.docs: 1 insert, 0 tombstone */
+    uint64_t n_docs;
+} fpx_file_segment;
+
+/* A memory segment as MemorySegment holds it (MemorySegment.zig:21-28). */
+typedef struct fpx_memory_segment {
+    uint64_t commit_id;
+    uint64_t merges;
+    const uint64_t *items; /* MemorySegment.items: packed Item = (hash<<32)|id, ascending (segment.zig:87-106) */
+    uint64_t n_items;
+    const uint32_t *doc_ids;
+    const uint8_t *doc_alive;
+    uint64_t n_docs;
+} fpx_memory_segment;
+
+/* common.zig:50-54 SearchOptions (already resolved: see fpx_default_min_score). */
+typedef struct fpx_search_opts {
+    uint32_t max_results;
+    uint32_t min_score;
+    uint32_t min_score_pct;
+} fpx_search_opts;
+
+typedef struct fpx_snapshot_info {
+    uint64_t n_segments;
+    uint64_t n_terms;            /* CSR rows */
+    uint64_t n_postings;         /* live, reachable postings kept */
+    uint64_t n_postings_total;   /* postings seen in the input segments */
+    uint64_t n_dropped_unreachable; /* cut by the 4-block / >1000-doc scan caps (FileSegment.zig:173-174) */
+    uint64_t n_dropped_superseded;  /* newer segment mentions the id (Index.zig:133-149) */
+    uint64_t n_dropped_out_of_range;/* outside this shard's docid range */
+    uint64_t device_bytes;       /* HBM held by this snapshot */
+    uint64_t max_row_len;
+    uint32_t pad_id;             /* docid value used to pad rows to 16 bytes (not a live id) */
+    uint32_t table_log2;         /* log2 of the term hash table capacity */
+    uint32_t doc_lo, doc_hi;     /* docid range [lo, hi) of this shard (0, 0 = everything) */
+} fpx_snapshot_info;
+
+/* Host view of the compiled CSR (debug / tests; valid until the builder is committed or aborted). */
+typedef struct fpx_csr_view {
+    uint64_t n_terms;
+    const uint32_t *terms;       /* ascending, unique */
+    const uint64_t *row_offsets; /* n_terms+1, in docids (unpadded, dense) */
+    const uint32_t *docids;      /* row r = docids[row_offsets[r] .. row_offsets[r+1]), ascending */
+} fpx_csr_view;
+
+typedef struct fpx_profile {
+    /* accumulated since the last fpx_profile_reset, FPX_FLAG_PROFILE only */
+    double prepare_ms;  uint64_t prepare_launches;
+    double search_ms;   uint64_t search_launches;   /* the gather+count+top-k kernel(s) */
+    double wide_ms;     uint64_t wide_launches;     /* overflow / oversized queries */
+    double h2d_ms, d2h_ms;
+    uint64_t queries, unique_terms, postings, results, wide_queries;
+    uint64_t h2d_bytes, d2h_bytes;
+} fpx_profile;
+
+/* ---- lifecycle ---- */
+uint32_t fpx_abi_version(void);
+const char *fpx_last_error_message(void);
+fpx_status fpx_init(const fpx_config *config /* may be NULL */, fpx_ctx **out);
+void fpx_shutdown(fpx_ctx *ctx);
+
+/* ---- snapshot build: called where Index.swapSnapshot installs a new Segments ---- */
+fpx_status fpx_snapshot_begin(fpx_ctx *ctx, fpx_snapshot_builder **out);
+/* Segments must be added oldest -> newest, all file segments before all memory segments
+ * (Index.zig:33-41).  Input is fully consumed (decoded) during the call. */
+fpx_status fpx_snapshot_add_file_segment(fpx_snapshot_builder *b, const fpx_file_segment *seg);
+fpx_status fpx_snapshot_add_memory_segment(fpx_snapshot_builder *b, const fpx_memory_segment *seg);
+/* Restrict the snapshot to docids in [lo, hi) (multi-GPU docid-range sharding).  The scan caps and
+ * supersession rules are applied on the whole snapshot first, so shards union to the full result. */
+fpx_status fpx_snapshot_set_doc_range(fpx_snapshot_builder *b, uint32_t lo, uint32_t hi);
+/* Compile to CSR on the host (idempotent; commit calls it if needed). */
+fpx_status fpx_snapshot_compile(fpx_snapshot_builder *b);
+fpx_status fpx_snapshot_csr(fpx_snapshot_builder *b, fpx_csr_view *out);
+/* Upload to HBM; consumes the builder on success.  refcount starts at 1. */
+fpx_status fpx_snapshot_commit(fpx_snapshot_builder *b, fpx_snapshot **out);
+void fpx_snapshot_abort(fpx_snapshot_builder *b);
+
+fpx_status fpx_snapshot_acquire(fpx_snapshot *s);
+fpx_status fpx_snapshot_release(fpx_snapshot *s);
+fpx_status fpx_snapshot_get_info(const fpx_snapshot *s, fpx_snapshot_info *out);
+/* Row length of each term (0 if absent) from the host-side copy of the term directory. */
+fpx_status fpx_snapshot_row_lengths(const fpx_snapshot *s, const uint32_t *terms, uint64_t n,
+                                    uint32_t *out_lengths);
+
+/* ---- search: called where IndexReader.search + SearchResults.finish are ---- */
+/* MultiIndex.zig:304: min_score = (raw query length + 19) / 20 when the request has none. */
+uint32_t fpx_default_min_score(uint64_t raw_query_len);
+
+/* One query (IndexReader.search + finish).  `terms` is NOT modified (the reference sorts in place). */
+fpx_status fpx_search(fpx_snapshot *s, const uint32_t *terms, uint64_t n_terms,
+                      const fpx_search_opts *opts, uint32_t *out_ids, uint32_t *out_scores,
+                      uint32_t capacity, uint32_t *out_count);
+
+/* A batch of independent queries; host buffers.  Query q = terms[term_offsets[q] .. term_offsets[q+1]).
+ * Results of query q go to out_ids/out_scores[q*k_stride ...], count to out_counts[q]; at most
+ * min(opts[q].max_results, k_stride) results per query (a prefix of the reference's list). */
+fpx_status fpx_search_batch(fpx_snapshot *s, uint64_t n_queries, const uint32_t *terms,
+                            const uint64_t *term_offsets, const fpx_search_opts *opts,
+                            uint32_t k_stride, uint32_t *out_ids, uint32_t *out_scores,
+                            uint32_t *out_counts);
+
+/* Same, all buffers already in device memory, enqueued on `cuda_stream` (a cudaStream_t; NULL = the
+ * legacy default stream).  Asynchronous: results are ready when the stream reaches this point. */
+fpx_status fpx_search_batch_device(fpx_snapshot *s, uint64_t n_queries, const uint32_t *d_terms,
+                                   const uint64_t *d_term_offsets, const fpx_search_opts *d_opts,
+                                   uint32_t k_stride, uint32_t *d_out_ids, uint32_t *d_out_scores,
+                                   uint32_t *d_out_counts, void *cuda_stream);
+
+/* Merge per-shard top-k lists (docid-range sharded corpus): for each query take the global best
+ * min(max_results, k_stride) under (score desc, id asc), then apply the relative cutoff anchored on the
+ * global best (common.zig:153-166).  Shards must have been searched with min_score_pct = 0.
+ * Host buffers; shard g's lists at ids[g*n_queries*k_stride ...]. */
+fpx_status fpx_merge_shard_results(uint32_t n_shards, uint64_t n_queries, uint32_t k_stride,
+                                   const uint32_t *ids, const uint32_t *scores, const uint32_t *counts,
+                                   const fpx_search_opts *opts, uint32_t *out_ids, uint32_t *out_scores,
+                                   uint32_t *out_counts);
+
+/* ---- profiling ---- */
+fpx_status fpx_profile_reset(fpx_ctx *ctx);
+fpx_status fpx_profile_read(fpx_ctx *ctx, fpx_profile *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPX_H */
