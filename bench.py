@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — queries/sec of the batched `_search` path on synthetic fingerprint corpora.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl fpx|reference] [--workload c3|c2|c5|tiny]
+
+One step = one pass of the hot path over one batch of synthetic queries.  Workload c3 (default) is the
+configuration BASELINE.json's metric is quoted on: 10 M fingerprints x 120 hashes, 100 K-query batch of
+100-term queries, HTTP default options (limit 40, min_score (T+19)/20, score_pct 10).
+
+  value     whole-job queries/s with the batch already resident in HBM (fpx_search_batch_device), CUDA-event
+            timed over exactly K steps, max over ranks
+  e2e       the same batch through the host-buffer C-ABI call fpx_search_batch (pinned host memory; H2D of the
+            queries and D2H of the results inside the timed region)
+  roofline  the dominant kernel (search_smem_kernel: gather + count + top-k) — algorithmic bytes / its
+            CUDA-event time, against the measured HBM peak in MEASURED_PEAKS.json
+  cpu_baseline  the C++ restatement of the reference CPU path (oracle/), all host threads, bounded sample
+
+N > 1: one process per GPU (torchrun), corpus replicated, each rank answers its own batch (weak scaling);
+the only collective is an NCCL all-gather of the per-query result lists.
+`--impl reference` times the CPU restatement alone (the Zig reference cannot be built here: no zig, no network).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_docs, hashes/doc, vocab_log2, zipf_s, n_queries, terms/query, corpus seed, query seed)
+    "tiny": (50_000, 60, 16, 0.0, 4096, 100, 0xF1D00001, 0xF1D01001),
+    "c2": (1_000_000, 100, 20, 0.0, 10_000, 100, 0xF1D00001 + 2, 0xF1D01001 + 2),
+    "c3": (10_000_000, 120, 24, 0.0, 100_000, 100, 0xF1D00001 + 3, 0xF1D01001 + 3),
+    "c5": (10_000_000, 120, 20, 1.0, 100_000, 100, 0xF1D00001 + 5, 0xF1D01001 + 5),
+}
+K_STRIDE = 40
+METRIC = "queries/sec at 10M fingerprints, 100-term queries"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_corpus(pkg, wl, device):
+    n_docs, H, vlog, zipf, *_ = WORKLOADS[wl]
+    cfg = pkg.synth.SynthConfig(n_docs=n_docs, hashes_per_doc=H, vocab_log2=vlog, seed=WORKLOADS[wl][6], zipf_s=zipf)
+    syn = pkg.synth.Synth(cfg, device=device)
+    t = time.time()
+    items, doc_ids, doc_alive = syn.corpus_items()
+    log("[bench] corpus: %d postings generated+sorted in %.1fs" % (len(items), time.time() - t))
+    return syn, items, doc_ids, doc_alive
+
+
+def make_queries(syn, wl, rank):
+    nq, T, qseed = WORKLOADS[wl][4], WORKLOADS[wl][5], WORKLOADS[wl][7]
+    terms, _ = syn.queries(nq, T, seed=qseed + 1000 * rank)
+    offs = np.arange(nq + 1, dtype=np.uint64) * T
+    return terms, offs, nq, T
+
+
+def cpu_baseline(orc_index, terms, offs, opts, threads, budget_s=12.0):
+    """Oracle (C++ restatement of the reference CPU path) on a bounded sample of the same batch."""
+    nq = len(offs) - 1
+    probe = min(nq, 64 * threads)
+    secs = orc_index.search_batch(terms, offs[:probe + 1], opts[:probe], K_STRIDE, n_threads=threads)[3]
+    rate = probe / max(secs, 1e-9)
+    sample = int(min(nq, max(probe, rate * budget_s)))
+    secs = orc_index.search_batch(terms, offs[:sample + 1], opts[:sample], K_STRIDE, n_threads=threads)[3]
+    return sample / secs, sample
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import __graft_entry__ as graft
+    from _oracle import OracleIndex, build as build_oracle
+    build_oracle()
+    pkg = graft.load_package()  # synthetic data generator only; no libfpx call on this arm
+    wl = args.workload
+    dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+    syn, items, doc_ids, doc_alive = build_corpus(pkg, wl, dev)
+    t = time.time()
+    orc = OracleIndex()
+    orc.add_file_segment_sorted(items, doc_ids, doc_alive)   # the oracle's own block writer
+    del items
+    log("[bench] oracle segment written in %.1fs" % (time.time() - t))
+    terms, offs, nq, T = make_queries(syn, wl, 0)
+    opts = pkg.synth.http_opts(nq, T)
+    threads = os.cpu_count() or 1
+    flat = terms.reshape(-1)
+    probe = min(nq, 64 * threads)
+    secs = orc.search_batch(flat, offs[:probe + 1], opts[:probe], K_STRIDE, n_threads=threads)[3]
+    per_step = int(min(nq, max(probe, probe / secs * 6.0)))   # ~6 s of CPU work per step
+    for _ in range(args.warmup):
+        orc.search_batch(flat, offs[:per_step + 1], opts[:per_step], K_STRIDE, n_threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.search_batch(flat, offs[:per_step + 1], opts[:per_step], K_STRIDE, n_threads=threads)
+    dt = time.perf_counter() - t0
+    qps = per_step * args.steps / dt
+    sample = "%d queries/step of the %s batch" % (per_step, wl)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(wl, "cpu"),
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "C++ restatement of the reference CPU path (Zig toolchain unavailable); not the reference binary",
+    }), flush=True)
+
+
+def workload_config(wl, parallelism):
+    n_docs, H, vlog, zipf, nq, T, *_ = WORKLOADS[wl]
+    return {"workload": "%s: %d fingerprints x %d hashes, vocab 2^%d%s, %d-query batch x %d terms, limit 40, "
+                        "min_score (T+19)/20, score_pct 10, one merged file segment (512-byte blocks)"
+                        % (wl, n_docs, H, vlog, ", Zipf s=%.1f" % zipf if zipf else "", nq, T),
+            "parallelism": parallelism,
+            "l2": "inputs larger than L2: CSR rows touched per step (~GBs) >> 126 MB L2; no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="fpx", choices=["fpx", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import __graft_entry__ as graft
+    pkg = graft.load_package()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the fpx search path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    wl = args.workload
+    host_threads = max(1, (os.cpu_count() or 1) // max(1, world))
+
+    # ---- setup (untimed): synthetic corpus -> reference-format segment -> GPU snapshot
+    syn, items, doc_ids, doc_alive = build_corpus(pkg, wl, str(dev))
+    t = time.time()
+    seg = pkg.FileSegment.from_items(items, doc_ids, doc_alive, commit_id=1, threads=host_threads)
+    del items
+    log("[bench] segment: %d blocks written in %.1fs" % (seg.num_blocks, time.time() - t))
+    t = time.time()
+    ctx = pkg.Context(device=local_rank, profile=True, host_threads=host_threads)
+    snap = pkg.swap_snapshot(ctx, [seg])
+    info = snap.info()
+    log("[bench] snapshot: %d terms, %d postings, %.2f GB in HBM, built in %.1fs"
+        % (info["n_terms"], info["n_postings"], info["device_bytes"] / 1e9, time.time() - t))
+    reader = pkg.IndexReader(snap)
+    terms, offs, nq, T = make_queries(syn, wl, rank)
+    opts = pkg.synth.http_opts(nq, T)
+    torch.cuda.empty_cache()
+
+    # device-resident inputs/outputs
+    d_terms = torch.from_numpy(terms.reshape(-1).view(np.int32)).to(dev)
+    d_offs = torch.from_numpy(offs.view(np.int64)).to(dev)
+    d_opts = torch.from_numpy(opts.view(np.int32)).to(dev)
+    d_ids = torch.zeros((nq, K_STRIDE), dtype=torch.int32, device=dev)
+    d_sc = torch.zeros((nq, K_STRIDE), dtype=torch.int32, device=dev)
+    d_cnt = torch.zeros(nq, dtype=torch.int32, device=dev)
+    gather_buf = None
+    if world > 1:
+        packed = torch.empty((nq, 2 * K_STRIDE + 1), dtype=torch.int32, device=dev)
+        gather_buf = torch.empty((world * nq, 2 * K_STRIDE + 1), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        reader.search_batch_device(nq, d_terms.data_ptr(), d_offs.data_ptr(), d_opts.data_ptr(), K_STRIDE,
+                                   d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(), stream.cuda_stream)
+        if world > 1:  # the one exchange step: collect every rank's per-query result lists (NCCL over NVLink)
+            packed[:, :K_STRIDE] = d_ids
+            packed[:, K_STRIDE:2 * K_STRIDE] = d_sc
+            packed[:, 2 * K_STRIDE] = d_cnt
+            dist.all_gather_into_tensor(gather_buf, packed)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    ctx.profile_reset()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    prof = ctx.profile()
+    if world > 1:
+        tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    ms_per_step = ms_total / args.steps
+    value = world * nq / (ms_per_step * 1e-3)
+
+    # ---- e2e through the host-buffer C-ABI call, pinned host memory, copies inside the timed region
+    h_terms = torch.from_numpy(terms.reshape(-1).view(np.int32).copy()).pin_memory()
+    h_offs = torch.from_numpy(offs.view(np.int64).copy()).pin_memory()
+    h_opts = torch.from_numpy(opts.view(np.int32).copy()).pin_memory()
+    h_ids = torch.zeros((nq, K_STRIDE), dtype=torch.int32).pin_memory()
+    h_sc = torch.zeros((nq, K_STRIDE), dtype=torch.int32).pin_memory()
+    h_cnt = torch.zeros(nq, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        reader.search_batch_ptr(nq, h_terms.data_ptr(), h_offs.data_ptr(), h_opts.data_ptr(), K_STRIDE,
+                                h_ids.data_ptr(), h_sc.data_ptr(), h_cnt.data_ptr())
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_qps = world * nq * args.steps / e2e_s
+    h2d = int(h_terms.numel() * 4 + h_offs.numel() * 8 + h_opts.numel() * 4)
+    d2h = int(h_ids.numel() * 4 + h_sc.numel() * 4 + h_cnt.numel() * 4)
+    # the e2e results must equal the device-resident ones
+    assert np.array_equal(h_cnt.numpy(), d_cnt.cpu().numpy()), "e2e and device-resident results differ"
+
+    # ---- roofline of the dominant kernel (search_smem_kernel launches of the timed region)
+    peak, peak_src = measured_peak()
+    steps = args.steps
+    rows = prof["unique_terms"] / steps        # upper bound of row descriptors read (present terms <= unique terms)
+    postings = prof["postings"] / steps
+    results = prof["results"] / steps
+    search_bytes = 8.0 * rows + 4.0 * postings + 8.0 * results + 4.0 * nq
+    path_bytes = 20.0 * rows + 4.0 * postings + 8.0 * results          # SURVEY.md §8d per-query formula
+    search_ms = prof["search_ms"] / steps
+    achieved = search_bytes / (search_ms * 1e-3) / 1e9 if search_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % wl)
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "search_smem_kernel<14> (gather + count + top-k)",
+                "kernel_ms_per_step": search_ms, "algorithmic_bytes_per_step": search_bytes,
+                "whole_path_bytes_per_step": path_bytes, "postings_per_step": postings,
+                "prepare_ms_per_step": prof["prepare_ms"] / steps, "wide_ms_per_step": prof["wide_ms"] / steps,
+                "wide_queries_per_step": prof["wide_queries"] / steps, "peak_source": peak_src}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(wl, "replicated corpus, query batch per GPU x%d" % world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": 7 * args.steps,
+        "roofline": roofline,
+    }
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): oracle port on a bounded sample of the same batch
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from _oracle import OracleIndex, build as build_oracle
+        build_oracle()
+        orc = OracleIndex()
+        orc.adopt_file_segment(1, 0, seg.block_size, seg.blocks, seg.num_blocks, seg.block_index, seg.doc_ids,
+                               seg.doc_alive)
+        threads = os.cpu_count() or 1
+        qps, sample = cpu_baseline(orc, terms.reshape(-1), offs, opts, threads)
+        # and check the GPU answers on that sample while we are here (bit-exact)
+        oi, os_, oc, _ = orc.search_batch(terms.reshape(-1), offs[:min(sample, 2000) + 1], opts[:min(sample, 2000)],
+                                          K_STRIDE, n_threads=threads)
+        n_chk = len(oc)
+        g_cnt = h_cnt.numpy().view(np.uint32)[:n_chk]
+        g_ids = h_ids.numpy().view(np.uint32)[:n_chk]
+        mask = np.arange(K_STRIDE)[None, :] < oc[:, None]
+        parity = bool(np.array_equal(g_cnt, oc) and np.array_equal(g_ids[mask], oi[mask]))
+        out["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                               "sample": "%d queries of the same batch" % sample}
+        out["parity_checked_queries"] = n_chk
+        out["parity_bit_exact"] = parity
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    snap.release()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,329 @@
+"""GPU parity: the CUDA path (through the C ABI) vs the CPU oracle on identical inputs, bit-exact.
+Covers BASELINE.json configs C1, C2 (full size) and a Zipf stress, plus the edge cases the reference tests."""
+import numpy as np
+import pytest
+
+from _helpers import flat_queries, have_gpu, pkg, segments_from_oracle
+from _oracle import OracleIndex
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    if not have_gpu():
+        pytest.skip("no CUDA device")
+    c = pkg.Context(device=0, profile=True)
+    yield c
+    c.close()
+
+
+def _snapshot_of(ctx, ix, doc_range=None):
+    files, mems = segments_from_oracle(ix)
+    return pkg.swap_snapshot(ctx, files, mems, doc_range=doc_range)
+
+
+def _compare_batch(reader, ix, terms, offs, opts, k_stride, threads=8):
+    ids, sc, cnt = reader.search_batch(terms, offs, opts, k_stride)
+    oi, os_, oc, _ = ix.search_batch(terms, offs, opts, k_stride, n_threads=threads)
+    bad = np.nonzero(cnt != oc)[0]
+    assert len(bad) == 0, "count mismatch at queries %s: gpu %s oracle %s" % (bad[:5], cnt[bad[:5]], oc[bad[:5]])
+    mask = np.arange(k_stride)[None, :] < cnt[:, None]
+    assert np.array_equal(np.where(mask, ids, 0), np.where(mask, oi, 0)), "ids differ"
+    assert np.array_equal(np.where(mask, sc, 0), np.where(mask, os_, 0)), "scores differ"
+    return ids, sc, cnt
+
+
+def _build_c1():
+    """C1: 1K fingerprints x 50 hashes: 1 file segment (first 800 docs) + 2 memory segments with
+    20 re-inserts and 10 deletes."""
+    cfg = pkg.synth.SynthConfig(n_docs=1000, hashes_per_doc=50, vocab_log2=10, seed=0xF1D00001 + 1)
+    syn = pkg.synth.Synth(cfg)
+    fps = syn.doc_hashes(np.arange(1000))
+    ix = OracleIndex()
+    ix.update([("insert", i + 1, fps[i].tolist()) for i in range(800)])
+    ix.checkpoint()
+    ix.update([("insert", i + 1, fps[i].tolist()) for i in range(800, 900)] +
+              [("insert", i + 1, fps[999 - i].tolist()) for i in range(20)])          # 20 re-inserts
+    ix.update([("insert", i + 1, fps[i].tolist()) for i in range(900, 1000)] +
+              [("delete", i + 1) for i in range(100, 110)])                          # 10 deletes
+    return ix, syn, fps
+
+
+def test_c1_single_term_queries(ctx):
+    ix, syn, fps = _build_c1()
+    snap = _snapshot_of(ctx, ix)
+    reader = pkg.IndexReader(snap)
+    terms, _ = syn.queries(100, 1, single_term=True)
+    offs = np.arange(101, dtype=np.uint64)
+    opts = pkg.synth.http_opts(100, 1)
+    _, _, cnt = _compare_batch(reader, ix, terms.reshape(-1), offs, opts, 40)
+    assert cnt.sum() > 0
+    # reference-interface mirror, one query at a time, HTTP option mapping
+    for q in range(10):
+        got = pkg.multi_index_search(reader, pkg.SearchRequest([int(terms[q, 0])]))
+        assert [tuple(r) for r in got] == ix.search_http([int(terms[q, 0])])
+    # full fingerprints as queries: updated / deleted docs must follow the supersession rules
+    for d in (0, 5, 19, 100, 109, 500, 850, 999):
+        q = fps[d].tolist()
+        got = pkg.multi_index_search(reader, pkg.SearchRequest(q))
+        assert [tuple(r) for r in got] == ix.search_http(q)
+    snap.release()
+
+
+def test_reference_kats_through_the_gpu(ctx):
+    """The reference's own e2e vectors (tests/test_fingerprint_api.py:5-52, 102-260; Index.zig:1056-1096)."""
+    ix = OracleIndex()
+    ix.update([("insert", 1, [101, 201, 301]), ("insert", 2, [102, 202, 302])])
+    r = pkg.IndexReader(_snapshot_of(ctx, ix))
+    assert pkg.multi_index_search(r, pkg.SearchRequest([101, 201, 301])) == [(1, 3)]
+    assert pkg.multi_index_search(r, pkg.SearchRequest([101, 201, 301, 102, 202, 302])) == [(1, 3), (2, 3)]
+    assert r.search([101, 101], pkg.SearchOptions(10, 1, 10)) == [(1, 1)]          # duplicate query hashes
+    ix.checkpoint()
+    r = pkg.IndexReader(_snapshot_of(ctx, ix))
+    assert r.search([101, 101], pkg.SearchOptions(10, 1, 10)) == [(1, 1)]
+    ix.update([("insert", 1, [101, 201, 999])])                                      # partial update
+    r = pkg.IndexReader(_snapshot_of(ctx, ix))
+    assert pkg.multi_index_search(r, pkg.SearchRequest([101, 201, 301])) == [(1, 2)]
+    assert pkg.multi_index_search(r, pkg.SearchRequest([101, 201, 999])) == [(1, 3)]
+    ix.update([("delete", 1), ("delete", 2)])
+    r = pkg.IndexReader(_snapshot_of(ctx, ix))
+    assert pkg.multi_index_search(r, pkg.SearchRequest([101, 201, 301, 102, 202, 302])) == []
+    assert r.search([], pkg.SearchOptions(10, 0, 10)) == []
+    ix2 = OracleIndex()
+    ix2.update([("insert", 1001, [11000, 12000, 13000]), ("insert", 1002, [11000, 12000, 19000])])
+    r = pkg.IndexReader(_snapshot_of(ctx, ix2))                                      # tests/test_legacy.py:61-69
+    assert r.search([11000, 12000, 13000], pkg.SearchOptions(500, 1, 10)) == [(1001, 3), (1002, 2)]
+    assert r.search([11000, 12000, 19000], pkg.SearchOptions(500, 1, 10)) == [(1002, 3), (1001, 2)]
+
+
+def _random_index(rng, rounds=9, n_docs=400, H=30, vocab=4000, hot=(7, 8)):
+    ix = OracleIndex()
+    next_id, all_ids = 1, []
+    for r in range(rounds):
+        ch = []
+        for _ in range(n_docs):
+            roll = rng.random()
+            if all_ids and roll < 0.1:
+                did = int(rng.choice(all_ids))
+            elif all_ids and roll < 0.15:
+                ch.append(("delete", int(rng.choice(all_ids))))
+                continue
+            else:
+                did = next_id
+                next_id += 1
+                all_ids.append(did)
+            hs = rng.integers(0, vocab, size=H)
+            hs[rng.random(H) < 0.2] = rng.choice(hot)
+            hs = hs.tolist()
+            if rng.random() < 0.3:
+                hs[1] = hs[0]
+            ch.append(("insert", did, hs))
+        ix.update(ch)
+        if r % 3 == 2:
+            ix.checkpoint()
+    return ix, all_ids
+
+
+def test_random_multi_segment_varied_options(ctx):
+    rng = np.random.default_rng(42)
+    ix, _ = _random_index(rng)
+    assert ix.num_file_segments == 3 and ix.num_memory_segments == 0
+    ix.update([("insert", 5, [1, 2, 3])])
+    snap = _snapshot_of(ctx, ix)
+    info = snap.info()
+    assert info["n_dropped_superseded"] > 0 and info["n_dropped_unreachable"] > 0
+    reader = pkg.IndexReader(snap)
+    queries = [rng.integers(0, 4000, size=int(rng.integers(0, 120))).tolist() for _ in range(600)]
+    queries += [[7, 8] + rng.integers(0, 4000, size=30).tolist() for _ in range(100)]
+    terms, offs = flat_queries(queries)
+    nq = len(queries)
+    for k_stride, opt in ((40, (40, 1, 10)), (64, (10, 2, 0)), (8, (100, 1, 100)), (600, (500, 1, 10)),
+                          (1024, (1024, 0, 3)), (40, (0, 1, 10)), (40, (40, 3, 250)), (1, (5, 1, 10))):
+        opts = np.tile(np.array(opt, dtype=np.uint32), (nq, 1))
+        _compare_batch(reader, ix, terms, offs, opts, k_stride)
+    # per-query mixed options in one batch
+    opts = np.stack([rng.integers(0, 60, nq), rng.integers(0, 6, nq), rng.integers(0, 120, nq)], 1).astype(np.uint32)
+    _compare_batch(reader, ix, terms, offs, opts, 64)
+    snap.release()
+
+
+def test_count_overflow_and_duplicates_fall_back_exactly(ctx):
+    """Docs with hundreds of duplicate hashes push per-doc counts past the packed table's counter: the
+    shared-memory path must notice and the global-memory path must still give the reference's answer."""
+    ix = OracleIndex()
+    ch = [("insert", 1, [5] * 700 + [6] * 300), ("insert", 2, [5] * 600), ("insert", 3, [5, 6, 7])]
+    ch += [("insert", 10 + i, [5, 1000 + i]) for i in range(300)]
+    ix.update(ch)
+    ix.update([("insert", 4, [6] * 2000)])
+    for flush in (False, True):
+        if flush:
+            ix.checkpoint()
+        snap = _snapshot_of(ctx, ix)
+        reader = pkg.IndexReader(snap)
+        queries = [[5], [5, 6], [5, 6, 7], [6], [7] + list(range(1000, 1100))]
+        terms, offs = flat_queries(queries)
+        for opt in ((40, 1, 10), (500, 1, 0), (3, 2, 0)):
+            opts = np.tile(np.array(opt, dtype=np.uint32), (len(queries), 1))
+            _compare_batch(reader, ix, terms, offs, opts, 512)
+        ctx.profile_reset()
+        reader.search([5, 6], pkg.SearchOptions(40, 1, 10))
+        assert ctx.profile()["wide_queries"] >= 1
+        snap.release()
+
+
+def test_long_queries(ctx):
+    rng = np.random.default_rng(3)
+    ix, _ = _random_index(rng, rounds=6, vocab=20000, hot=(7,))
+    snap = _snapshot_of(ctx, ix)
+    reader = pkg.IndexReader(snap)
+    queries = [rng.integers(0, 20000, size=n).tolist() for n in (128, 129, 130, 255, 256, 257, 1000, 4096, 8192, 1, 0)]
+    queries.append([3] * 500 + [4] * 500)            # heavy duplication in a long query
+    terms, offs = flat_queries(queries)
+    opts = np.array([[40, pkg.lib().fpx_default_min_score(len(q)), 10] for q in queries], dtype=np.uint32)
+    _compare_batch(reader, ix, terms, offs, opts, 40)
+    opts[:, 1] = 1
+    _compare_batch(reader, ix, terms, offs, opts, 40)
+    with pytest.raises(pkg.FpxError) as e:
+        reader.search(list(range(8193)), pkg.SearchOptions())
+    assert e.value.status == pkg._ffi.FPX_UNSUPPORTED
+    snap.release()
+
+
+def test_doc_range_shards_merge_to_the_unsharded_answer(ctx):
+    rng = np.random.default_rng(9)
+    ix, ids = _random_index(rng, rounds=6)
+    queries = [rng.integers(0, 4000, size=40).tolist() for _ in range(200)]
+    terms, offs = flat_queries(queries)
+    nq, k = len(queries), 40
+    opts = np.tile(np.array((40, 1, 10), dtype=np.uint32), (nq, 1))
+    whole = pkg.IndexReader(_snapshot_of(ctx, ix))
+    want = whole.search_batch(terms, offs, opts, k)
+    cuts = [0, int(np.quantile(ids, 0.3)), int(np.quantile(ids, 0.7)), 0xFFFFFFFF]
+    shard_opts = opts.copy()
+    shard_opts[:, 2] = 0                                 # absolute floor only on the shards
+    parts = [pkg.IndexReader(_snapshot_of(ctx, ix, (cuts[i], cuts[i + 1]))).search_batch(terms, offs, shard_opts, k)
+             for i in range(3)]
+    got = pkg.merge_shard_results(np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]),
+                                  np.stack([p[2] for p in parts]), opts, k)
+    assert np.array_equal(got[2], want[2])
+    mask = np.arange(k)[None, :] < want[2][:, None]
+    assert np.array_equal(np.where(mask, got[0], 0), np.where(mask, want[0], 0))
+    assert np.array_equal(np.where(mask, got[1], 0), np.where(mask, want[1], 0))
+    _compare_batch(whole, ix, terms, offs, opts, k)
+
+
+@pytest.fixture(scope="module")
+def c2(ctx):
+    """C2: 1M fingerprints x 100 hashes, one fully merged file segment; 10K queries x 100 terms."""
+    cfg = pkg.synth.SynthConfig(n_docs=1_000_000, hashes_per_doc=100, vocab_log2=20, seed=0xF1D00001 + 2)
+    syn = pkg.synth.Synth(cfg, device="cuda:0")
+    items, doc_ids, doc_alive = syn.corpus_items()
+    seg = pkg.FileSegment.from_items(items, doc_ids, doc_alive, commit_id=1)
+    del items
+    snap = pkg.swap_snapshot(ctx, [seg])
+    ix = OracleIndex()
+    ix.adopt_file_segment(1, 0, seg.block_size, seg.blocks, seg.num_blocks, seg.block_index, seg.doc_ids, seg.doc_alive)
+    yield syn, seg, snap, ix
+    snap.release()
+
+
+def test_c2_full_size_bit_exact(ctx, c2):
+    syn, seg, snap, ix = c2
+    info = snap.info()
+    assert info["n_postings_total"] == 100_000_000
+    reader = pkg.IndexReader(snap)
+    terms, src = syn.queries(10_000, 100, seed=0xF1D01001 + 2)
+    nq, T = terms.shape
+    offs = np.arange(nq + 1, dtype=np.uint64) * T
+    opts = pkg.synth.http_opts(nq, T)
+    ids, sc, cnt = _compare_batch(reader, ix, terms.reshape(-1), offs, opts, 40, threads=16)
+    # domain property: a noisy copy of doc d finds d first
+    hit = src >= 0
+    assert (cnt[hit] >= 1).all()
+    assert (ids[hit, 0] == (src[hit] + 1)).mean() > 0.99
+    # legacy options (limit 500, min_score 1) on a slice: exercises the many-candidates path
+    opts2 = np.tile(np.array((500, 1, 10), dtype=np.uint32), (500, 1))
+    _compare_batch(reader, ix, terms[:500].reshape(-1), offs[:501], opts2, 500, threads=16)
+
+
+def test_c2_size_independent_properties(ctx, c2):
+    syn, seg, snap, ix = c2
+    reader = pkg.IndexReader(snap)
+    rng = np.random.default_rng(1)
+    terms, _ = syn.queries(4000, 100, seed=77)
+    nq, T = terms.shape
+    offs = np.arange(nq + 1, dtype=np.uint64) * T
+    opts = pkg.synth.http_opts(nq, T)
+    a = reader.search_batch(terms.reshape(-1), offs, opts, 40)
+    b = reader.search_batch(terms.reshape(-1), offs, opts, 40)                       # idempotence
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    perm = np.stack([rng.permutation(T) for _ in range(nq)])                          # the query is a set:
+    shuffled = np.take_along_axis(terms, perm, 1)                                    # order and repeats do not matter
+    doubled = np.concatenate([shuffled, terms[:, :37]], 1)
+    offs2 = np.arange(nq + 1, dtype=np.uint64) * doubled.shape[1]
+    c = reader.search_batch(doubled.reshape(-1), offs2, opts, 40)
+    assert all(np.array_equal(x, y) for x, y in zip(a, c))
+    ids, sc, cnt = a
+    mask = np.arange(40)[None, :] < cnt[:, None]
+    s = np.where(mask, sc, 0).astype(np.int64)
+    assert (np.diff(s, axis=1) <= 0).all()                                           # score descending
+    tie = mask[:, 1:] & (sc[:, 1:] == sc[:, :-1])
+    assert (ids[:, 1:][tie] > ids[:, :-1][tie]).all()                                # id ascending on ties
+    floor = np.maximum(opts[:, 1], (sc[:, 0] * opts[:, 2]) // 100)
+    assert (np.where(mask, sc, 1 << 30) >= floor[:, None]).all()                     # both cutoffs hold
+    # splitting the batch (other chunking, other workspaces) changes nothing
+    h = nq // 3
+    p1 = reader.search_batch(terms[:h].reshape(-1), offs[:h + 1], opts[:h], 40)
+    p2 = reader.search_batch(terms[h:].reshape(-1), offs[:nq - h + 1], opts[h:], 40)
+    assert np.array_equal(np.concatenate([p1[2], p2[2]]), cnt)
+    assert np.array_equal(np.concatenate([p1[0], p2[0]])[mask], ids[mask])
+
+
+def test_zipf_hot_postings(ctx):
+    """C5-shaped stress at test size: Zipf vocabulary, rows cut by the scan caps, multi-pass queries."""
+    cfg = pkg.synth.SynthConfig(n_docs=300_000, hashes_per_doc=60, vocab_log2=14, seed=0xF1D00001 + 5, zipf_s=1.0)
+    syn = pkg.synth.Synth(cfg, device="cuda:0")
+    items, doc_ids, doc_alive = syn.corpus_items()
+    seg = pkg.FileSegment.from_items(items, doc_ids, doc_alive, commit_id=1)
+    snap = pkg.swap_snapshot(ctx, [seg])
+    info = snap.info()
+    assert info["n_dropped_unreachable"] > 0 and info["max_row_len"] > 1000
+    ix = OracleIndex()
+    ix.adopt_file_segment(1, 0, seg.block_size, seg.blocks, seg.num_blocks, seg.block_index, seg.doc_ids, seg.doc_alive)
+    reader = pkg.IndexReader(snap)
+    terms, _ = syn.queries(3000, 100, seed=5)
+    nq, T = terms.shape
+    offs = np.arange(nq + 1, dtype=np.uint64) * T
+    ctx.profile_reset()
+    _compare_batch(reader, ix, terms.reshape(-1), offs, pkg.synth.http_opts(nq, T), 40, threads=16)
+    opts = np.tile(np.array((100, 2, 0), dtype=np.uint32), (nq, 1))
+    _compare_batch(reader, ix, terms.reshape(-1), offs, opts, 100, threads=16)
+    snap.release()
+
+
+def test_device_resident_api_matches_host_api(ctx, c2):
+    import torch
+    syn, seg, snap, ix = c2
+    reader = pkg.IndexReader(snap)
+    terms, _ = syn.queries(3000, 100, seed=123)
+    nq, T = terms.shape
+    offs = np.arange(nq + 1, dtype=np.uint64) * T
+    opts = pkg.synth.http_opts(nq, T)
+    want = reader.search_batch(terms.reshape(-1), offs, opts, 40)
+    dev = torch.device("cuda:0")
+    d_terms = torch.from_numpy(terms.reshape(-1).view(np.int32)).to(dev)
+    d_offs = torch.from_numpy(offs.view(np.int64)).to(dev)
+    d_opts = torch.from_numpy(opts.view(np.int32)).to(dev)
+    d_ids = torch.zeros((nq, 40), dtype=torch.int32, device=dev)
+    d_sc = torch.zeros((nq, 40), dtype=torch.int32, device=dev)
+    d_cnt = torch.zeros(nq, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream()
+    reader.search_batch_device(nq, d_terms.data_ptr(), d_offs.data_ptr(), d_opts.data_ptr(), 40, d_ids.data_ptr(),
+                               d_sc.data_ptr(), d_cnt.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    cnt = d_cnt.cpu().numpy().view(np.uint32)
+    assert np.array_equal(cnt, want[2])
+    mask = np.arange(40)[None, :] < cnt[:, None]
+    assert np.array_equal(d_ids.cpu().numpy().view(np.uint32)[mask], want[0][mask])
+    assert np.array_equal(d_sc.cpu().numpy().view(np.uint32)[mask], want[1][mask])
