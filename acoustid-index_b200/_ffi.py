@@ -24,6 +24,7 @@ STATUS_NAMES = {
 }
 FPX_FLAG_PROFILE = 1
 FPX_FLAG_HOST_ONLY = 2
+FPX_FLAG_NO_SKETCH = 4
 FPX_MAX_QUERY_TERMS = 8192
 FPX_MAX_RESULTS = 1024
 
@@ -70,11 +71,13 @@ class CsrView(C.Structure):
 
 class Profile(C.Structure):
     _fields_ = [("prepare_ms", C.c_double), ("prepare_launches", C.c_uint64),
+                ("sketch_ms", C.c_double), ("sketch_launches", C.c_uint64),
                 ("search_ms", C.c_double), ("search_launches", C.c_uint64),
                 ("wide_ms", C.c_double), ("wide_launches", C.c_uint64),
                 ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("queries", C.c_uint64), ("unique_terms", C.c_uint64), ("postings", C.c_uint64),
-                ("results", C.c_uint64), ("wide_queries", C.c_uint64),
+                ("results", C.c_uint64), ("sketch_queries", C.c_uint64), ("wide_queries", C.c_uint64),
+                ("overflow_requeues", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 

@@ -43,7 +43,7 @@ fpx_status cuda_fail(cudaError_t e, const char *what) {
         if (e__ != cudaSuccess) return cuda_fail(e__, #call);    \
     } while (0)
 
-enum KernelKind { KK_PREPARE = 0, KK_SEARCH = 1, KK_WIDE = 2, KK_H2D = 3, KK_D2H = 4 };
+enum KernelKind { KK_PREPARE = 0, KK_SEARCH = 1, KK_WIDE = 2, KK_H2D = 3, KK_D2H = 4, KK_SKETCH = 5 };
 
 struct EventPair {
     int kind;
@@ -75,8 +75,8 @@ struct Workspace {
     cudaEvent_t done = nullptr; // last use (async device API)
     bool done_pending = false;
     DevBuf<uint2> rows;
-    DevBuf<QueryInfo> qinfo;
-    DevBuf<uint32_t> queues, long_queue;
+    DevBuf<WorkItem> items;
+    DevBuf<uint32_t> long_queue;
     DevBuf<unsigned long long> wide_tables;
     BatchCounters *counters = nullptr;
     // staging for host batches
@@ -87,8 +87,7 @@ struct Workspace {
 
     ~Workspace() {
         rows.release();
-        qinfo.release();
-        queues.release();
+        items.release();
         long_queue.release();
         wide_tables.release();
         d_terms.release();
@@ -115,6 +114,7 @@ struct fpx_ctx {
     uint32_t chunk_queries = 32768;
     uint32_t flags = 0;
     bool host_only = false;
+    bool use_sketch = true;
     std::mutex mu;
     std::vector<Workspace *> free_ws;
     DeviceStats *d_stats = nullptr;
@@ -199,10 +199,10 @@ fpx_status enqueue_batch(fpx_snapshot *s, Workspace *w, cudaStream_t st, uint64_
                          uint32_t *d_counts) {
     fpx_ctx *ctx = s->ctx;
     if (n_queries == 0) return FPX_OK;
-    if (n_queries > 0x7FFFFFFFull) return set_error(FPX_INVALID_ARGUMENT, "batch too large (split it)");
+    if (n_queries > 0x7FFFFFFFull || n_terms_total > 0xFFFFFFFFull)
+        return set_error(FPX_INVALID_ARGUMENT, "batch too large (split it)");
     cudaError_t e = w->rows.reserve(n_terms_total + 1);
-    if (e == cudaSuccess) e = w->qinfo.reserve(n_queries);
-    if (e == cudaSuccess) e = w->queues.reserve(n_queries * kNumClasses);
+    if (e == cudaSuccess) e = w->items.reserve(n_queries * kNumClasses);
     if (e == cudaSuccess) e = w->long_queue.reserve(n_queries);
     if (e != cudaSuccess) return cuda_fail(e, "workspace growth");
 
@@ -218,13 +218,13 @@ fpx_status enqueue_batch(fpx_snapshot *s, Workspace *w, cudaStream_t st, uint64_
     a.out_scores = d_scores;
     a.out_counts = d_counts;
     a.rows = w->rows.p;
-    a.qinfo = w->qinfo.p;
-    a.queues = w->queues.p;
+    a.items = w->items.p;
     a.long_queue = w->long_queue.p;
     a.counters = w->counters;
     a.stats = (ctx->flags & FPX_FLAG_PROFILE) ? ctx->d_stats : nullptr;
     a.wide_tables = w->wide_tables.p;
     a.wide_cap_log2 = kWideCapLog2;
+    a.use_sketch = ctx->use_sketch ? 1u : 0u;
 
     FPX_CUDA(cudaMemsetAsync(w->counters, 0, sizeof(BatchCounters), st));
     {
@@ -232,9 +232,13 @@ fpx_status enqueue_batch(fpx_snapshot *s, Workspace *w, cudaStream_t st, uint64_
         launch_prepare(a, st);
         launch_prepare_long(a, st, ctx->n_sms);
     }
+    if (a.use_sketch) {
+        Timed t(ctx, st, KK_SKETCH);
+        launch_search_sketch(a, st, ctx->n_sms);
+    }
     {
         Timed t(ctx, st, KK_SEARCH);
-        for (int c = 0; c < 3; ++c) launch_search_class(a, c, st, ctx->n_sms);
+        for (int c = 1; c <= 3; ++c) launch_search_class(a, c, st, ctx->n_sms);
     }
     {
         Timed t(ctx, st, KK_WIDE);
@@ -265,6 +269,7 @@ fpx_status fpx_init(const fpx_config *config, fpx_ctx **out) {
     ctx->host_threads = cfg.host_threads ? cfg.host_threads : std::max(1u, std::thread::hardware_concurrency());
     if (cfg.chunk_queries) ctx->chunk_queries = cfg.chunk_queries;
     ctx->host_only = (cfg.flags & FPX_FLAG_HOST_ONLY) != 0;
+    ctx->use_sketch = (cfg.flags & FPX_FLAG_NO_SKETCH) == 0;
     if (!ctx->host_only) {
         int n = 0;
         cudaError_t e = cudaGetDeviceCount(&n);
@@ -702,6 +707,7 @@ fpx_status fpx_profile_read(fpx_ctx *ctx, fpx_profile *out) {
             switch (p.kind) {
             case KK_PREPARE: ctx->prof.prepare_ms += ms; ctx->prof.prepare_launches += 2; break;
             case KK_SEARCH: ctx->prof.search_ms += ms; ctx->prof.search_launches += 3; break;
+            case KK_SKETCH: ctx->prof.sketch_ms += ms; ctx->prof.sketch_launches += 1; break;
             case KK_WIDE: ctx->prof.wide_ms += ms; ctx->prof.wide_launches += 1; break;
             case KK_H2D: ctx->prof.h2d_ms += ms; break;
             case KK_D2H: ctx->prof.d2h_ms += ms; break;
@@ -716,6 +722,8 @@ fpx_status fpx_profile_read(fpx_ctx *ctx, fpx_profile *out) {
         ctx->prof.postings = ds.postings;
         ctx->prof.results = ds.results;
         ctx->prof.wide_queries = ds.wide_queries;
+        ctx->prof.sketch_queries = ds.sketch_queries;
+        ctx->prof.overflow_requeues = ds.overflow_requeues;
     }
     *out = ctx->prof;
     return FPX_OK;

@@ -5,6 +5,13 @@
 // Here, over a whole batch, against the CSR built by fpx_snapshot_host.h:
 //   prepare_kernel       one warp per query: dedup terms, probe the term directory, emit row
 //                        descriptors, bin the query by posting volume
+//   search_sketch_kernel the hot path (min_score >= 2, i.e. every HTTP-default query of >= 21 terms):
+//                        warp-specialised persistent CTAs.  Producer warps gather the query's posting rows
+//                        into a shared-memory stage with TMA bulk copies (cp.async.bulk + mbarrier
+//                        complete_tx); consumer warps (1) scatter-add every docid into a per-query u16
+//                        count sketch with fire-and-forget shared atomics, (2) re-read the staged postings
+//                        and send only docids whose sketch counter reaches min_score to a small exact
+//                        table, (3) rank the survivors.  The sketch never under-counts, so this is exact.
 //   search_smem_kernel   persistent CTAs, one query at a time: stream the rows with 128-bit loads,
 //                        count docids in a shared-memory open-addressing table (one packed 32-bit word
 //                        per doc: quotient tag | probe number | count), then scan the table, rank the
@@ -49,9 +56,23 @@ __device__ __forceinline__ bool directory_lookup(const SnapshotDev &s, uint32_t 
     }
 }
 
+// Which exact shared-memory class (1..3) or the wide class holds `postings` postings.
+__device__ __forceinline__ uint32_t exact_class_for(unsigned long long postings, uint32_t k_eff) {
+    if (k_eff > kFastKbuf) return kWideClass;
+    if (postings <= 4096) return 1;
+    if (postings <= 8192) return 2;
+    if (postings <= 64ull * 12288) return 3; // multi-pass above 16384 (see search_smem_kernel)
+    return kWideClass;
+}
+
+__device__ __forceinline__ void enqueue(const BatchArgs &a, uint32_t cls, const WorkItem &w) {
+    const uint32_t pos = atomicAdd(&a.counters->qcount[cls], 1u);
+    a.items[(size_t)cls * a.n_queries + pos] = w;
+}
+
 // Bin a prepared query (called by one thread).
-__device__ void classify_and_enqueue(const BatchArgs &a, uint32_t q, uint32_t n_rows, unsigned long long postings,
-                                     uint32_t n_unique) {
+__device__ void classify_and_enqueue(const BatchArgs &a, uint32_t q, uint32_t rows_off, uint32_t n_rows,
+                                     unsigned long long postings, unsigned long long total4, uint32_t n_unique) {
     const SearchOpts o = a.opts[q];
     const uint32_t k_eff = min(o.max_results, a.k_stride);
     if (a.stats) {
@@ -63,29 +84,27 @@ __device__ void classify_and_enqueue(const BatchArgs &a, uint32_t q, uint32_t n_
         a.out_counts[q] = 0;
         return;
     }
-    uint32_t cls, passes = 1;
-    if (k_eff > kFastKbuf) {
-        cls = kWideClass;
-    } else if (postings <= 4096) {
-        cls = 0;
-    } else if (postings <= 8192) {
-        cls = 1;
-    } else if (postings <= 16384) {
-        cls = 2;
-    } else {
-        cls = 2;
-        const unsigned long long per_pass = 12288; // load <= 0.375 per pass on average
-        while ((unsigned long long)passes * per_pass < postings && passes <= 64) passes <<= 1;
-        if (passes > 64) cls = kWideClass;
-    }
-    QueryInfo qi;
-    qi.n_rows = n_rows;
-    qi.postings = postings > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)postings;
-    qi.passes = passes;
-    qi.reserved = 0;
-    a.qinfo[q] = qi;
-    const uint32_t pos = atomicAdd(&a.counters->qcount[cls], 1u);
-    a.queues[(size_t)cls * a.n_queries + pos] = q;
+    WorkItem w;
+    w.q = q;
+    w.rows_off = rows_off;
+    w.n_rows = n_rows;
+    w.total4 = total4 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)total4;
+    w.postings = postings > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)postings;
+    w.k_eff = k_eff;
+    w.min_score = o.min_score;
+    w.min_score_pct = o.min_score_pct;
+    uint32_t cls;
+    // The sketch path needs min_score >= 2 (it only recounts docids whose sketch counter reaches
+    // min_score) and the query must fit one 32 KB stage.  With a low floor and many postings nearly every
+    // counter is "hot" and the recount list would overflow, so those go to the exact count-table path.
+    bool sketch_ok = a.use_sketch && o.min_score >= 2 && total4 <= kStageU4 && k_eff <= kFastKbuf;
+    if (o.min_score == 2 && postings > 2048) sketch_ok = false;
+    if (o.min_score == 3 && postings > 5000) sketch_ok = false;
+    if (sketch_ok)
+        cls = kSketchClass;
+    else
+        cls = exact_class_for(postings, k_eff);
+    enqueue(a, cls, w);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -152,7 +171,7 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(BatchArgs a) {
             }
         }
         uint32_t n_unique = 0, n_rows = 0;
-        unsigned long long postings = 0;
+        unsigned long long postings = 0, total4 = 0;
         uint32_t st[4], ln[4];
         bool found[4];
 #pragma unroll
@@ -169,12 +188,16 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(BatchArgs a) {
                 const uint32_t pos = n_rows + __popc(fm & ((1u << lane) - 1u));
                 a.rows[o0 + pos] = make_uint2(st[j], ln[j]);
                 postings += ln[j];
+                total4 += (ln[j] + 3) >> 2;
             }
             n_rows += __popc(fm);
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) postings += __shfl_xor_sync(0xFFFFFFFFu, postings, off);
-        if (lane == 0) classify_and_enqueue(a, q, n_rows, postings, n_unique);
+        for (int off = 16; off > 0; off >>= 1) {
+            postings += __shfl_xor_sync(0xFFFFFFFFu, postings, off);
+            total4 += __shfl_xor_sync(0xFFFFFFFFu, total4, off);
+        }
+        if (lane == 0) classify_and_enqueue(a, q, (uint32_t)o0, n_rows, postings, total4, n_unique);
     }
 }
 
@@ -182,7 +205,7 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(BatchArgs a) {
 __global__ void __launch_bounds__(kThreads) prepare_long_kernel(BatchArgs a) {
     __shared__ uint32_t s_terms[kMaxQueryTerms];
     __shared__ uint32_t s_idx, s_rows, s_unique;
-    __shared__ unsigned long long s_post;
+    __shared__ unsigned long long s_post, s_tot4;
     const uint32_t tid = threadIdx.x;
     for (;;) {
         __syncthreads();
@@ -199,6 +222,7 @@ __global__ void __launch_bounds__(kThreads) prepare_long_kernel(BatchArgs a) {
             s_rows = 0;
             s_unique = 0;
             s_post = 0;
+            s_tot4 = 0;
         }
         __syncthreads();
         for (uint32_t k = 2; k <= m; k <<= 1)
@@ -224,44 +248,52 @@ __global__ void __launch_bounds__(kThreads) prepare_long_kernel(BatchArgs a) {
             if (directory_lookup(a.snap, v, st, ln)) {
                 a.rows[o0 + atomicAdd(&s_rows, 1u)] = make_uint2(st, ln);
                 atomicAdd(&s_post, (unsigned long long)ln);
+                atomicAdd(&s_tot4, (unsigned long long)((ln + 3) >> 2));
             }
         }
         __syncthreads();
-        if (tid == 0) classify_and_enqueue(a, q, s_rows, s_post, s_unique);
+        if (tid == 0) classify_and_enqueue(a, q, (uint32_t)o0, s_rows, s_post, s_tot4, s_unique);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // ranking helpers: key = (0xFFFFFFFF - score) << 32 | id, ascending == (score desc, id asc)
-// (common.zig:169-171 compareResults)
+// (common.zig:169-171 compareResults).  "group" = the threads that cooperate on one query: the whole
+// CTA (barrier 0) in the exact kernels, the consumer warps (barrier 1) in the sketch kernel.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long rank_key(uint32_t score, uint32_t id) {
     return ((unsigned long long)(0xFFFFFFFFu - score) << 32) | id;
 }
 
-// Sort kbuf[0..n) ascending; m = padded power of two (entries n..m overwritten with ~0).
-__device__ void block_sort_keys(unsigned long long *kbuf, uint32_t n, uint32_t cap) {
-    const uint32_t tid = threadIdx.x;
+struct Group {
+    uint32_t tid, size, bar; // thread index in the group, group size (multiple of 32), named barrier id
+    __device__ __forceinline__ void sync() const {
+        asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(size) : "memory");
+    }
+};
+
+// Sort kbuf[0..n) ascending (entries n..pow2 are overwritten with ~0).  All group threads call this.
+__device__ void group_sort_keys(const Group &g, unsigned long long *kbuf, uint32_t n, uint32_t cap) {
     if (n <= 1) return;
     if (n <= 32) {
-        if (tid < 32) {
-            const unsigned long long key = tid < n ? kbuf[tid] : ~0ull;
+        if (g.tid < 32) {
+            const unsigned long long key = g.tid < n ? kbuf[g.tid] : ~0ull;
             uint32_t rank = 0;
             for (uint32_t l = 0; l < n; ++l) rank += (__shfl_sync(0xFFFFFFFFu, key, l) < key) ? 1u : 0u;
             __syncwarp();
-            if (tid < n) kbuf[rank] = key;
+            if (g.tid < n) kbuf[rank] = key;
         }
-        __syncthreads();
+        g.sync();
         return;
     }
     uint32_t m = 64;
     while (m < n) m <<= 1;
     if (m > cap) m = cap;
-    for (uint32_t i = n + tid; i < m; i += kThreads) kbuf[i] = ~0ull;
-    __syncthreads();
+    for (uint32_t i = n + g.tid; i < m; i += g.size) kbuf[i] = ~0ull;
+    g.sync();
     for (uint32_t k = 2; k <= m; k <<= 1)
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = tid; i < m; i += kThreads) {
+            for (uint32_t i = g.tid; i < m; i += g.size) {
                 const uint32_t x = i ^ j;
                 if (x > i) {
                     const unsigned long long u = kbuf[i], v = kbuf[x];
@@ -271,45 +303,292 @@ __device__ void block_sort_keys(unsigned long long *kbuf, uint32_t n, uint32_t c
                     }
                 }
             }
-            __syncthreads();
+            g.sync();
         }
 }
 
 // common.zig:153-166: walk the ranked candidates, at most k_eff, relative cutoff anchored on the best.
-// kbuf[0..n) sorted.  All threads of the CTA call this.
-__device__ void emit_results(const BatchArgs &a, uint32_t q, const unsigned long long *kbuf, uint32_t n,
-                             const SearchOpts &o) {
-    const uint32_t tid = threadIdx.x;
-    const uint32_t k_eff = min(o.max_results, a.k_stride);
-    const uint32_t lim = min(n, k_eff);
-    uint32_t ms = o.min_score;
+// kbuf[0..n) sorted and visible to the group.  All group threads call this; s_count is group-shared scratch.
+__device__ void group_emit_results(const Group &g, const BatchArgs &a, const WorkItem &w,
+                                   const unsigned long long *kbuf, uint32_t n, uint32_t *s_count) {
+    const uint32_t lim = min(n, w.k_eff);
+    uint32_t ms = w.min_score;
     if (lim > 0) {
         const uint32_t s0 = 0xFFFFFFFFu - (uint32_t)(kbuf[0] >> 32);
-        ms = max(ms, (uint32_t)(s0 * o.min_score_pct) / 100u); // u32 wrapping product, truncating division
+        ms = max(ms, (uint32_t)(s0 * w.min_score_pct) / 100u); // u32 wrapping product, truncating division
     }
-    uint32_t total = 0;
-    for (uint32_t base = 0; base < lim; base += kThreads) {
-        const uint32_t i = base + tid;
-        bool pass = false;
-        if (i < lim) {
-            const unsigned long long key = kbuf[i];
-            const uint32_t score = 0xFFFFFFFFu - (uint32_t)(key >> 32);
-            pass = (i == 0) || score >= ms; // the best candidate is emitted before the cutoff is raised
-            if (pass) {
-                a.out_ids[(size_t)q * a.k_stride + i] = (uint32_t)key;
-                a.out_scores[(size_t)q * a.k_stride + i] = score;
-            }
+    if (g.tid == 0) *s_count = 0;
+    g.sync();
+    for (uint32_t i = g.tid; i < lim; i += g.size) {
+        const unsigned long long key = kbuf[i];
+        const uint32_t score = 0xFFFFFFFFu - (uint32_t)(key >> 32);
+        if (i == 0 || score >= ms) { // the best candidate is emitted before the cutoff is raised
+            a.out_ids[(size_t)w.q * a.k_stride + i] = (uint32_t)key;
+            a.out_scores[(size_t)w.q * a.k_stride + i] = score;
+            atomicAdd(s_count, 1u);
         }
-        total += __syncthreads_count(pass);
     }
-    if (tid == 0) {
-        a.out_counts[q] = total;
-        if (a.stats) atomicAdd(&a.stats->results, (unsigned long long)total);
+    g.sync();
+    if (g.tid == 0) {
+        a.out_counts[w.q] = *s_count;
+        if (a.stats) atomicAdd(&a.stats->results, (unsigned long long)*s_count);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// shared-memory path
+// mbarrier / TMA bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// for waits that are expected to be long: do not burn issue slots the other warps need
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(128);
+}
+// global -> shared bulk copy (16-byte aligned, size multiple of 16), completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// sketch path (class 0)
+// ------------------------------------------------------------------------------------------------
+constexpr int kSkConsumerWarps = 8;
+constexpr int kSkProducerWarps = 4; // all producers fill the same stage: row r is issued by warp r % 4
+constexpr int kSkStages = 2;
+constexpr int kSkThreads = (kSkConsumerWarps + kSkProducerWarps) * 32;
+constexpr int kSkConsumers = kSkConsumerWarps * 32;
+constexpr uint32_t kSketchLog = 14;                          // 16384 u16 counters = 32 KB
+constexpr uint32_t kSketchWords = (1u << kSketchLog) / 2;
+constexpr uint32_t kExSlots = 1024;                          // exact table: at most 512 distinct docids
+constexpr uint32_t kHotCap = kFastKbuf * 2;                  // sketch-hot postings per query (aliases kbuf)
+constexpr size_t kSkSmemBytes = (size_t)kSketchWords * 4 + (size_t)kSkStages * kStageU4 * 16 +
+                                kExSlots * 8 + kFastKbuf * 8;
+
+__device__ __forceinline__ void sketch_add(uint32_t *sketch, uint32_t d, uint32_t pad) {
+    const uint32_t h = (d * kMult) >> (32 - kSketchLog);
+    atomicAdd(sketch + (h >> 1), (d != pad ? 1u : 0u) << ((h & 1u) * 16u));
+}
+__device__ __forceinline__ uint32_t sketch_get(const uint32_t *sketch, uint32_t d) {
+    const uint32_t h = (d * kMult) >> (32 - kSketchLog);
+    return (sketch[h >> 1] >> ((h & 1u) * 16u)) & 0xFFFFu;
+}
+
+__global__ void __launch_bounds__(kSkThreads, 2) search_sketch_kernel(BatchArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t *sketch = reinterpret_cast<uint32_t *>(smem_raw);
+    uint4 *stage = reinterpret_cast<uint4 *>(smem_raw + (size_t)kSketchWords * 4);
+    uint32_t *ex_keys = reinterpret_cast<uint32_t *>(smem_raw + (size_t)kSketchWords * 4 +
+                                                     (size_t)kSkStages * kStageU4 * 16);
+    uint32_t *ex_cnts = ex_keys + kExSlots;
+    unsigned long long *kbuf = reinterpret_cast<unsigned long long *>(ex_cnts + kExSlots);
+    __shared__ uint64_t full[kSkStages], empty[kSkStages];
+    __shared__ WorkItem meta[kSkStages];
+    __shared__ uint32_t s_ncand, s_nkeys, s_ovf, s_count, s_nhot;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t count = a.counters->qcount[kSketchClass];
+    const WorkItem *items = a.items + (size_t)kSketchClass * a.n_queries;
+    const uint32_t pad = a.snap.pad_id;
+
+    if (tid == 0) {
+        for (int s = 0; s < kSkStages; ++s) {
+            mbar_init(&full[s], kSkProducerWarps);
+            mbar_init(&empty[s], 1);
+        }
+        s_ncand = s_nkeys = s_ovf = s_nhot = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < kSkConsumers) {
+        for (uint32_t i = tid; i < kSketchWords / 4; i += kSkConsumers)
+            reinterpret_cast<uint4 *>(sketch)[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = tid; i < kExSlots; i += kSkConsumers) {
+            ex_keys[i] = pad;
+            ex_cnts[i] = 0;
+        }
+    }
+    __syncthreads();
+
+    if (warp >= kSkConsumerWarps) {
+        // ===== producers: TMA bulk copies (UBLKCP) of the query's posting rows into stage it % 2.
+        // Issue is the scarce resource (~70 clk per copy per warp), so the four producer warps split
+        // every query row-wise; each computes all offsets itself, no inter-warp traffic.
+        const uint32_t p = warp - kSkConsumerWarps;
+        const uint4 *docids4 = reinterpret_cast<const uint4 *>(a.snap.docids);
+        for (uint32_t it = 0;; ++it) {
+            const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
+            if (idx >= count) break;
+            const uint32_t s = it % kSkStages;
+            const WorkItem w = items[idx];
+            if (it >= kSkStages) { // wait until the consumers released the previous tenant of this stage
+                if (lane == 0) mbar_wait_relaxed(&empty[s], ((it / kSkStages) - 1) & 1);
+                __syncwarp();
+            }
+            uint4 *dst = stage + (size_t)s * kStageU4;
+            uint32_t base = 0, mine = 0;
+            // first pass over the row descriptors: my byte count (expect_tx must precede my copies)
+            for (uint32_t r0 = 0; r0 < w.n_rows; r0 += 32) {
+                const uint32_t r = r0 + lane;
+                const uint32_t n4 = r < w.n_rows ? (a.rows[w.rows_off + r].y + 3) >> 2 : 0u;
+                mine += (r % kSkProducerWarps == p) ? n4 : 0u;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
+            if (lane == 0) {
+                if (p == 0) meta[s] = w;
+                mbar_expect_tx(&full[s], mine * 16u);
+            }
+            __syncwarp();
+            for (uint32_t r0 = 0; r0 < w.n_rows; r0 += 32) {
+                const uint32_t r = r0 + lane;
+                const uint2 d = r < w.n_rows ? a.rows[w.rows_off + r] : make_uint2(0u, 0u);
+                const uint32_t n4 = (d.y + 3) >> 2;
+                uint32_t x = n4;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                    if (lane >= (uint32_t)o) x += y;
+                }
+                if (n4 && (r % kSkProducerWarps == p)) bulk_g2s(dst + base + x - n4, docids4 + d.x, n4 * 16u, &full[s]);
+                base += __shfl_sync(0xFFFFFFFFu, x, 31);
+            }
+        }
+        return;
+    }
+
+    // ===== consumers
+    const Group g{tid, (uint32_t)kSkConsumers, 1u};
+    for (uint32_t it = 0;; ++it) {
+        const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
+        if (idx >= count) break;
+        const uint32_t s = it % kSkStages;
+        if (warp == 0) { // one poller; everybody else sleeps in the hardware barrier
+            if (lane == 0) mbar_wait(&full[s], (it / kSkStages) & 1);
+            __syncwarp();
+        }
+        g.sync();
+        const WorkItem w = meta[s];
+        const uint4 *st = stage + (size_t)s * kStageU4;
+        const uint32_t thr = w.min_score; // >= 2 in this class
+
+        // pass 1: count sketch, branch-free (padding adds 0).  counter(h) >= true count of every docid
+        // hashing to h, so no qualifying doc can be missed in pass 2.
+        for (uint32_t i = tid; i < w.total4; i += kSkConsumers) {
+            const uint4 v = st[i];
+            sketch_add(sketch, v.x, pad);
+            sketch_add(sketch, v.y, pad);
+            sketch_add(sketch, v.z, pad);
+            sketch_add(sketch, v.w, pad);
+        }
+        g.sync();
+        // pass 2: postings whose counter reaches min_score are compacted into a short list ...
+        uint32_t *hot = reinterpret_cast<uint32_t *>(kbuf); // kFastKbuf*2 u32 entries, free until the harvest
+        for (uint32_t i = tid; i < w.total4; i += kSkConsumers) {
+            const uint4 v = st[i];
+            const uint32_t c0 = sketch_get(sketch, v.x), c1 = sketch_get(sketch, v.y);
+            const uint32_t c2 = sketch_get(sketch, v.z), c3 = sketch_get(sketch, v.w);
+            const uint32_t m = (c0 >= thr ? 1u : 0u) | (c1 >= thr ? 2u : 0u) | (c2 >= thr ? 4u : 0u) | (c3 >= thr ? 8u : 0u);
+            if (m == 0u) continue;
+            uint32_t pos = atomicAdd(&s_nhot, (uint32_t)__popc(m));
+            if ((m & 1u) && pos < kHotCap) hot[pos++] = v.x; else pos += (m & 1u);
+            if ((m & 2u) && pos < kHotCap) hot[pos++] = v.y; else pos += (m >> 1) & 1u;
+            if ((m & 4u) && pos < kHotCap) hot[pos++] = v.z; else pos += (m >> 2) & 1u;
+            if ((m & 8u) && pos < kHotCap) hot[pos] = v.w;
+        }
+        g.sync();
+        if (tid == 0) mbar_arrive(&empty[s]); // stage may be refilled
+        const uint32_t nhot = s_nhot;
+        // ... and counted exactly, all lanes busy (pads never get here: their slot only holds real counts,
+        // and a pad posting itself is filtered below)
+        if (nhot <= kHotCap) {
+            for (uint32_t i = tid; i < nhot; i += kSkConsumers) {
+                const uint32_t d = hot[i];
+                if (d == pad) continue;
+                uint32_t x = (d * kMult2) >> 22;
+                for (uint32_t tries = 0;; ++tries) {
+                    const uint32_t old = atomicCAS(ex_keys + x, pad, d);
+                    if (old == pad) {
+                        if (atomicAdd(&s_nkeys, 1u) >= kExSlots / 2) s_ovf = 1u;
+                    }
+                    if (old == pad || old == d) {
+                        atomicAdd(ex_cnts + x, 1u);
+                        break;
+                    }
+                    x = (x + 1) & (kExSlots - 1);
+                    if (tries >= kExSlots || s_ovf) {
+                        s_ovf = 1u;
+                        break;
+                    }
+                }
+            }
+        } else if (tid == 0) {
+            s_ovf = 1u;
+        }
+        g.sync();
+        // clear the sketch, harvest + clear the exact table
+        for (uint32_t i = tid; i < kSketchWords / 4; i += kSkConsumers)
+            reinterpret_cast<uint4 *>(sketch)[i] = make_uint4(0, 0, 0, 0);
+        if (s_nkeys != 0) {
+            for (uint32_t i = tid; i < kExSlots; i += kSkConsumers) {
+                const uint32_t k = ex_keys[i];
+                if (k == pad) continue;
+                const uint32_t c = ex_cnts[i];
+                ex_keys[i] = pad;
+                ex_cnts[i] = 0;
+                if (c >= thr) {
+                    const uint32_t pos = atomicAdd(&s_ncand, 1u);
+                    if (pos < kFastKbuf) kbuf[pos] = rank_key(c, k);
+                }
+            }
+        }
+        g.sync();
+        const uint32_t n = s_ncand;
+        const bool redo = s_ovf || n > kFastKbuf;
+        if (redo) {
+            // more sketch-hot docids than the exact table holds: the exact count-table path takes the query
+            if (tid == 0) {
+                enqueue(a, exact_class_for(w.postings, w.k_eff), w);
+                if (a.stats) atomicAdd(&a.stats->overflow_requeues, 1ull);
+            }
+        } else if (n == 0) {
+            if (tid == 0) a.out_counts[w.q] = 0;
+        } else {
+            group_sort_keys(g, kbuf, n, kFastKbuf);
+            group_emit_results(g, a, w, kbuf, n, &s_count);
+        }
+        if (tid == 0) {
+            if (a.stats && !redo) atomicAdd(&a.stats->sketch_queries, 1ull);
+        }
+        g.sync();
+        if (tid == 0) s_ncand = s_nkeys = s_ovf = s_nhot = 0;
+        // the next query's first updates of these counters happen after two more group barriers
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact shared-memory path (classes 1..3)
 // ------------------------------------------------------------------------------------------------
 template <int LOG> struct Packed {
     static constexpr int kRemBits = 32 - LOG;
@@ -362,14 +641,15 @@ template <int LOG> constexpr size_t smem_bytes_for() {
 template <int LOG>
 __global__ void __launch_bounds__(kThreads, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))) search_smem_kernel(BatchArgs a) {
     using P = Packed<LOG>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem_raw);
     unsigned long long *kbuf = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)P::kSlots * 4);
     uint2 *rows_s = reinterpret_cast<uint2 *>(smem_raw + (size_t)P::kSlots * 4 + kFastKbuf * 8);
-    __shared__ uint32_t s_idx, s_ncand, s_ovf;
+    __shared__ uint32_t s_idx, s_ncand, s_ovf, s_count;
 
-    constexpr int cls = LOG - 13;
+    constexpr int cls = LOG - 12;
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    const Group g{tid, (uint32_t)kThreads, 0u};
     const uint4 *docids4 = reinterpret_cast<const uint4 *>(a.snap.docids);
     const uint32_t pad = a.snap.pad_id;
     uint4 *tab4 = reinterpret_cast<uint4 *>(tab);
@@ -386,16 +666,17 @@ __global__ void __launch_bounds__(kThreads, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1)
         }
         __syncthreads();
         if (s_idx >= qcount) break;
-        const uint32_t q = a.queues[(size_t)cls * a.n_queries + s_idx];
-        const QueryInfo qi = a.qinfo[q];
-        const SearchOpts o = a.opts[q];
-        const uint32_t thr = max(o.min_score, 1u); // a doc in the table has score >= 1
-        const uint2 *rows = a.rows + (a.term_offsets[q] - a.term_base);
-        const uint32_t pmask = qi.passes - 1u;
+        const WorkItem w = a.items[(size_t)cls * a.n_queries + s_idx];
+        const uint32_t thr = max(w.min_score, 1u); // a doc in the table has score >= 1
+        const uint2 *rows = a.rows + w.rows_off;
+        uint32_t passes = 1;
+        if (LOG == 15)
+            while ((unsigned long long)passes * 12288ull < w.postings && w.postings > 16384u) passes <<= 1;
+        const uint32_t pmask = passes - 1u;
 
-        for (uint32_t pass = 0; pass < qi.passes; ++pass) {
-            for (uint32_t r0 = 0; r0 < qi.n_rows; r0 += kRowsChunk) {
-                const uint32_t nr = min(kRowsChunk, qi.n_rows - r0);
+        for (uint32_t pass = 0; pass < passes; ++pass) {
+            for (uint32_t r0 = 0; r0 < w.n_rows; r0 += kRowsChunk) {
+                const uint32_t nr = min(kRowsChunk, w.n_rows - r0);
                 __syncthreads();
                 for (uint32_t i = tid; i < nr; i += kThreads) rows_s[i] = rows[r0 + i];
                 __syncthreads();
@@ -422,10 +703,10 @@ __global__ void __launch_bounds__(kThreads, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1)
             __syncthreads();
             // scan + clear; candidates are docs with score >= max(min_score,1)  (common.zig:140-145)
             for (uint32_t i = tid; i < P::kSlots / 4; i += kThreads) {
-                const uint4 w = tab4[i];
-                if ((w.x | w.y | w.z | w.w) == 0u) continue;
+                const uint4 wd = tab4[i];
+                if ((wd.x | wd.y | wd.z | wd.w) == 0u) continue;
                 tab4[i] = make_uint4(0, 0, 0, 0);
-                const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+                const uint32_t ws[4] = {wd.x, wd.y, wd.z, wd.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const uint32_t cnt = ws[e] & P::kCntMask;
@@ -441,13 +722,13 @@ __global__ void __launch_bounds__(kThreads, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1)
         if (s_ovf || n > kFastKbuf) {
             // not representable here: hand the query to the global-memory path (still exact)
             if (tid == 0) {
-                a.queues[(size_t)kWideClass * a.n_queries + atomicAdd(&a.counters->qcount[kWideClass], 1u)] = q;
+                enqueue(a, kWideClass, w);
                 if (a.stats) atomicAdd(&a.stats->overflow_requeues, 1ull);
             }
             continue;
         }
-        block_sort_keys(kbuf, n, kFastKbuf);
-        emit_results(a, q, kbuf, n, o);
+        group_sort_keys(g, kbuf, n, kFastKbuf);
+        group_emit_results(g, a, w, kbuf, n, &s_count);
     }
 }
 
@@ -457,10 +738,11 @@ __global__ void __launch_bounds__(kThreads, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1)
 __global__ void __launch_bounds__(kThreads) search_wide_kernel(BatchArgs a) {
     __shared__ unsigned long long kbuf[kWideKbuf];
     __shared__ uint2 rows_s[kRowsChunk];
-    __shared__ uint32_t s_idx, s_kn, s_new, s_fail;
+    __shared__ uint32_t s_idx, s_kn, s_new, s_fail, s_count;
     __shared__ unsigned long long s_kth;
 
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    const Group g{tid, (uint32_t)kThreads, 0u};
     unsigned long long *table = a.wide_tables + ((size_t)blockIdx.x << a.wide_cap_log2);
     const uint4 *docids4 = reinterpret_cast<const uint4 *>(a.snap.docids);
     const uint32_t pad = a.snap.pad_id;
@@ -471,16 +753,14 @@ __global__ void __launch_bounds__(kThreads) search_wide_kernel(BatchArgs a) {
         if (tid == 0) s_idx = atomicAdd(&a.counters->qhead[kWideClass], 1u);
         __syncthreads();
         if (s_idx >= qcount) break;
-        const uint32_t q = a.queues[(size_t)kWideClass * a.n_queries + s_idx];
-        const QueryInfo qi = a.qinfo[q];
-        const SearchOpts o = a.opts[q];
-        const uint32_t thr = max(o.min_score, 1u);
-        const uint32_t k_eff = min(min(o.max_results, a.k_stride), kMaxResults);
-        const uint2 *rows = a.rows + (a.term_offsets[q] - a.term_base);
+        const WorkItem w = a.items[(size_t)kWideClass * a.n_queries + s_idx];
+        const uint32_t thr = max(w.min_score, 1u);
+        const uint32_t k_eff = min(w.k_eff, kMaxResults);
+        const uint2 *rows = a.rows + w.rows_off;
         if (tid == 0 && a.stats) atomicAdd(&a.stats->wide_queries, 1ull);
 
         // table size: aim for load <= 0.25; more hash partitions when one table cannot hold that
-        const unsigned long long need = 4ull * qi.postings;
+        const unsigned long long need = 4ull * w.postings;
         uint32_t passes = 1;
         while ((need / passes) > (1ull << a.wide_cap_log2) && passes < (1u << 16)) passes <<= 1;
         bool done = false;
@@ -502,8 +782,8 @@ __global__ void __launch_bounds__(kThreads) search_wide_kernel(BatchArgs a) {
                     s_fail = 0;
                 }
                 __syncthreads();
-                for (uint32_t r0 = 0; r0 < qi.n_rows; r0 += kRowsChunk) {
-                    const uint32_t nr = min(kRowsChunk, qi.n_rows - r0);
+                for (uint32_t r0 = 0; r0 < w.n_rows; r0 += kRowsChunk) {
+                    const uint32_t nr = min(kRowsChunk, w.n_rows - r0);
                     __syncthreads();
                     for (uint32_t i = tid; i < nr; i += kThreads) rows_s[i] = rows[r0 + i];
                     __syncthreads();
@@ -563,7 +843,7 @@ __global__ void __launch_bounds__(kThreads) search_wide_kernel(BatchArgs a) {
                     __syncthreads();
                     if (s_kn > kWideKbuf - 4 * kThreads) {
                         const uint32_t n = s_kn;
-                        block_sort_keys(kbuf, n, kWideKbuf);
+                        group_sort_keys(g, kbuf, n, kWideKbuf);
                         __syncthreads();
                         if (tid == 0) {
                             s_kn = min(n, k_eff);
@@ -577,7 +857,7 @@ __global__ void __launch_bounds__(kThreads) search_wide_kernel(BatchArgs a) {
                 if (passes >= (1u << 16)) { // cannot happen with < 2^32 postings; fail loudly instead of looping
                     if (tid == 0) {
                         a.counters->error = FPX_UNSUPPORTED_CODE;
-                        a.out_counts[q] = 0;
+                        a.out_counts[w.q] = 0;
                     }
                     done = true;
                     break;
@@ -587,9 +867,9 @@ __global__ void __launch_bounds__(kThreads) search_wide_kernel(BatchArgs a) {
             }
             __syncthreads();
             const uint32_t n = s_kn;
-            block_sort_keys(kbuf, n, kWideKbuf);
+            group_sort_keys(g, kbuf, n, kWideKbuf);
             __syncthreads();
-            emit_results(a, q, kbuf, n, o);
+            group_emit_results(g, a, w, kbuf, n, &s_count);
             done = true;
         }
     }
@@ -607,6 +887,8 @@ cudaError_t configure_kernels() {
     e = cudaFuncSetAttribute(search_smem_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for<14>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_smem_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for<15>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(search_sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
     return e;
 }
 
@@ -630,11 +912,15 @@ void launch_prepare_long(const BatchArgs &a, cudaStream_t st, int n_sms) {
     prepare_long_kernel<<<n_sms, kThreads, 0, st>>>(a);
 }
 
+void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms) {
+    search_sketch_kernel<<<n_sms * 2, kSkThreads, kSkSmemBytes, st>>>(a);
+}
+
 void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms) {
     switch (cls) {
-    case 0: search_smem_kernel<13><<<n_sms * 4, kThreads, smem_bytes_for<13>(), st>>>(a); break;
-    case 1: search_smem_kernel<14><<<n_sms * 3, kThreads, smem_bytes_for<14>(), st>>>(a); break;
-    case 2: search_smem_kernel<15><<<n_sms * 1, kThreads, smem_bytes_for<15>(), st>>>(a); break;
+    case 1: search_smem_kernel<13><<<n_sms * 4, kThreads, smem_bytes_for<13>(), st>>>(a); break;
+    case 2: search_smem_kernel<14><<<n_sms * 3, kThreads, smem_bytes_for<14>(), st>>>(a); break;
+    case 3: search_smem_kernel<15><<<n_sms * 1, kThreads, smem_bytes_for<15>(), st>>>(a); break;
     default: break;
     }
 }

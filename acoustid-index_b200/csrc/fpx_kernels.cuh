@@ -21,21 +21,29 @@ struct SnapshotDev {
     uint32_t pad_id;
 };
 
-struct QueryInfo {
-    uint32_t n_rows;    // unique terms present in the snapshot
-    uint32_t postings;  // sum of row lengths (saturating)
-    uint32_t passes;    // hash partitions needed by the shared-memory path
-    uint32_t reserved;
-};
-
 struct SearchOpts { // == fpx_search_opts
     uint32_t max_results, min_score, min_score_pct;
 };
 
-// Work classes: shared-memory count table of 2^13 / 2^14 / 2^15 slots, and the global-memory path.
-constexpr int kNumClasses = 4;
-constexpr int kWideClass = 3;
-constexpr uint32_t kClassLog[3] = {13, 14, 15};
+// One prepared query, as the search kernels consume it (32 bytes).
+struct WorkItem {
+    uint32_t q;         // query index in the batch
+    uint32_t rows_off;  // first row descriptor in BatchArgs::rows
+    uint32_t n_rows;    // unique query terms present in the snapshot
+    uint32_t total4;    // sum over rows of ceil(len/4): padded posting volume in 16-byte units
+    uint32_t postings;  // sum of row lengths (saturating)
+    uint32_t k_eff;     // min(max_results, k_stride)
+    uint32_t min_score;
+    uint32_t min_score_pct;
+};
+
+// Work classes.
+//   0      sketch path: TMA-staged rows, u16 count sketch + small exact table (needs min_score >= 2)
+//   1..3   exact shared-memory count table of 2^13 / 2^14 / 2^15 packed slots
+//   4      global-memory table: whatever the others cannot represent exactly
+constexpr int kNumClasses = 5;
+constexpr int kSketchClass = 0;
+constexpr int kWideClass = 4;
 
 struct BatchCounters {
     uint32_t qcount[kNumClasses];
@@ -47,7 +55,7 @@ struct BatchCounters {
 };
 
 struct DeviceStats { // accumulated across batches (profiling)
-    unsigned long long queries, unique_terms, postings, results, wide_queries, overflow_requeues;
+    unsigned long long queries, unique_terms, postings, results, wide_queries, overflow_requeues, sketch_queries;
 };
 
 struct BatchArgs {
@@ -61,26 +69,28 @@ struct BatchArgs {
     uint32_t *out_ids, *out_scores, *out_counts;
     // workspace
     uint2 *rows;            // per query at [term_offsets[q]-term_base ...): {start4, len}
-    QueryInfo *qinfo;
-    uint32_t *queues;       // kNumClasses * n_queries
+    WorkItem *items;        // kNumClasses * n_queries
     uint32_t *long_queue;   // n_queries
     BatchCounters *counters;
     DeviceStats *stats;
     unsigned long long *wide_tables; // per wide CTA: wide_cap 64-bit slots
     uint32_t wide_cap_log2;
+    uint32_t use_sketch;    // 0 disables class 0 (A/B testing)
 };
 
 constexpr uint32_t kWarpQueryTerms = 128; // queries up to this many raw terms are prepared by one warp
 constexpr uint32_t kMaxQueryTerms = 8192; // FPX_MAX_QUERY_TERMS
-constexpr uint32_t kFastKbuf = 512;       // candidate buffer of the shared-memory path
+constexpr uint32_t kFastKbuf = 512;       // candidate buffer of the shared-memory paths
 constexpr uint32_t kWideKbuf = 2048;      // candidate buffer of the global-memory path
 constexpr uint32_t kMaxResults = 1024;    // FPX_MAX_RESULTS
 constexpr uint32_t kRowsChunk = 256;      // row descriptors staged per round
+constexpr uint32_t kStageU4 = 2048;       // sketch path: one query's padded rows must fit 32 KB
 
 void launch_build_table(TermEntry *table, uint32_t log2cap, const uint32_t *terms, const uint32_t *lens,
                         const uint32_t *start4, uint64_t n_terms, cudaStream_t st);
 void launch_prepare(const BatchArgs &a, cudaStream_t st);
 void launch_prepare_long(const BatchArgs &a, cudaStream_t st, int n_sms);
+void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms);
 void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms);
 void launch_search_wide(const BatchArgs &a, cudaStream_t st, int n_ctas);
 cudaError_t configure_kernels();

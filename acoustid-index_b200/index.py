@@ -127,9 +127,10 @@ class MemorySegment:
 
 
 class Context:
-    def __init__(self, device=-1, profile=False, host_only=False, host_threads=0, chunk_queries=0):
+    def __init__(self, device=-1, profile=False, host_only=False, host_threads=0, chunk_queries=0, no_sketch=False):
         cfg = _ffi.Config(device, host_threads, chunk_queries,
-                          (_ffi.FPX_FLAG_PROFILE if profile else 0) | (_ffi.FPX_FLAG_HOST_ONLY if host_only else 0))
+                          (_ffi.FPX_FLAG_PROFILE if profile else 0) | (_ffi.FPX_FLAG_HOST_ONLY if host_only else 0) |
+                          (_ffi.FPX_FLAG_NO_SKETCH if no_sketch else 0))
         self.h = C.c_void_p()
         check(lib().fpx_init(C.byref(cfg), C.byref(self.h)))
 

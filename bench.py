@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--impl", default="fpx", choices=["fpx", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sketch", action="store_true", help="A/B: exact count-table kernels only")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -220,7 +221,7 @@ def main():
     del items
     log("[bench] segment: %d blocks written in %.1fs" % (seg.num_blocks, time.time() - t))
     t = time.time()
-    ctx = pkg.Context(device=local_rank, profile=True, host_threads=host_threads)
+    ctx = pkg.Context(device=local_rank, profile=True, host_threads=host_threads, no_sketch=args.no_sketch)
     snap = pkg.swap_snapshot(ctx, [seg])
     info = snap.info()
     log("[bench] snapshot: %d terms, %d postings, %.2f GB in HBM, built in %.1fs"
@@ -318,7 +319,14 @@ def main():
     results = prof["results"] / steps
     search_bytes = 8.0 * rows + 4.0 * postings + 8.0 * results + 4.0 * nq
     path_bytes = 20.0 * rows + 4.0 * postings + 8.0 * results          # SURVEY.md §8d per-query formula
-    search_ms = prof["search_ms"] / steps
+    sketch_share = prof["sketch_queries"] / max(1, prof["queries"])
+    if sketch_share >= 0.5:   # the TMA/sketch kernel answers (nearly) all queries of this workload
+        kernel_name = "search_sketch_kernel (TMA gather + u16 count sketch + exact recount + top-k)"
+        search_ms = prof["sketch_ms"] / steps
+        search_bytes *= sketch_share
+    else:
+        kernel_name = "search_smem_kernel<13|14|15> (gather + exact count table + top-k)"
+        search_ms = prof["search_ms"] / steps
     achieved = search_bytes / (search_ms * 1e-3) / 1e9 if search_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % wl)
@@ -328,8 +336,11 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "search_smem_kernel<14> (gather + count + top-k)",
+                "traffic": traffic, "kernel": kernel_name,
                 "kernel_ms_per_step": search_ms, "algorithmic_bytes_per_step": search_bytes,
+                "sketch_ms_per_step": prof["sketch_ms"] / steps, "exact_ms_per_step": prof["search_ms"] / steps,
+                "sketch_queries_per_step": prof["sketch_queries"] / steps,
+                "overflow_requeues_per_step": prof["overflow_requeues"] / steps,
                 "whole_path_bytes_per_step": path_bytes, "postings_per_step": postings,
                 "prepare_ms_per_step": prof["prepare_ms"] / steps, "wide_ms_per_step": prof["wide_ms"] / steps,
                 "wide_queries_per_step": prof["wide_queries"] / steps, "peak_source": peak_src}
@@ -341,7 +352,7 @@ def main():
         "config": workload_config(wl, "replicated corpus, query batch per GPU x%d" % world),
         "clocks": clocks,
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": 7 * args.steps,
+        "gpu_launches": 7 * args.steps,  # prepare, prepare_long, sketch, 3 exact classes, wide
         "roofline": roofline,
     }
 

@@ -60,6 +60,7 @@ typedef struct fpx_config {
 } fpx_config;
 #define FPX_FLAG_PROFILE 1u    /* record CUDA events around every kernel (fpx_profile_read) */
 #define FPX_FLAG_HOST_ONLY 2u  /* no device: only snapshot compilation / introspection work (CPU tests) */
+#define FPX_FLAG_NO_SKETCH 4u  /* route every query through the exact count-table kernels (A/B testing) */
 
 /* An immutable file segment exactly as FileSegment holds it in RAM (FileSegment.zig:33-53). */
 typedef struct fpx_file_segment {
@@ -119,10 +120,12 @@ typedef struct fpx_csr_view {
 typedef struct fpx_profile {
     /* accumulated since the last fpx_profile_reset, FPX_FLAG_PROFILE only */
     double prepare_ms;  uint64_t prepare_launches;
-    double search_ms;   uint64_t search_launches;   /* the gather+count+top-k kernel(s) */
-    double wide_ms;     uint64_t wide_launches;     /* overflow / oversized queries */
+    double sketch_ms;   uint64_t sketch_launches;   /* search_sketch_kernel: TMA gather + count sketch + top-k */
+    double search_ms;   uint64_t search_launches;   /* search_smem_kernel<13|14|15>: exact count-table path */
+    double wide_ms;     uint64_t wide_launches;     /* search_wide_kernel: overflow / oversized queries */
     double h2d_ms, d2h_ms;
-    uint64_t queries, unique_terms, postings, results, wide_queries;
+    uint64_t queries, unique_terms, postings, results;
+    uint64_t sketch_queries, wide_queries, overflow_requeues;
     uint64_t h2d_bytes, d2h_bytes;
 } fpx_profile;
 

@@ -302,6 +302,31 @@ def test_zipf_hot_postings(ctx):
     snap.release()
 
 
+def test_sketch_and_exact_kernels_agree(ctx, c2):
+    """The TMA/sketch kernel and the exact count-table kernels must give identical answers."""
+    syn, seg, snap, ix = c2
+    terms, _ = syn.queries(3000, 60, seed=321)     # 60 x ~95 postings fits the 32 KB stage of the sketch path
+    nq, T = terms.shape
+    offs = np.arange(nq + 1, dtype=np.uint64) * T
+    ctx2 = pkg.Context(device=0, profile=True, no_sketch=True)
+    snap2 = pkg.swap_snapshot(ctx2, [seg])
+    for opt in ((40, 5, 10), (40, 2, 0), (100, 3, 50), (512, 2, 10)):
+        opts = np.tile(np.array(opt, dtype=np.uint32), (nq, 1))
+        ctx.profile_reset()
+        a = pkg.IndexReader(snap).search_batch(terms.reshape(-1), offs, opts, opt[0])
+        prof = ctx.profile()
+        if opt[1] >= 4:
+            assert prof["sketch_queries"] > 0.9 * nq, prof
+        ctx2.profile_reset()
+        b = pkg.IndexReader(snap2).search_batch(terms.reshape(-1), offs, opts, opt[0])
+        assert ctx2.profile()["sketch_queries"] == 0
+        assert np.array_equal(a[2], b[2])
+        mask = np.arange(opt[0])[None, :] < a[2][:, None]
+        assert np.array_equal(a[0][mask], b[0][mask]) and np.array_equal(a[1][mask], b[1][mask])
+    snap2.release()
+    ctx2.close()
+
+
 def test_device_resident_api_matches_host_api(ctx, c2):
     import torch
     syn, seg, snap, ix = c2
