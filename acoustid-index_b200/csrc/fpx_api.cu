@@ -5,6 +5,7 @@
 // compiled CSR, and the batched search driver (chunked H2D -> kernels -> D2H on rotating streams).
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -115,6 +116,7 @@ struct fpx_ctx {
     uint32_t flags = 0;
     bool host_only = false;
     bool use_sketch = true;
+    uint32_t debug = 0; // FPX_DEBUG_ABLATE environment variable, profiling only
     std::mutex mu;
     std::vector<Workspace *> free_ws;
     DeviceStats *d_stats = nullptr;
@@ -225,6 +227,7 @@ fpx_status enqueue_batch(fpx_snapshot *s, Workspace *w, cudaStream_t st, uint64_
     a.wide_tables = w->wide_tables.p;
     a.wide_cap_log2 = kWideCapLog2;
     a.use_sketch = ctx->use_sketch ? 1u : 0u;
+    a.debug = ctx->debug;
 
     FPX_CUDA(cudaMemsetAsync(w->counters, 0, sizeof(BatchCounters), st));
     {
@@ -270,6 +273,7 @@ fpx_status fpx_init(const fpx_config *config, fpx_ctx **out) {
     if (cfg.chunk_queries) ctx->chunk_queries = cfg.chunk_queries;
     ctx->host_only = (cfg.flags & FPX_FLAG_HOST_ONLY) != 0;
     ctx->use_sketch = (cfg.flags & FPX_FLAG_NO_SKETCH) == 0;
+    if (const char *dbg = std::getenv("FPX_DEBUG_ABLATE")) ctx->debug = (uint32_t)std::strtoul(dbg, nullptr, 0);
     if (!ctx->host_only) {
         int n = 0;
         cudaError_t e = cudaGetDeviceCount(&n);

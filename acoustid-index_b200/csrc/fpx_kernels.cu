@@ -70,21 +70,12 @@ __device__ __forceinline__ void enqueue(const BatchArgs &a, uint32_t cls, const 
     a.items[(size_t)cls * a.n_queries + pos] = w;
 }
 
-// Bin a prepared query (called by one thread).
-__device__ void classify_and_enqueue(const BatchArgs &a, uint32_t q, uint32_t rows_off, uint32_t n_rows,
-                                     unsigned long long postings, unsigned long long total4, uint32_t n_unique) {
+// Decide how a prepared query is answered.  Returns the class, or kNumClasses when the answer is already
+// known to be empty (no term present / limit 0).
+__device__ uint32_t make_item(const BatchArgs &a, uint32_t q, uint32_t rows_off, uint32_t n_rows,
+                              unsigned long long postings, unsigned long long total4, WorkItem &w) {
     const SearchOpts o = a.opts[q];
     const uint32_t k_eff = min(o.max_results, a.k_stride);
-    if (a.stats) {
-        atomicAdd(&a.stats->queries, 1ull);
-        atomicAdd(&a.stats->unique_terms, (unsigned long long)n_unique);
-        atomicAdd(&a.stats->postings, postings);
-    }
-    if (n_rows == 0 || k_eff == 0) {
-        a.out_counts[q] = 0;
-        return;
-    }
-    WorkItem w;
     w.q = q;
     w.rows_off = rows_off;
     w.n_rows = n_rows;
@@ -93,18 +84,32 @@ __device__ void classify_and_enqueue(const BatchArgs &a, uint32_t q, uint32_t ro
     w.k_eff = k_eff;
     w.min_score = o.min_score;
     w.min_score_pct = o.min_score_pct;
-    uint32_t cls;
+    if (n_rows == 0 || k_eff == 0) return kNumClasses;
     // The sketch path needs min_score >= 2 (it only recounts docids whose sketch counter reaches
     // min_score) and the query must fit one 32 KB stage.  With a low floor and many postings nearly every
     // counter is "hot" and the recount list would overflow, so those go to the exact count-table path.
-    bool sketch_ok = a.use_sketch && o.min_score >= 2 && total4 <= kStageU4 && k_eff <= kFastKbuf;
-    if (o.min_score == 2 && postings > 2048) sketch_ok = false;
-    if (o.min_score == 3 && postings > 5000) sketch_ok = false;
-    if (sketch_ok)
-        cls = kSketchClass;
+    bool sketch_ok = a.use_sketch && o.min_score >= 2 && total4 <= kStageU4 && k_eff <= kFastKbuf &&
+                     n_rows <= kSketchMaxRows;
+    // expected records = postings that find their counter already at min_score-1 (Poisson, 16384 counters)
+    if (o.min_score == 2 && postings > 1500) sketch_ok = false;
+    if (o.min_score == 3 && postings > 4500) sketch_ok = false;
+    return sketch_ok ? (uint32_t)kSketchClass : exact_class_for(postings, k_eff);
+}
+
+// Bin a prepared query (called by one thread).
+__device__ void classify_and_enqueue(const BatchArgs &a, uint32_t q, uint32_t rows_off, uint32_t n_rows,
+                                     unsigned long long postings, unsigned long long total4, uint32_t n_unique) {
+    if (a.stats) {
+        atomicAdd(&a.stats->queries, 1ull);
+        atomicAdd(&a.stats->unique_terms, (unsigned long long)n_unique);
+        atomicAdd(&a.stats->postings, postings);
+    }
+    WorkItem w;
+    const uint32_t cls = make_item(a, q, rows_off, n_rows, postings, total4, w);
+    if (cls == kNumClasses)
+        a.out_counts[q] = 0;
     else
-        cls = exact_class_for(postings, k_eff);
-    enqueue(a, cls, w);
+        enqueue(a, cls, w);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -132,8 +137,31 @@ __global__ void build_table_kernel(TermEntry *table, uint32_t mask, uint32_t shi
 // prepare: Index.zig:171-172 (sort + dedupSorted => the query is a SET) + term -> row lookup
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) prepare_kernel(BatchArgs a) {
+    __shared__ uint32_t s_set[kWarps][256]; // per-warp hash set for de-duplication (<= 128 terms, load <= 0.5)
     const uint32_t lane = lane_id();
+    uint32_t *set = s_set[threadIdx.x >> 5];
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    // lane i parks the work item of the i-th query this warp prepared; they are enqueued 32 at a time
+    WorkItem mine{};
+    uint32_t mine_cls = kNumClasses, n_parked = 0;
+    unsigned long long st_q = 0, st_unique = 0, st_post = 0; // lane 0: statistics
+
+    auto flush = [&]() {
+#pragma unroll
+        for (uint32_t c = 0; c < (uint32_t)kNumClasses; ++c) {
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine_cls == c);
+            if (m == 0u) continue;
+            const uint32_t leader = __ffs(m) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&a.counters->qcount[c], (uint32_t)__popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (mine_cls == c) a.items[(size_t)c * a.n_queries + base + __popc(m & lt_mask)] = mine;
+        }
+        mine_cls = kNumClasses;
+        n_parked = 0;
+    };
+
     for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < a.n_queries; q += warps_total) {
         const unsigned long long o0 = a.term_offsets[q] - a.term_base;
         const unsigned long long T64 = a.term_offsets[q + 1] - a.term_offsets[q];
@@ -157,38 +185,57 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(BatchArgs a) {
             live[j] = idx < T;
             t[j] = live[j] ? __ldg(a.terms + o0 + idx) : 0u;
         }
-        // drop later duplicates (the reference dedups after sorting; order is irrelevant to the result)
+        // The query is a set (Index.zig:171-172 sorts and dedups): drop repeats with a small hash set.
+        // Slot value 0 means empty, so the term 0 is handled by a ballot instead.
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            if (jj * 32u >= T) break;
-            for (uint32_t l = 0; l < 32; ++l) {
-                const uint32_t s = jj * 32 + l;
-                if (s >= T) break;
-                const uint32_t v = __shfl_sync(0xFFFFFFFFu, t[jj], l);
+        for (int j = 0; j < 8; ++j) set[lane + 32 * j] = 0u;
+        __syncwarp();
+        bool zero_seen = false;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (live[j] && s < lane + 32u * j && v == t[j]) live[j] = false;
+        for (int j = 0; j < 4; ++j) {
+            const bool is_zero = live[j] && t[j] == 0u;
+            const uint32_t zm = __ballot_sync(0xFFFFFFFFu, is_zero);
+            if (is_zero && (zero_seen || (zm & lt_mask))) live[j] = false;
+            zero_seen = zero_seen || zm != 0u;
+            if (live[j] && t[j] != 0u) {
+                uint32_t h = (t[j] * kMult) >> 24;
+                for (;;) {
+                    const uint32_t old = atomicCAS(set + h, 0u, t[j]);
+                    if (old == 0u) break;
+                    if (old == t[j]) {
+                        live[j] = false;
+                        break;
+                    }
+                    h = (h + 1) & 255u;
+                }
             }
+        }
+        __syncwarp();
+        // term directory: issue the first probe of all four lookups before looking at any of them
+        uint32_t h[4];
+        uint4 e[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            h[j] = (t[j] * kMult) >> a.snap.table_shift;
+            e[j] = make_uint4(0, 0, 0, 0);
+            if (live[j]) e[j] = __ldg(reinterpret_cast<const uint4 *>(a.snap.table + h[j]));
         }
         uint32_t n_unique = 0, n_rows = 0;
         unsigned long long postings = 0, total4 = 0;
-        uint32_t st[4], ln[4];
-        bool found[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            st[j] = ln[j] = 0;
-            found[j] = live[j] && directory_lookup(a.snap, t[j], st[j], ln[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
+            while (e[j].w != 0u && e[j].x != t[j]) { // linear probing; an empty slot ends the search
+                h[j] = (h[j] + 1) & a.snap.table_mask;
+                e[j] = __ldg(reinterpret_cast<const uint4 *>(a.snap.table + h[j]));
+            }
+            const bool found = live[j] && e[j].w != 0u;
             const uint32_t um = __ballot_sync(0xFFFFFFFFu, live[j]);
-            const uint32_t fm = __ballot_sync(0xFFFFFFFFu, found[j]);
+            const uint32_t fm = __ballot_sync(0xFFFFFFFFu, found);
             n_unique += __popc(um);
-            if (found[j]) {
-                const uint32_t pos = n_rows + __popc(fm & ((1u << lane) - 1u));
-                a.rows[o0 + pos] = make_uint2(st[j], ln[j]);
-                postings += ln[j];
-                total4 += (ln[j] + 3) >> 2;
+            if (found) {
+                a.rows[o0 + n_rows + __popc(fm & lt_mask)] = make_uint2(e[j].z, e[j].y);
+                postings += e[j].y;
+                total4 += (e[j].y + 3) >> 2;
             }
             n_rows += __popc(fm);
         }
@@ -197,7 +244,28 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(BatchArgs a) {
             postings += __shfl_xor_sync(0xFFFFFFFFu, postings, off);
             total4 += __shfl_xor_sync(0xFFFFFFFFu, total4, off);
         }
-        if (lane == 0) classify_and_enqueue(a, q, (uint32_t)o0, n_rows, postings, total4, n_unique);
+        // every lane computes the (identical) work item; lane n_parked keeps it
+        WorkItem w;
+        const uint32_t cls = make_item(a, q, (uint32_t)o0, n_rows, postings, total4, w);
+        if (lane == 0) {
+            st_q += 1;
+            st_unique += n_unique;
+            st_post += postings;
+            if (cls == kNumClasses) a.out_counts[q] = 0;
+        }
+        if (cls != kNumClasses) {
+            if (lane == n_parked) {
+                mine = w;
+                mine_cls = cls;
+            }
+            if (++n_parked == 32) flush();
+        }
+    }
+    flush();
+    if (lane == 0 && a.stats && st_q) {
+        atomicAdd(&a.stats->queries, st_q);
+        atomicAdd(&a.stats->unique_terms, st_unique);
+        atomicAdd(&a.stats->postings, st_post);
     }
 }
 
@@ -348,11 +416,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the thread is parked by the hardware until the phase completes (or
+// the hint expires) instead of spinning — spinning lanes would steal issue slots from the ALU-bound counters.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok = 0;
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
                  : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
                  : "memory");
     return ok != 0;
 }
@@ -360,10 +430,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
-// for waits that are expected to be long: do not burn issue slots the other warps need
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(128);
-}
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) { mbar_wait(bar, parity); }
 // global -> shared bulk copy (16-byte aligned, size multiple of 16), completion counted on `bar`
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -373,40 +440,56 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 
 // ------------------------------------------------------------------------------------------------
-// sketch path (class 0)
+// sketch path (class 0): two persistent CTAs per SM, three warp roles each
+//   producers (4 warps)  TMA bulk copies (cp.async.bulk, mbarrier complete_tx) of the query's posting rows
+//                        into one of two 32 KB shared-memory stages, one query ahead of the counters
+//   counters  (8 warps)  scatter-add every staged docid into a 16384 x u16 count sketch with shared
+//                        atomics.  The add returns the counter's previous value; a posting that finds
+//                        its counter already at min_score-1 or more records its docid as a candidate.
+//                        Then the (few) distinct candidates are counted exactly by binary search in the
+//                        staged rows, which are sorted by docid.
+//   ranker    (1 warp)   ranks the candidates, applies the reference's cutoffs, writes the results — while
+//                        the counters already work on the next query
+// Two CTAs share an SM so that one CTA's latency-bound phases overlap the other's ALU-bound counting.
+// Why this is exact: a counter holds the sum of the true counts of all docids hashing to it and only grows
+// by one per posting.  If doc d has c >= min_score postings in the query, at most min_score-1 of them can
+// be among the first min_score-1 arrivals at its counter, so at least one posting of d arrives when the
+// counter is already >= min_score-1 and d is recorded.  Its exact count is then taken from the rows.
+// The kernel is bound by the integer ALU, not by memory, so everything per posting is kept minimal.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSkConsumerWarps = 8;
-constexpr int kSkProducerWarps = 4; // all producers fill the same stage: row r is issued by warp r % 4
+constexpr int kSkCounterWarps = 8;
+constexpr int kSkProducerWarps = 4; // row r of a query is issued by producer warp r % 4
 constexpr int kSkStages = 2;
-constexpr int kSkThreads = (kSkConsumerWarps + kSkProducerWarps) * 32;
-constexpr int kSkConsumers = kSkConsumerWarps * 32;
-constexpr uint32_t kSketchLog = 14;                          // 16384 u16 counters = 32 KB
+constexpr int kSkRankerWarp = kSkCounterWarps;
+constexpr int kSkFirstProducer = kSkCounterWarps + 1;
+constexpr int kSkThreads = (kSkCounterWarps + 1 + kSkProducerWarps) * 32;
+constexpr int kSkCounters = kSkCounterWarps * 32;
+constexpr uint32_t kSketchLog = 14;       // 16384 u16 counters, two per 32-bit word = 32 KB
 constexpr uint32_t kSketchWords = (1u << kSketchLog) / 2;
-constexpr uint32_t kExSlots = 1024;                          // exact table: at most 512 distinct docids
-constexpr uint32_t kHotCap = kFastKbuf * 2;                  // sketch-hot postings per query (aliases kbuf)
-constexpr size_t kSkSmemBytes = (size_t)kSketchWords * 4 + (size_t)kSkStages * kStageU4 * 16 +
-                                kExSlots * 8 + kFastKbuf * 8;
+constexpr uint32_t kRecCap = 512;         // candidate records per query (with repeats)
+constexpr uint32_t kSetSlots = 64;        // distinct-candidate hash set
+constexpr uint32_t kMaxCand = 32;         // distinct candidates handled here; more -> exact count-table path
+constexpr size_t kSkSmemBytes = (size_t)kSketchWords * 4 + (size_t)kSkStages * kStageU4 * 16 + kRecCap * 4;
 
-__device__ __forceinline__ void sketch_add(uint32_t *sketch, uint32_t d, uint32_t pad) {
-    const uint32_t h = (d * kMult) >> (32 - kSketchLog);
-    atomicAdd(sketch + (h >> 1), (d != pad ? 1u : 0u) << ((h & 1u) * 16u));
-}
-__device__ __forceinline__ uint32_t sketch_get(const uint32_t *sketch, uint32_t d) {
-    const uint32_t h = (d * kMult) >> (32 - kSketchLog);
-    return (sketch[h >> 1] >> ((h & 1u) * 16u)) & 0xFFFFu;
-}
+struct StageMeta {
+    WorkItem item;
+    uint32_t row_off[kSketchMaxRows]; // first docid of row r inside the stage
+    uint32_t row_len[kSketchMaxRows]; // postings in row r (without padding)
+};
 
 __global__ void __launch_bounds__(kSkThreads, 2) search_sketch_kernel(BatchArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint32_t *sketch = reinterpret_cast<uint32_t *>(smem_raw);
+    unsigned char *sketch_b = smem_raw;
     uint4 *stage = reinterpret_cast<uint4 *>(smem_raw + (size_t)kSketchWords * 4);
-    uint32_t *ex_keys = reinterpret_cast<uint32_t *>(smem_raw + (size_t)kSketchWords * 4 +
-                                                     (size_t)kSkStages * kStageU4 * 16);
-    uint32_t *ex_cnts = ex_keys + kExSlots;
-    unsigned long long *kbuf = reinterpret_cast<unsigned long long *>(ex_cnts + kExSlots);
-    __shared__ uint64_t full[kSkStages], empty[kSkStages];
-    __shared__ WorkItem meta[kSkStages];
-    __shared__ uint32_t s_ncand, s_nkeys, s_ovf, s_count, s_nhot;
+    uint32_t *rec = reinterpret_cast<uint32_t *>(smem_raw + (size_t)kSketchWords * 4 + (size_t)kSkStages * kStageU4 * 16);
+    __shared__ uint64_t full[kSkStages], empty[kSkStages], rank_full[2], rank_empty[2];
+    __shared__ StageMeta meta[kSkStages];
+    __shared__ uint32_t s_nrec, s_nset, s_ovf, s_known;
+    __shared__ uint32_t set_keys[kSetSlots];
+    __shared__ uint32_t r_ids[2][kMaxCand], r_cnts[2][kMaxCand], r_n[2], r_redo[2];
+    __shared__ WorkItem r_item[2];
+    __shared__ unsigned long long r_keys[kMaxCand];
+    __shared__ uint32_t r_count;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t count = a.counters->qcount[kSketchClass];
@@ -418,172 +501,274 @@ __global__ void __launch_bounds__(kSkThreads, 2) search_sketch_kernel(BatchArgs 
             mbar_init(&full[s], kSkProducerWarps);
             mbar_init(&empty[s], 1);
         }
-        s_ncand = s_nkeys = s_ovf = s_nhot = 0;
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&rank_full[b], 1);
+            mbar_init(&rank_empty[b], 1);
+        }
+        s_nrec = s_nset = s_ovf = 0;
+        s_known = a.snap.pad_id;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < kSkConsumers) {
-        for (uint32_t i = tid; i < kSketchWords / 4; i += kSkConsumers)
-            reinterpret_cast<uint4 *>(sketch)[i] = make_uint4(0, 0, 0, 0);
-        for (uint32_t i = tid; i < kExSlots; i += kSkConsumers) {
-            ex_keys[i] = pad;
-            ex_cnts[i] = 0;
-        }
+    if (tid < kSkCounters) {
+        for (uint32_t i = tid; i < kSketchWords / 4; i += kSkCounters)
+            reinterpret_cast<uint4 *>(sketch_b)[i] = make_uint4(0, 0, 0, 0);
+        if (tid < kSetSlots) set_keys[tid] = pad;
     }
     __syncthreads();
 
-    if (warp >= kSkConsumerWarps) {
-        // ===== producers: TMA bulk copies (UBLKCP) of the query's posting rows into stage it % 2.
-        // Issue is the scarce resource (~70 clk per copy per warp), so the four producer warps split
-        // every query row-wise; each computes all offsets itself, no inter-warp traffic.
-        const uint32_t p = warp - kSkConsumerWarps;
+    if (warp >= kSkFirstProducer) {
+        // ===== producers.  Issue is the scarce resource (~70 clk per bulk copy per warp), so the four warps
+        // split every query row-wise; each computes all offsets itself from row descriptors it holds in
+        // registers (4 per lane).  Work items are fetched two queries ahead and row descriptors one query
+        // ahead, so neither dependent global load sits on the critical path.
+        const uint32_t p = warp - kSkFirstProducer;
         const uint4 *docids4 = reinterpret_cast<const uint4 *>(a.snap.docids);
-        for (uint32_t it = 0;; ++it) {
+        auto item_at = [&](uint32_t it, WorkItem &w) -> bool {
             const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
-            if (idx >= count) break;
+            if (idx >= count) return false;
+            w = items[idx];
+            return true;
+        };
+        auto rows_of = [&](const WorkItem &w, uint2 (&d)[4]) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t r = lane + 32 * j;
+                d[j] = r < w.n_rows ? a.rows[w.rows_off + r] : make_uint2(0u, 0u);
+            }
+        };
+        WorkItem w{}, w1{}, w2{};
+        uint2 d[4], d1[4];
+        bool have = item_at(0, w), have1 = item_at(1, w1);
+        if (have) rows_of(w, d);
+        for (uint32_t it = 0; have; ++it) {
             const uint32_t s = it % kSkStages;
-            const WorkItem w = items[idx];
-            if (it >= kSkStages) { // wait until the consumers released the previous tenant of this stage
+            if (have1) rows_of(w1, d1);               // rows of query it+1
+            const bool have2 = item_at(it + 2, w2);   // item of query it+2
+            if (it >= kSkStages) { // wait until the counters released the previous tenant of this stage
                 if (lane == 0) mbar_wait_relaxed(&empty[s], ((it / kSkStages) - 1) & 1);
                 __syncwarp();
             }
             uint4 *dst = stage + (size_t)s * kStageU4;
-            uint32_t base = 0, mine = 0;
-            // first pass over the row descriptors: my byte count (expect_tx must precede my copies)
-            for (uint32_t r0 = 0; r0 < w.n_rows; r0 += 32) {
-                const uint32_t r = r0 + lane;
-                const uint32_t n4 = r < w.n_rows ? (a.rows[w.rows_off + r].y + 3) >> 2 : 0u;
-                mine += (r % kSkProducerWarps == p) ? n4 : 0u;
-            }
+            uint32_t off[4], n4[4], base = 0, mine = 0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
-            if (lane == 0) {
-                if (p == 0) meta[s] = w;
-                mbar_expect_tx(&full[s], mine * 16u);
-            }
-            __syncwarp();
-            for (uint32_t r0 = 0; r0 < w.n_rows; r0 += 32) {
-                const uint32_t r = r0 + lane;
-                const uint2 d = r < w.n_rows ? a.rows[w.rows_off + r] : make_uint2(0u, 0u);
-                const uint32_t n4 = (d.y + 3) >> 2;
-                uint32_t x = n4;
+            for (int j = 0; j < 4; ++j) {
+                n4[j] = (d[j].y + 3) >> 2;
+                uint32_t x = n4[j];
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
                     if (lane >= (uint32_t)o) x += y;
                 }
-                if (n4 && (r % kSkProducerWarps == p)) bulk_g2s(dst + base + x - n4, docids4 + d.x, n4 * 16u, &full[s]);
+                off[j] = base + x - n4[j];
                 base += __shfl_sync(0xFFFFFFFFu, x, 31);
+                mine += (lane % kSkProducerWarps == p) ? n4[j] : 0u; // (lane + 32 j) % 4 == lane % 4
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
+            if (p == 0) { // stage directory for the exact recount
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    meta[s].row_off[lane + 32 * j] = off[j] * 4u;
+                    meta[s].row_len[lane + 32 * j] = d[j].y;
+                }
+                if (lane == 0) meta[s].item = w;
+            }
+            if (a.debug & 8u) mine = 0;
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(&full[s], mine * 16u); // expect_tx precedes my copies (release)
+            __syncwarp();
+            if (!(a.debug & 8u)) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n4[j] && (lane % kSkProducerWarps == p))
+                        bulk_g2s(dst + off[j], docids4 + d[j].x, n4[j] * 16u, &full[s]);
+            }
+            have = have1;
+            have1 = have2;
+            w = w1;
+            w1 = w2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = d1[j];
         }
         return;
     }
 
-    // ===== consumers
-    const Group g{tid, (uint32_t)kSkConsumers, 1u};
+    if (warp == kSkRankerWarp) {
+        // ===== ranker: candidates -> (score desc, id asc), cutoffs, result write-out
+        const Group g{lane, 32u, 2u};
+        for (uint32_t it = 0;; ++it) {
+            const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
+            if (idx >= count) break;
+            const uint32_t b = it & 1u;
+            if (lane == 0) mbar_wait(&rank_full[b], (it >> 1) & 1);
+            __syncwarp();
+            const WorkItem w = r_item[b];
+            const uint32_t nc = r_n[b];
+            const bool redo = r_redo[b] != 0u;
+            uint32_t n = 0;
+            if (!redo) {
+                const bool keep = lane < nc && r_cnts[b][lane] >= w.min_score; // common.zig:140-145
+                const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+                if (keep) r_keys[__popc(km & ((1u << lane) - 1u))] = rank_key(r_cnts[b][lane], r_ids[b][lane]);
+                n = __popc(km);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&rank_empty[b]); // the counters may reuse this hand-over buffer
+            if (redo) {
+                // too many candidates for this path: the exact count-table kernels take the query
+                if (lane == 0) {
+                    enqueue(a, exact_class_for(w.postings, w.k_eff), w);
+                    if (a.stats) atomicAdd(&a.stats->overflow_requeues, 1ull);
+                }
+            } else if (n == 0) {
+                if (lane == 0) a.out_counts[w.q] = 0;
+            } else {
+                group_sort_keys(g, r_keys, n, kMaxCand);
+                group_emit_results(g, a, w, r_keys, n, &r_count);
+            }
+            if (lane == 0 && a.stats && !redo) atomicAdd(&a.stats->sketch_queries, 1ull);
+            __syncwarp();
+        }
+        return;
+    }
+
+    // ===== counters
+    const Group g{tid, (uint32_t)kSkCounters, 1u};
     for (uint32_t it = 0;; ++it) {
         const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
         if (idx >= count) break;
-        const uint32_t s = it % kSkStages;
+        const uint32_t s = it % kSkStages, b = it & 1u;
         if (warp == 0) { // one poller; everybody else sleeps in the hardware barrier
             if (lane == 0) mbar_wait(&full[s], (it / kSkStages) & 1);
             __syncwarp();
         }
         g.sync();
-        const WorkItem w = meta[s];
+        const uint32_t total4 = meta[s].item.total4, n_rows = meta[s].item.n_rows;
+        const uint32_t thr_m1 = meta[s].item.min_score - 1u; // min_score >= 2 in this class
         const uint4 *st = stage + (size_t)s * kStageU4;
-        const uint32_t thr = w.min_score; // >= 2 in this class
+        // "either 16-bit half >= thr_m1" in two ALU ops: add (0x8000 - thr_m1) to both halves, test bit 15
+        // of each (counts stay below 8192, so nothing carries across).  A min_score above 32768 can never be
+        // reached by <= 8192 postings: bias 0 then never fires.
+        const uint32_t bias = thr_m1 < 0x8000u ? (0x8000u - thr_m1) * 0x10001u : 0u;
 
-        // pass 1: count sketch, branch-free (padding adds 0).  counter(h) >= true count of every docid
-        // hashing to h, so no qualifying doc can be missed in pass 2.
-        for (uint32_t i = tid; i < w.total4; i += kSkConsumers) {
-            const uint4 v = st[i];
-            sketch_add(sketch, v.x, pad);
-            sketch_add(sketch, v.y, pad);
-            sketch_add(sketch, v.z, pad);
-            sketch_add(sketch, v.w, pad);
+        // pass 1: count sketch, two 16-bit counters per word.  All four adds of a 16-byte granule are issued
+        // before any result is used.  A pad adds 0 and is never recorded.
+        if (!(a.debug & 1u)) {
+#pragma unroll 2
+            for (uint32_t i = tid; i < total4; i += kSkCounters) {
+                const uint4 v = st[i];
+                const uint32_t dd[4] = {v.x, v.y, v.z, v.w};
+                uint32_t sh[4], oo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t hv = dd[e] * kMult;
+                    sh[e] = (hv >> 14) & 16u;                    // hash bit 18 selects the half
+                    oo[e] = atomicAdd(reinterpret_cast<uint32_t *>(sketch_b + ((hv >> 17) & 0x7FFCu)),
+                                      (dd[e] != pad ? 1u : 0u) << sh[e]);
+                }
+                const uint32_t hit = ((oo[0] + bias) | (oo[1] + bias) | (oo[2] + bias) | (oo[3] + bias)) & 0x80008000u;
+                if (hit) { // some counter in one of the four words was already at min_score-1
+                    // The true match triggers this once per matching row; after its first record the docid
+                    // is "known" and the later ones leave right away (a stale s_known only costs a repeat).
+                    const uint32_t known = s_known;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (dd[e] != known && ((oo[e] >> sh[e]) & 0xFFFFu) >= thr_m1 && dd[e] != pad) {
+                            const uint32_t p = atomicAdd(&s_nrec, 1u);
+                            if (p < kRecCap) rec[p] = dd[e];
+                            s_known = dd[e];
+                        }
+                }
+            }
         }
         g.sync();
-        // pass 2: postings whose counter reaches min_score are compacted into a short list ...
-        uint32_t *hot = reinterpret_cast<uint32_t *>(kbuf); // kFastKbuf*2 u32 entries, free until the harvest
-        for (uint32_t i = tid; i < w.total4; i += kSkConsumers) {
-            const uint4 v = st[i];
-            const uint32_t c0 = sketch_get(sketch, v.x), c1 = sketch_get(sketch, v.y);
-            const uint32_t c2 = sketch_get(sketch, v.z), c3 = sketch_get(sketch, v.w);
-            const uint32_t m = (c0 >= thr ? 1u : 0u) | (c1 >= thr ? 2u : 0u) | (c2 >= thr ? 4u : 0u) | (c3 >= thr ? 8u : 0u);
-            if (m == 0u) continue;
-            uint32_t pos = atomicAdd(&s_nhot, (uint32_t)__popc(m));
-            if ((m & 1u) && pos < kHotCap) hot[pos++] = v.x; else pos += (m & 1u);
-            if ((m & 2u) && pos < kHotCap) hot[pos++] = v.y; else pos += (m >> 1) & 1u;
-            if ((m & 4u) && pos < kHotCap) hot[pos++] = v.z; else pos += (m >> 2) & 1u;
-            if ((m & 8u) && pos < kHotCap) hot[pos] = v.w;
-        }
-        g.sync();
-        if (tid == 0) mbar_arrive(&empty[s]); // stage may be refilled
-        const uint32_t nhot = s_nhot;
-        // ... and counted exactly, all lanes busy (pads never get here: their slot only holds real counts,
-        // and a pad posting itself is filtered below)
-        if (nhot <= kHotCap) {
-            for (uint32_t i = tid; i < nhot; i += kSkConsumers) {
-                const uint32_t d = hot[i];
-                if (d == pad) continue;
-                uint32_t x = (d * kMult2) >> 22;
-                for (uint32_t tries = 0;; ++tries) {
-                    const uint32_t old = atomicCAS(ex_keys + x, pad, d);
-                    if (old == pad) {
-                        if (atomicAdd(&s_nkeys, 1u) >= kExSlots / 2) s_ovf = 1u;
+        const uint32_t nrec = (a.debug & 2u) ? 0u : s_nrec;
+        // the sketch is no longer needed: clear it for the next query
+        if (!(a.debug & 16u))
+            for (uint32_t i = tid; i < kSketchWords / 4; i += kSkCounters)
+                reinterpret_cast<uint4 *>(sketch_b)[i] = make_uint4(0, 0, 0, 0);
+        if (nrec != 0u) {
+            // distinct candidates (the true match is recorded about once per matching row)
+            if (nrec <= kRecCap) {
+                for (uint32_t i = tid; i < nrec; i += kSkCounters) {
+                    const uint32_t d = rec[i];
+                    uint32_t x = (d * kMult2) >> 26;
+                    for (uint32_t tries = 0;; ++tries) {
+                        const uint32_t old = atomicCAS(set_keys + x, pad, d);
+                        if (old == pad) {
+                            if (atomicAdd(&s_nset, 1u) >= kMaxCand) s_ovf = 1u;
+                            break;
+                        }
+                        if (old == d) break;
+                        x = (x + 1) & (kSetSlots - 1);
+                        if (tries >= kSetSlots || s_ovf) {
+                            s_ovf = 1u;
+                            break;
+                        }
                     }
-                    if (old == pad || old == d) {
-                        atomicAdd(ex_cnts + x, 1u);
-                        break;
+                }
+            } else if (tid == 0) {
+                s_ovf = 1u;
+            }
+            g.sync();
+            // warp 0 compacts the set straight into the ranker's hand-over buffer (and resets the set)
+            if (tid < 32) {
+                if (it >= 2 && lane == 0) mbar_wait(&rank_empty[b], ((it >> 1) - 1) & 1);
+                __syncwarp();
+                uint32_t nc = 0;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t k = set_keys[lane + 32 * half];
+                    const bool occ = k != pad;
+                    const uint32_t om = __ballot_sync(0xFFFFFFFFu, occ);
+                    const uint32_t pos = nc + __popc(om & ((1u << lane) - 1u));
+                    if (occ && pos < kMaxCand) {
+                        r_ids[b][pos] = k;
+                        r_cnts[b][pos] = 0;
                     }
-                    x = (x + 1) & (kExSlots - 1);
-                    if (tries >= kExSlots || s_ovf) {
-                        s_ovf = 1u;
-                        break;
+                    nc += __popc(om);
+                    set_keys[lane + 32 * half] = pad;
+                }
+                if (lane == 0) {
+                    r_n[b] = min(nc, kMaxCand);
+                    r_redo[b] = s_ovf;
+                }
+            }
+            g.sync();
+            if (!s_ovf) {
+                // exact recount: every (candidate, row) pair is an equal-range search in a sorted row
+                const uint32_t *stw = reinterpret_cast<const uint32_t *>(st);
+                const uint32_t nc = r_n[b];
+                for (uint32_t r = tid; r < nc * 128u; r += kSkCounters) { // 128 = kSketchMaxRows
+                    const uint32_t c = r >> 7, row_i = r & 127u;
+                    if (row_i >= n_rows) continue;
+                    const uint32_t d = r_ids[b][c];
+                    const uint32_t *row = stw + meta[s].row_off[row_i];
+                    const uint32_t len = meta[s].row_len[row_i];
+                    // lower bound by halving steps (no data-dependent branches): lo = #elements < d
+                    uint32_t lo = 0;
+                    for (uint32_t step = 1u << (31 - __clz(len | 1u)); step; step >>= 1) {
+                        const uint32_t probe = lo + step;
+                        if (probe <= len && row[probe - 1] < d) lo = probe;
                     }
+                    uint32_t m = 0;
+                    while (lo + m < len && row[lo + m] == d) ++m; // repeated (hash, id) pairs all count
+                    if (m) atomicAdd(&r_cnts[b][c], m);
                 }
             }
         } else if (tid == 0) {
-            s_ovf = 1u;
+            if (it >= 2) mbar_wait(&rank_empty[b], ((it >> 1) - 1) & 1);
+            r_n[b] = 0;
+            r_redo[b] = 0;
         }
         g.sync();
-        // clear the sketch, harvest + clear the exact table
-        for (uint32_t i = tid; i < kSketchWords / 4; i += kSkConsumers)
-            reinterpret_cast<uint4 *>(sketch)[i] = make_uint4(0, 0, 0, 0);
-        if (s_nkeys != 0) {
-            for (uint32_t i = tid; i < kExSlots; i += kSkConsumers) {
-                const uint32_t k = ex_keys[i];
-                if (k == pad) continue;
-                const uint32_t c = ex_cnts[i];
-                ex_keys[i] = pad;
-                ex_cnts[i] = 0;
-                if (c >= thr) {
-                    const uint32_t pos = atomicAdd(&s_ncand, 1u);
-                    if (pos < kFastKbuf) kbuf[pos] = rank_key(c, k);
-                }
-            }
-        }
-        g.sync();
-        const uint32_t n = s_ncand;
-        const bool redo = s_ovf || n > kFastKbuf;
-        if (redo) {
-            // more sketch-hot docids than the exact table holds: the exact count-table path takes the query
-            if (tid == 0) {
-                enqueue(a, exact_class_for(w.postings, w.k_eff), w);
-                if (a.stats) atomicAdd(&a.stats->overflow_requeues, 1ull);
-            }
-        } else if (n == 0) {
-            if (tid == 0) a.out_counts[w.q] = 0;
-        } else {
-            group_sort_keys(g, kbuf, n, kFastKbuf);
-            group_emit_results(g, a, w, kbuf, n, &s_count);
-        }
         if (tid == 0) {
-            if (a.stats && !redo) atomicAdd(&a.stats->sketch_queries, 1ull);
+            r_item[b] = meta[s].item;
+            mbar_arrive(&empty[s]);     // the stage may be refilled
+            mbar_arrive(&rank_full[b]); // hand-over to the ranker (release)
+            s_nrec = s_nset = s_ovf = 0;
+            s_known = pad;
         }
-        g.sync();
-        if (tid == 0) s_ncand = s_nkeys = s_ovf = s_nhot = 0;
-        // the next query's first updates of these counters happen after two more group barriers
     }
 }
 

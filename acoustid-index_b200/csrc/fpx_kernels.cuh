@@ -76,6 +76,7 @@ struct BatchArgs {
     unsigned long long *wide_tables; // per wide CTA: wide_cap 64-bit slots
     uint32_t wide_cap_log2;
     uint32_t use_sketch;    // 0 disables class 0 (A/B testing)
+    uint32_t debug;         // ablation bits for profiling runs (results are wrong when set): see fpx_kernels.cu
 };
 
 constexpr uint32_t kWarpQueryTerms = 128; // queries up to this many raw terms are prepared by one warp
@@ -85,6 +86,7 @@ constexpr uint32_t kWideKbuf = 2048;      // candidate buffer of the global-memo
 constexpr uint32_t kMaxResults = 1024;    // FPX_MAX_RESULTS
 constexpr uint32_t kRowsChunk = 256;      // row descriptors staged per round
 constexpr uint32_t kStageU4 = 2048;       // sketch path: one query's padded rows must fit 32 KB
+constexpr uint32_t kSketchMaxRows = 128;  // sketch path: row descriptors live in producer registers
 
 void launch_build_table(TermEntry *table, uint32_t log2cap, const uint32_t *terms, const uint32_t *lens,
                         const uint32_t *start4, uint64_t n_terms, cudaStream_t st);
