@@ -75,7 +75,7 @@ struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr; // last use (async device API)
     bool done_pending = false;
-    DevBuf<uint2> rows;
+    DevBuf<uint4> rows;
     DevBuf<WorkItem> items;
     DevBuf<uint32_t> long_queue;
     DevBuf<unsigned long long> wide_tables;

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(BatchArgs a) {
             e[j] = make_uint4(0, 0, 0, 0);
             if (live[j]) e[j] = __ldg(reinterpret_cast<const uint4 *>(a.snap.table + h[j]));
         }
-        uint32_t n_unique = 0, n_rows = 0;
+        uint32_t n_unique = 0, n_rows = 0, off4_base = 0;
         unsigned long long postings = 0, total4 = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -232,18 +232,24 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(BatchArgs a) {
             const uint32_t um = __ballot_sync(0xFFFFFFFFu, live[j]);
             const uint32_t fm = __ballot_sync(0xFFFFFFFFu, found);
             n_unique += __popc(um);
-            if (found) {
-                a.rows[o0 + n_rows + __popc(fm & lt_mask)] = make_uint2(e[j].z, e[j].y);
-                postings += e[j].y;
-                total4 += (e[j].y + 3) >> 2;
+            // exclusive prefix of the padded row sizes in compaction order = the row's place in a stage
+            const uint32_t my4 = found ? (e[j].y + 3) >> 2 : 0u;
+            uint32_t incl = my4;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= (uint32_t)o) incl += y;
             }
+            if (found) {
+                a.rows[o0 + n_rows + __popc(fm & lt_mask)] = make_uint4(e[j].z, e[j].y, off4_base + incl - my4, 0u);
+                postings += e[j].y;
+            }
+            off4_base += __shfl_sync(0xFFFFFFFFu, incl, 31);
             n_rows += __popc(fm);
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            postings += __shfl_xor_sync(0xFFFFFFFFu, postings, off);
-            total4 += __shfl_xor_sync(0xFFFFFFFFu, total4, off);
-        }
+        for (int off = 16; off > 0; off >>= 1) postings += __shfl_xor_sync(0xFFFFFFFFu, postings, off);
+        total4 = off4_base;
         // every lane computes the (identical) work item; lane n_parked keeps it
         WorkItem w;
         const uint32_t cls = make_item(a, q, (uint32_t)o0, n_rows, postings, total4, w);
@@ -314,9 +320,9 @@ __global__ void __launch_bounds__(kThreads) prepare_long_kernel(BatchArgs a) {
             atomicAdd(&s_unique, 1u);
             uint32_t st, ln;
             if (directory_lookup(a.snap, v, st, ln)) {
-                a.rows[o0 + atomicAdd(&s_rows, 1u)] = make_uint2(st, ln);
+                const unsigned long long off4 = atomicAdd(&s_tot4, (unsigned long long)((ln + 3) >> 2));
+                a.rows[o0 + atomicAdd(&s_rows, 1u)] = make_uint4(st, ln, (uint32_t)off4, 0u);
                 atomicAdd(&s_post, (unsigned long long)ln);
-                atomicAdd(&s_tot4, (unsigned long long)((ln + 3) >> 2));
             }
         }
         __syncthreads();
@@ -529,15 +535,15 @@ __global__ void __launch_bounds__(kSkThreads, 2) search_sketch_kernel(BatchArgs 
             w = items[idx];
             return true;
         };
-        auto rows_of = [&](const WorkItem &w, uint2 (&d)[4]) {
+        auto rows_of = [&](const WorkItem &w, uint4 (&d)[4]) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint32_t r = lane + 32 * j;
-                d[j] = r < w.n_rows ? a.rows[w.rows_off + r] : make_uint2(0u, 0u);
+                d[j] = r < w.n_rows ? a.rows[w.rows_off + r] : make_uint4(0u, 0u, 0u, 0u);
             }
         };
         WorkItem w{}, w1{}, w2{};
-        uint2 d[4], d1[4];
+        uint4 d[4], d1[4];
         bool have = item_at(0, w), have1 = item_at(1, w1);
         if (have) rows_of(w, d);
         for (uint32_t it = 0; have; ++it) {
@@ -549,26 +555,16 @@ __global__ void __launch_bounds__(kSkThreads, 2) search_sketch_kernel(BatchArgs 
                 __syncwarp();
             }
             uint4 *dst = stage + (size_t)s * kStageU4;
-            uint32_t off[4], n4[4], base = 0, mine = 0;
+            // the row's place in the stage (d.z) was computed by prepare_kernel; my share = rows r % 4 == p
+            uint32_t mine = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                n4[j] = (d[j].y + 3) >> 2;
-                uint32_t x = n4[j];
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-                    if (lane >= (uint32_t)o) x += y;
-                }
-                off[j] = base + x - n4[j];
-                base += __shfl_sync(0xFFFFFFFFu, x, 31);
-                mine += (lane % kSkProducerWarps == p) ? n4[j] : 0u; // (lane + 32 j) % 4 == lane % 4
-            }
+            for (int j = 0; j < 4; ++j) mine += (lane % kSkProducerWarps == p) ? (d[j].y + 3) >> 2 : 0u;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
             if (p == 0) { // stage directory for the exact recount
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    meta[s].row_off[lane + 32 * j] = off[j] * 4u;
+                    meta[s].row_off[lane + 32 * j] = d[j].z * 4u;
                     meta[s].row_len[lane + 32 * j] = d[j].y;
                 }
                 if (lane == 0) meta[s].item = w;
@@ -580,8 +576,8 @@ __global__ void __launch_bounds__(kSkThreads, 2) search_sketch_kernel(BatchArgs 
             if (!(a.debug & 8u)) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (n4[j] && (lane % kSkProducerWarps == p))
-                        bulk_g2s(dst + off[j], docids4 + d[j].x, n4[j] * 16u, &full[s]);
+                    if (d[j].y && (lane % kSkProducerWarps == p))
+                        bulk_g2s(dst + d[j].z, docids4 + d[j].x, ((d[j].y + 3) >> 2) * 16u, &full[s]);
             }
             have = have1;
             have1 = have2;
@@ -651,20 +647,22 @@ __global__ void __launch_bounds__(kSkThreads, 2) search_sketch_kernel(BatchArgs 
         // reached by <= 8192 postings: bias 0 then never fires.
         const uint32_t bias = thr_m1 < 0x8000u ? (0x8000u - thr_m1) * 0x10001u : 0u;
 
-        // pass 1: count sketch, two 16-bit counters per word.  All four adds of a 16-byte granule are issued
-        // before any result is used.  A pad adds 0 and is never recorded.
+        // pass 1: count sketch, two 16-bit counters per word: hash bits 30..18 pick the word, the sign bit
+        // the half.  All four adds of a 16-byte granule are issued before any result is used.  Row padding
+        // is made of unused docids spread over many values, so it needs no test here: it is counted like
+        // anything else, can only make a counter too high, and an exact recount gives it score 0.
         if (!(a.debug & 1u)) {
 #pragma unroll 2
             for (uint32_t i = tid; i < total4; i += kSkCounters) {
                 const uint4 v = st[i];
                 const uint32_t dd[4] = {v.x, v.y, v.z, v.w};
-                uint32_t sh[4], oo[4];
+                uint32_t oo[4];
+                int hv[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const uint32_t hv = dd[e] * kMult;
-                    sh[e] = (hv >> 14) & 16u;                    // hash bit 18 selects the half
-                    oo[e] = atomicAdd(reinterpret_cast<uint32_t *>(sketch_b + ((hv >> 17) & 0x7FFCu)),
-                                      (dd[e] != pad ? 1u : 0u) << sh[e]);
+                    hv[e] = (int)(dd[e] * kMult);
+                    oo[e] = atomicAdd(reinterpret_cast<uint32_t *>(sketch_b + (((uint32_t)hv[e] >> 16) & 0x7FFCu)),
+                                      hv[e] < 0 ? 0x10000u : 1u);
                 }
                 const uint32_t hit = ((oo[0] + bias) | (oo[1] + bias) | (oo[2] + bias) | (oo[3] + bias)) & 0x80008000u;
                 if (hit) { // some counter in one of the four words was already at min_score-1
@@ -673,7 +671,7 @@ __global__ void __launch_bounds__(kSkThreads, 2) search_sketch_kernel(BatchArgs 
                     const uint32_t known = s_known;
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
-                        if (dd[e] != known && ((oo[e] >> sh[e]) & 0xFFFFu) >= thr_m1 && dd[e] != pad) {
+                        if (dd[e] != known && ((oo[e] >> (hv[e] < 0 ? 16 : 0)) & 0xFFFFu) >= thr_m1) {
                             const uint32_t p = atomicAdd(&s_nrec, 1u);
                             if (p < kRecCap) rec[p] = dd[e];
                             s_known = dd[e];
@@ -820,7 +818,7 @@ template <int LOG> __device__ __forceinline__ uint32_t table_docid(uint32_t word
 }
 
 template <int LOG> constexpr size_t smem_bytes_for() {
-    return (size_t)Packed<LOG>::kSlots * 4 + kFastKbuf * 8 + kRowsChunk * 8;
+    return (size_t)Packed<LOG>::kSlots * 4 + kFastKbuf * 8 + kRowsChunk * 16;
 }
 
 template <int LOG>
@@ -829,14 +827,13 @@ __global__ void __launch_bounds__(kThreads, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem_raw);
     unsigned long long *kbuf = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)P::kSlots * 4);
-    uint2 *rows_s = reinterpret_cast<uint2 *>(smem_raw + (size_t)P::kSlots * 4 + kFastKbuf * 8);
+    uint4 *rows_s = reinterpret_cast<uint4 *>(smem_raw + (size_t)P::kSlots * 4 + kFastKbuf * 8);
     __shared__ uint32_t s_idx, s_ncand, s_ovf, s_count;
 
     constexpr int cls = LOG - 12;
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const Group g{tid, (uint32_t)kThreads, 0u};
     const uint4 *docids4 = reinterpret_cast<const uint4 *>(a.snap.docids);
-    const uint32_t pad = a.snap.pad_id;
     uint4 *tab4 = reinterpret_cast<uint4 *>(tab);
 
     for (uint32_t i = tid; i < P::kSlots / 4; i += kThreads) tab4[i] = make_uint4(0, 0, 0, 0);
@@ -853,7 +850,7 @@ __global__ void __launch_bounds__(kThreads, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1)
         if (s_idx >= qcount) break;
         const WorkItem w = a.items[(size_t)cls * a.n_queries + s_idx];
         const uint32_t thr = max(w.min_score, 1u); // a doc in the table has score >= 1
-        const uint2 *rows = a.rows + w.rows_off;
+        const uint4 *rows = a.rows + w.rows_off;
         uint32_t passes = 1;
         if (LOG == 15)
             while ((unsigned long long)passes * 12288ull < w.postings && w.postings > 16384u) passes <<= 1;
@@ -865,20 +862,21 @@ __global__ void __launch_bounds__(kThreads, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1)
                 __syncthreads();
                 for (uint32_t i = tid; i < nr; i += kThreads) rows_s[i] = rows[r0 + i];
                 __syncthreads();
-                // a warp per posting row, 128-bit loads, two rows in flight
+                // a warp per posting row, 128-bit loads, two rows in flight; the tail of a row's last
+                // 16-byte granule is padding (a repeat of the last docid) and is masked by position
                 for (uint32_t r = warp * 2; r < nr; r += kWarps * 2) {
-                    const uint2 ra = rows_s[r];
-                    const uint2 rb = (r + 1 < nr) ? rows_s[r + 1] : make_uint2(0u, 0u);
+                    const uint4 ra = rows_s[r];
+                    const uint4 rb = (r + 1 < nr) ? rows_s[r + 1] : make_uint4(0u, 0u, 0u, 0u);
                     const uint32_t na = (ra.y + 3) >> 2, nb = (rb.y + 3) >> 2;
                     const uint32_t nmax = max(na, nb);
                     for (uint32_t i = lane; i < nmax; i += 32) {
-                        uint4 va = make_uint4(pad, pad, pad, pad), vb = va;
+                        uint4 va = make_uint4(0, 0, 0, 0), vb = va;
                         if (i < na) va = __ldg(docids4 + ra.x + i);
                         if (i < nb) vb = __ldg(docids4 + rb.x + i);
                         const uint32_t d[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            if (d[e] == pad) continue;
+                            if (4 * i + (e & 3) >= (e < 4 ? ra.y : rb.y)) continue;
                             if (pmask && (((d[e] * kMult2) >> 16) & pmask) != pass) continue;
                             table_insert<LOG>(tab, d[e], &s_ovf);
                         }
@@ -922,7 +920,7 @@ __global__ void __launch_bounds__(kThreads, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) search_wide_kernel(BatchArgs a) {
     __shared__ unsigned long long kbuf[kWideKbuf];
-    __shared__ uint2 rows_s[kRowsChunk];
+    __shared__ uint4 rows_s[kRowsChunk];
     __shared__ uint32_t s_idx, s_kn, s_new, s_fail, s_count;
     __shared__ unsigned long long s_kth;
 
@@ -930,7 +928,6 @@ __global__ void __launch_bounds__(kThreads) search_wide_kernel(BatchArgs a) {
     const Group g{tid, (uint32_t)kThreads, 0u};
     unsigned long long *table = a.wide_tables + ((size_t)blockIdx.x << a.wide_cap_log2);
     const uint4 *docids4 = reinterpret_cast<const uint4 *>(a.snap.docids);
-    const uint32_t pad = a.snap.pad_id;
     const uint32_t qcount = a.counters->qcount[kWideClass];
 
     for (;;) {
@@ -941,7 +938,7 @@ __global__ void __launch_bounds__(kThreads) search_wide_kernel(BatchArgs a) {
         const WorkItem w = a.items[(size_t)kWideClass * a.n_queries + s_idx];
         const uint32_t thr = max(w.min_score, 1u);
         const uint32_t k_eff = min(w.k_eff, kMaxResults);
-        const uint2 *rows = a.rows + w.rows_off;
+        const uint4 *rows = a.rows + w.rows_off;
         if (tid == 0 && a.stats) atomicAdd(&a.stats->wide_queries, 1ull);
 
         // table size: aim for load <= 0.25; more hash partitions when one table cannot hold that
@@ -973,7 +970,7 @@ __global__ void __launch_bounds__(kThreads) search_wide_kernel(BatchArgs a) {
                     for (uint32_t i = tid; i < nr; i += kThreads) rows_s[i] = rows[r0 + i];
                     __syncthreads();
                     for (uint32_t r = warp; r < nr; r += kWarps) {
-                        const uint2 ra = rows_s[r];
+                        const uint4 ra = rows_s[r];
                         const uint32_t na = (ra.y + 3) >> 2;
                         for (uint32_t i = lane; i < na; i += 32) {
                             const uint4 va = __ldg(docids4 + ra.x + i);
@@ -981,7 +978,7 @@ __global__ void __launch_bounds__(kThreads) search_wide_kernel(BatchArgs a) {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const uint32_t id = d[e];
-                                if (id == pad) continue;
+                                if (4 * i + e >= ra.y) continue; // padding of the row's last granule
                                 if (passes > 1 && (((id * kMult2) >> 16) & (passes - 1u)) != pass) continue;
                                 uint32_t h = (id * kMult) >> (32 - capl);
                                 const unsigned long long fresh = ((unsigned long long)id << 32) | 1ull;

@@ -18,7 +18,8 @@ struct SnapshotDev {
     uint32_t table_mask;
     uint32_t table_shift; // 32 - log2(capacity)
     const uint32_t *docids; // padded rows
-    uint32_t pad_id;
+    uint32_t pad_id; // a docid no posting uses: "empty" marker of candidate sets (row padding uses other unused
+                     // docids, see fpx_snapshot_host.h)
 };
 
 struct SearchOpts { // == fpx_search_opts
@@ -68,7 +69,8 @@ struct BatchArgs {
     const SearchOpts *opts;
     uint32_t *out_ids, *out_scores, *out_counts;
     // workspace
-    uint2 *rows;            // per query at [term_offsets[q]-term_base ...): {start4, len}
+    uint4 *rows;            // per query at [term_offsets[q]-term_base ...): {start4, len, off4, 0}; off4 = start of
+                            // the row inside a stage that holds the query's rows back to back (16-byte units)
     WorkItem *items;        // kNumClasses * n_queries
     uint32_t *long_queue;   // n_queries
     BatchCounters *counters;

@@ -378,13 +378,34 @@ class SnapshotCompiler {
                     }
             });
 
-        // padding value: a docid no live posting uses (ids are nonzero in the reference,
-        // MultiIndex.zig:333-343, so this is 0 in practice)
-        out->pad_id = choose_pad(*out);
+        // Rows are padded to 16 bytes.  No kernel tests "is this padding?" per posting: the exact kernels mask
+        // by position, and the sketch kernel simply counts the padding too — so padding must not pile up in
+        // one sketch counter.  It is therefore drawn from the unused docid space above the largest live id
+        // (64 Ki distinct values, varying from row to row); such values can never be live, and an exact
+        // recount (which uses the rows' true lengths) gives them score 0.  pad_id, the "empty" marker of the
+        // small candidate sets, is one more unused value.  If the ids reach up to 2^32 there is no such
+        // range and a single unused value is used for everything (still exact, the sketch is just less sharp).
+        uint32_t max_live = 0;
+        {
+            std::vector<uint32_t> mx(threads_, 0);
+            parallel_for(nt, threads_, [&](size_t g0, size_t g1, unsigned tid) {
+                uint32_t m = 0;
+                for (size_t g = g0; g < g1; ++g) {
+                    const uint32_t *p = out->docids.data() + (uint64_t)out->row_start4[g] * 4;
+                    for (uint32_t i = 0; i < out->row_len[g]; ++i) m = std::max(m, p[i]);
+                }
+                mx[tid] = m;
+            });
+            for (uint32_t m : mx) max_live = std::max(max_live, m);
+        }
+        const bool spread = max_live < 0xFFFE0000u;
+        out->pad_id = spread ? max_live + 1 : choose_pad(*out);
+        const uint32_t pad_base = max_live + 2;
         parallel_for(nt, threads_, [&](size_t g0, size_t g1, unsigned) {
             for (size_t g = g0; g < g1; ++g) {
                 uint32_t *p = out->docids.data() + (uint64_t)out->row_start4[g] * 4;
-                for (uint32_t i = out->row_len[g]; i < ((out->row_len[g] + 3) & ~3u); ++i) p[i] = out->pad_id;
+                for (uint32_t i = out->row_len[g]; i < ((out->row_len[g] + 3) & ~3u); ++i)
+                    p[i] = spread ? pad_base + (uint32_t)((g * 3 + i) & 0xFFFFu) : out->pad_id;
             }
         });
         compiled_ = std::move(out);
