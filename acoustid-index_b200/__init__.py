@@ -5,7 +5,7 @@ This Python package is the host-side mirror of the reference interface used by t
 The directory name has a hyphen (it mirrors the reference repo name); import it through
 `__graft_entry__.load_package()` which registers it as `acoustid_index_b200`.
 """
-from . import _ffi, index, synth  # noqa: F401
+from . import _ffi, index, synth  # noqa: F401  (multi_gpu is imported on demand: it needs torch.distributed)
 from ._ffi import FpxError, build as build_library, lib  # noqa: F401
 from .index import (Context, FileSegment, IndexReader, MemorySegment, SearchOptions, SearchRequest,  # noqa: F401
                     SearchResult, Snapshot, SnapshotBuilder, merge_shard_results, multi_index_search,

@@ -463,9 +463,8 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // counter is already >= min_score-1 and d is recorded.  Its exact count is then taken from the rows.
 // The kernel is bound by the integer ALU, not by memory, so everything per posting is kept minimal.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSkCounterWarps = 8;
+constexpr int kSkCounterWarps = 12;
 constexpr int kSkProducerWarps = 4; // row r of a query is issued by producer warp r % 4
-constexpr int kSkStages = 2;
 constexpr int kSkRankerWarp = kSkCounterWarps;
 constexpr int kSkFirstProducer = kSkCounterWarps + 1;
 constexpr int kSkThreads = (kSkCounterWarps + 1 + kSkProducerWarps) * 32;
@@ -475,7 +474,7 @@ constexpr uint32_t kSketchWords = (1u << kSketchLog) / 2;
 constexpr uint32_t kRecCap = 512;         // candidate records per query (with repeats)
 constexpr uint32_t kSetSlots = 64;        // distinct-candidate hash set
 constexpr uint32_t kMaxCand = 32;         // distinct candidates handled here; more -> exact count-table path
-constexpr size_t kSkSmemBytes = (size_t)kSketchWords * 4 + (size_t)kSkStages * kStageU4 * 16 + kRecCap * 4;
+constexpr size_t sketch_smem_bytes(int stages) { return (size_t)kSketchWords * 4 + (size_t)stages * kStageU4 * 16 + kRecCap * 4; }
 
 struct StageMeta {
     WorkItem item;
@@ -483,7 +482,8 @@ struct StageMeta {
     uint32_t row_len[kSketchMaxRows]; // postings in row r (without padding)
 };
 
-__global__ void __launch_bounds__(kSkThreads, 2) search_sketch_kernel(BatchArgs a) {
+template <int kSkStages, int kCtasPerSm>
+__global__ void __launch_bounds__(kSkThreads, kCtasPerSm) search_sketch_kernel(BatchArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *sketch_b = smem_raw;
     uint4 *stage = reinterpret_cast<uint4 *>(smem_raw + (size_t)kSketchWords * 4);
@@ -664,18 +664,25 @@ __global__ void __launch_bounds__(kSkThreads, 2) search_sketch_kernel(BatchArgs 
                     oo[e] = atomicAdd(reinterpret_cast<uint32_t *>(sketch_b + (((uint32_t)hv[e] >> 16) & 0x7FFCu)),
                                       hv[e] < 0 ? 0x10000u : 1u);
                 }
-                const uint32_t hit = ((oo[0] + bias) | (oo[1] + bias) | (oo[2] + bias) | (oo[3] + bias)) & 0x80008000u;
-                if (hit) { // some counter in one of the four words was already at min_score-1
-                    // The true match triggers this once per matching row; after its first record the docid
-                    // is "known" and the later ones leave right away (a stale s_known only costs a repeat).
+                uint32_t t[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) t[e] = oo[e] + bias;
+                if ((t[0] | t[1] | t[2] | t[3]) & 0x80008000u) { // some counter in one of the four words is hot
+                    // The true match lands here once per matching row.  After its first record its docid is
+                    // "known": neutralise it and re-test, so the repeats leave after a dozen instructions
+                    // (a stale s_known only costs a repeated record).
                     const uint32_t known = s_known;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (dd[e] != known && ((oo[e] >> (hv[e] < 0 ? 16 : 0)) & 0xFFFFu) >= thr_m1) {
-                            const uint32_t p = atomicAdd(&s_nrec, 1u);
-                            if (p < kRecCap) rec[p] = dd[e];
-                            s_known = dd[e];
-                        }
+                    for (int e = 0; e < 4; ++e) t[e] = dd[e] == known ? 0u : t[e];
+                    if ((t[0] | t[1] | t[2] | t[3]) & 0x80008000u) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (t[e] & (hv[e] < 0 ? 0x80000000u : 0x8000u)) { // this posting's own counter
+                                const uint32_t p = atomicAdd(&s_nrec, 1u);
+                                if (p < kRecCap) rec[p] = dd[e];
+                                s_known = dd[e];
+                            }
+                    }
                 }
             }
         }
@@ -1070,7 +1077,9 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_smem_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for<15>());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(search_sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
+    e = cudaFuncSetAttribute(search_sketch_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sketch_smem_bytes(2));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(search_sketch_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sketch_smem_bytes(1));
     return e;
 }
 
@@ -1095,7 +1104,10 @@ void launch_prepare_long(const BatchArgs &a, cudaStream_t st, int n_sms) {
 }
 
 void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms) {
-    search_sketch_kernel<<<n_sms * 2, kSkThreads, kSkSmemBytes, st>>>(a);
+    if (a.debug & 32u) // experimental: three CTAs per SM with a single stage each
+        search_sketch_kernel<1, 3><<<n_sms * 3, kSkThreads, sketch_smem_bytes(1), st>>>(a);
+    else
+        search_sketch_kernel<2, 2><<<n_sms * 2, kSkThreads, sketch_smem_bytes(2), st>>>(a);
 }
 
 void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms) {
