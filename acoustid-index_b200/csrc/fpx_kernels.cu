@@ -446,35 +446,44 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 
 // ------------------------------------------------------------------------------------------------
-// sketch path (class 0): two persistent CTAs per SM, three warp roles each
-//   producers (4 warps)  TMA bulk copies (cp.async.bulk, mbarrier complete_tx) of the query's posting rows
-//                        into one of two 32 KB shared-memory stages, one query ahead of the counters
-//   counters  (8 warps)  scatter-add every staged docid into a 16384 x u16 count sketch with shared
-//                        atomics.  The add returns the counter's previous value; a posting that finds
-//                        its counter already at min_score-1 or more records its docid as a candidate.
-//                        Then the (few) distinct candidates are counted exactly by binary search in the
-//                        staged rows, which are sorted by docid.
-//   ranker    (1 warp)   ranks the candidates, applies the reference's cutoffs, writes the results — while
-//                        the counters already work on the next query
-// Two CTAs share an SM so that one CTA's latency-bound phases overlap the other's ALU-bound counting.
+// sketch path (class 0): one persistent CTA per SM, 32 warps in three roles, no CTA-wide barrier anywhere —
+// every hand-over is an mbarrier, so each warp streams at its own pace and up to four queries are in
+// flight per SM (4 stages, 2 sketches):
+//   producers (8 warps)   TMA bulk copies (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) of the query's
+//                         posting rows into a ring of four 32 KB shared-memory stages.  Issue is the scarce
+//                         resource (~10 SASS instructions per copy through uniform registers), so the warps
+//                         split every query row-wise; row descriptors (with the row's place in the stage,
+//                         precomputed by prepare_kernel) sit in registers, loaded one query ahead.
+//   counters  (16 warps)  scatter-add every staged docid into a 16384 x u16 count sketch (two sketches,
+//                         alternating queries) with shared atomics.  The add returns the counter's previous
+//                         value; a posting that finds its counter already at min_score-1 or more records its
+//                         docid as a candidate.  A warp that finishes its slice arrives on `counted` and
+//                         moves straight on to the next query.
+//   resolvers (2 x 4 warps, alternating queries)  clear the sketch, de-duplicate the few candidates, count
+//                         each exactly by binary search in the staged rows (sorted by docid), rank, apply the
+//                         reference's cutoffs, write the results, hand the stage back.
 // Why this is exact: a counter holds the sum of the true counts of all docids hashing to it and only grows
 // by one per posting.  If doc d has c >= min_score postings in the query, at most min_score-1 of them can
 // be among the first min_score-1 arrivals at its counter, so at least one posting of d arrives when the
 // counter is already >= min_score-1 and d is recorded.  Its exact count is then taken from the rows.
-// The kernel is bound by the integer ALU, not by memory, so everything per posting is kept minimal.
+// The kernel is bound by integer-ALU issue, not by memory, so everything per posting is kept minimal.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSkCounterWarps = 12;
-constexpr int kSkProducerWarps = 4; // row r of a query is issued by producer warp r % 4
-constexpr int kSkRankerWarp = kSkCounterWarps;
-constexpr int kSkFirstProducer = kSkCounterWarps + 1;
-constexpr int kSkThreads = (kSkCounterWarps + 1 + kSkProducerWarps) * 32;
+constexpr int kSkCounterWarps = 16;
+constexpr int kSkResolverGroups = 2;
+constexpr int kSkResolverWarps = 4; // per group
+constexpr int kSkProducerWarps = 8; // row r of a query is issued by producer warp r % 8
+constexpr int kSkStages = 4;
+constexpr int kSkFirstResolver = kSkCounterWarps;
+constexpr int kSkFirstProducer = kSkCounterWarps + kSkResolverGroups * kSkResolverWarps;
+constexpr int kSkThreads = (kSkFirstProducer + kSkProducerWarps) * 32;
 constexpr int kSkCounters = kSkCounterWarps * 32;
+constexpr int kSkResolvers = kSkResolverWarps * 32;
 constexpr uint32_t kSketchLog = 14;       // 16384 u16 counters, two per 32-bit word = 32 KB
 constexpr uint32_t kSketchWords = (1u << kSketchLog) / 2;
 constexpr uint32_t kRecCap = 512;         // candidate records per query (with repeats)
 constexpr uint32_t kSetSlots = 64;        // distinct-candidate hash set
 constexpr uint32_t kMaxCand = 32;         // distinct candidates handled here; more -> exact count-table path
-constexpr size_t sketch_smem_bytes(int stages) { return (size_t)kSketchWords * 4 + (size_t)stages * kStageU4 * 16 + kRecCap * 4; }
+constexpr size_t kSkSmemBytes = 2 * (size_t)kSketchWords * 4 + (size_t)kSkStages * kStageU4 * 16 + 2 * kRecCap * 4;
 
 struct StageMeta {
     WorkItem item;
@@ -482,20 +491,22 @@ struct StageMeta {
     uint32_t row_len[kSketchMaxRows]; // postings in row r (without padding)
 };
 
-template <int kSkStages, int kCtasPerSm>
-__global__ void __launch_bounds__(kSkThreads, kCtasPerSm) search_sketch_kernel(BatchArgs a) {
+struct ResolverState { // private to one resolver group
+    uint32_t set_keys[kSetSlots];
+    uint32_t c_ids[kMaxCand], c_cnts[kMaxCand];
+    unsigned long long r_keys[kMaxCand];
+    uint32_t nset, ovf, c_n, r_count;
+};
+
+__global__ void __launch_bounds__(kSkThreads, 1) search_sketch_kernel(BatchArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char *sketch_b = smem_raw;
-    uint4 *stage = reinterpret_cast<uint4 *>(smem_raw + (size_t)kSketchWords * 4);
-    uint32_t *rec = reinterpret_cast<uint32_t *>(smem_raw + (size_t)kSketchWords * 4 + (size_t)kSkStages * kStageU4 * 16);
-    __shared__ uint64_t full[kSkStages], empty[kSkStages], rank_full[2], rank_empty[2];
+    unsigned char *sketch_base = smem_raw;                                   // 2 x 32 KB
+    uint4 *stage = reinterpret_cast<uint4 *>(smem_raw + 2 * (size_t)kSketchWords * 4);
+    uint32_t *rec_base = reinterpret_cast<uint32_t *>(smem_raw + 2 * (size_t)kSketchWords * 4 + (size_t)kSkStages * kStageU4 * 16);
+    __shared__ uint64_t full[kSkStages], empty[kSkStages], counted[2], sk_free[2];
     __shared__ StageMeta meta[kSkStages];
-    __shared__ uint32_t s_nrec, s_nset, s_ovf, s_known;
-    __shared__ uint32_t set_keys[kSetSlots];
-    __shared__ uint32_t r_ids[2][kMaxCand], r_cnts[2][kMaxCand], r_n[2], r_redo[2];
-    __shared__ WorkItem r_item[2];
-    __shared__ unsigned long long r_keys[kMaxCand];
-    __shared__ uint32_t r_count;
+    __shared__ uint32_t s_nrec[2], s_known[2];
+    __shared__ ResolverState rs[kSkResolverGroups];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t count = a.counters->qcount[kSketchClass];
@@ -508,25 +519,21 @@ __global__ void __launch_bounds__(kSkThreads, kCtasPerSm) search_sketch_kernel(B
             mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&rank_full[b], 1);
-            mbar_init(&rank_empty[b], 1);
+            mbar_init(&counted[b], kSkCounterWarps);
+            mbar_init(&sk_free[b], 1);
+            s_nrec[b] = 0;
+            s_known[b] = pad;
         }
-        s_nrec = s_nset = s_ovf = 0;
-        s_known = a.snap.pad_id;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < kSkCounters) {
-        for (uint32_t i = tid; i < kSketchWords / 4; i += kSkCounters)
-            reinterpret_cast<uint4 *>(sketch_b)[i] = make_uint4(0, 0, 0, 0);
-        if (tid < kSetSlots) set_keys[tid] = pad;
-    }
+    for (uint32_t i = tid; i < 2 * kSketchWords / 4; i += kSkThreads)
+        reinterpret_cast<uint4 *>(sketch_base)[i] = make_uint4(0, 0, 0, 0);
+    if (tid < kSkResolverGroups * kSetSlots) rs[tid / kSetSlots].set_keys[tid % kSetSlots] = pad;
+    if (tid < kSkResolverGroups) rs[tid].nset = rs[tid].ovf = 0;
     __syncthreads();
 
     if (warp >= kSkFirstProducer) {
-        // ===== producers.  Issue is the scarce resource (~70 clk per bulk copy per warp), so the four warps
-        // split every query row-wise; each computes all offsets itself from row descriptors it holds in
-        // registers (4 per lane).  Work items are fetched two queries ahead and row descriptors one query
-        // ahead, so neither dependent global load sits on the critical path.
+        // ===== producers
         const uint32_t p = warp - kSkFirstProducer;
         const uint4 *docids4 = reinterpret_cast<const uint4 *>(a.snap.docids);
         auto item_at = [&](uint32_t it, WorkItem &w) -> bool {
@@ -542,20 +549,20 @@ __global__ void __launch_bounds__(kSkThreads, kCtasPerSm) search_sketch_kernel(B
                 d[j] = r < w.n_rows ? a.rows[w.rows_off + r] : make_uint4(0u, 0u, 0u, 0u);
             }
         };
-        WorkItem w{}, w1{}, w2{};
+        WorkItem w{}, w1{};
         uint4 d[4], d1[4];
-        bool have = item_at(0, w), have1 = item_at(1, w1);
+        bool have = item_at(0, w);
         if (have) rows_of(w, d);
         for (uint32_t it = 0; have; ++it) {
             const uint32_t s = it % kSkStages;
-            if (have1) rows_of(w1, d1);               // rows of query it+1
-            const bool have2 = item_at(it + 2, w2);   // item of query it+2
-            if (it >= kSkStages) { // wait until the counters released the previous tenant of this stage
-                if (lane == 0) mbar_wait_relaxed(&empty[s], ((it / kSkStages) - 1) & 1);
+            const bool have1 = item_at(it + 1, w1); // next query's item and rows: in flight during the issue
+            if (have1) rows_of(w1, d1);
+            if (it >= kSkStages) { // wait until the resolvers released the previous tenant of this stage
+                if (lane == 0) mbar_wait(&empty[s], ((it / kSkStages) - 1) & 1);
                 __syncwarp();
             }
             uint4 *dst = stage + (size_t)s * kStageU4;
-            // the row's place in the stage (d.z) was computed by prepare_kernel; my share = rows r % 4 == p
+            // the row's place in the stage (d.z) was computed by prepare_kernel; my share = rows r % 8 == p
             uint32_t mine = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) mine += (lane % kSkProducerWarps == p) ? (d[j].y + 3) >> 2 : 0u;
@@ -580,77 +587,166 @@ __global__ void __launch_bounds__(kSkThreads, kCtasPerSm) search_sketch_kernel(B
                         bulk_g2s(dst + d[j].z, docids4 + d[j].x, ((d[j].y + 3) >> 2) * 16u, &full[s]);
             }
             have = have1;
-            have1 = have2;
             w = w1;
-            w1 = w2;
 #pragma unroll
             for (int j = 0; j < 4; ++j) d[j] = d1[j];
         }
         return;
     }
 
-    if (warp == kSkRankerWarp) {
-        // ===== ranker: candidates -> (score desc, id asc), cutoffs, result write-out
-        const Group g{lane, 32u, 2u};
-        for (uint32_t it = 0;; ++it) {
+    if (warp >= kSkFirstResolver) {
+        // ===== resolvers: group gidx owns sketch / record buffer gidx and every second query
+        const uint32_t gidx = (warp - kSkFirstResolver) / kSkResolverWarps;
+        const uint32_t rwarp = (warp - kSkFirstResolver) % kSkResolverWarps;
+        const uint32_t rtid = rwarp * 32 + lane;
+        const Group R{rtid, (uint32_t)kSkResolvers, 1u + gidx};
+        const Group W{lane, 32u, 3u + gidx};
+        ResolverState &st = rs[gidx];
+        const uint32_t b = gidx;
+        uint4 *sk4 = reinterpret_cast<uint4 *>(sketch_base + (size_t)b * kSketchWords * 4);
+        const uint32_t *rec = rec_base + b * kRecCap;
+        for (uint32_t it = gidx;; it += kSkResolverGroups) {
             const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
             if (idx >= count) break;
-            const uint32_t b = it & 1u;
-            if (lane == 0) mbar_wait(&rank_full[b], (it >> 1) & 1);
-            __syncwarp();
-            const WorkItem w = r_item[b];
-            const uint32_t nc = r_n[b];
-            const bool redo = r_redo[b] != 0u;
-            uint32_t n = 0;
-            if (!redo) {
-                const bool keep = lane < nc && r_cnts[b][lane] >= w.min_score; // common.zig:140-145
-                const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
-                if (keep) r_keys[__popc(km & ((1u << lane) - 1u))] = rank_key(r_cnts[b][lane], r_ids[b][lane]);
-                n = __popc(km);
+            const uint32_t s = it % kSkStages;
+            if (rwarp == 0) {
+                if (lane == 0) mbar_wait(&counted[b], (it >> 1) & 1); // all counter warps are done with query it
+                __syncwarp();
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&rank_empty[b]); // the counters may reuse this hand-over buffer
-            if (redo) {
-                // too many candidates for this path: the exact count-table kernels take the query
-                if (lane == 0) {
-                    enqueue(a, exact_class_for(w.postings, w.k_eff), w);
-                    if (a.stats) atomicAdd(&a.stats->overflow_requeues, 1ull);
+            R.sync();
+            const WorkItem w = meta[s].item;
+            const uint32_t nrec = (a.debug & 2u) ? 0u : s_nrec[b];
+            // the sketch is no longer needed: clear it for query it+2
+            if (!(a.debug & 16u))
+                for (uint32_t i = rtid; i < kSketchWords / 4; i += kSkResolvers) sk4[i] = make_uint4(0, 0, 0, 0);
+            // distinct candidates (the true match is recorded a few times at most, see s_known)
+            if (nrec != 0u) {
+                if (nrec <= kRecCap) {
+                    for (uint32_t i = rtid; i < nrec; i += kSkResolvers) {
+                        const uint32_t d = rec[i];
+                        uint32_t x = (d * kMult2) >> 26;
+                        for (uint32_t tries = 0;; ++tries) {
+                            const uint32_t old = atomicCAS(st.set_keys + x, pad, d);
+                            if (old == pad) {
+                                if (atomicAdd(&st.nset, 1u) >= kMaxCand) st.ovf = 1u;
+                                break;
+                            }
+                            if (old == d) break;
+                            x = (x + 1) & (kSetSlots - 1);
+                            if (tries >= kSetSlots || st.ovf) {
+                                st.ovf = 1u;
+                                break;
+                            }
+                        }
+                    }
+                } else if (rtid == 0) {
+                    st.ovf = 1u;
                 }
-            } else if (n == 0) {
-                if (lane == 0) a.out_counts[w.q] = 0;
-            } else {
-                group_sort_keys(g, r_keys, n, kMaxCand);
-                group_emit_results(g, a, w, r_keys, n, &r_count);
             }
-            if (lane == 0 && a.stats && !redo) atomicAdd(&a.stats->sketch_queries, 1ull);
-            __syncwarp();
+            R.sync();
+            if (rtid == 0) { // sketch cleared, records consumed: the counters may start query it+2 on them
+                s_nrec[b] = 0;
+                s_known[b] = pad;
+                mbar_arrive(&sk_free[b]);
+            }
+            uint32_t n = 0;
+            bool redo = false;
+            if (nrec != 0u) {
+                if (rwarp == 0) { // compact the set, reset it
+                    uint32_t nc = 0;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const uint32_t k = st.set_keys[lane + 32 * half];
+                        const bool occ = k != pad;
+                        const uint32_t om = __ballot_sync(0xFFFFFFFFu, occ);
+                        const uint32_t pos = nc + __popc(om & ((1u << lane) - 1u));
+                        if (occ && pos < kMaxCand) {
+                            st.c_ids[pos] = k;
+                            st.c_cnts[pos] = 0;
+                        }
+                        nc += __popc(om);
+                        st.set_keys[lane + 32 * half] = pad;
+                    }
+                    if (lane == 0) st.c_n = min(nc, kMaxCand);
+                }
+                R.sync();
+                redo = st.ovf != 0u;
+                const uint32_t nc = st.c_n;
+                if (!redo && rtid < w.n_rows) {
+                    // exact recount: every (candidate, row) pair is an equal-range search in a sorted row;
+                    // thread rtid owns row rtid (a query has at most 128 rows here)
+                    const uint32_t *row = reinterpret_cast<const uint32_t *>(stage + (size_t)s * kStageU4) + meta[s].row_off[rtid];
+                    const uint32_t len = meta[s].row_len[rtid];
+                    const uint32_t top = 1u << (31 - __clz(len | 1u));
+                    for (uint32_t c = 0; c < nc; ++c) {
+                        const uint32_t d = st.c_ids[c];
+                        uint32_t lo = 0; // lower bound by halving steps: lo = #elements < d
+                        for (uint32_t step = top; step; step >>= 1) {
+                            const uint32_t probe = lo + step;
+                            if (probe <= len && row[probe - 1] < d) lo = probe;
+                        }
+                        uint32_t m = 0;
+                        while (lo + m < len && row[lo + m] == d) ++m; // repeated (hash, id) pairs all count
+                        if (m) atomicAdd(&st.c_cnts[c], m);
+                    }
+                }
+                R.sync();
+                if (rwarp == 0 && !redo) {
+                    const bool keep = lane < nc && st.c_cnts[lane] >= w.min_score; // common.zig:140-145
+                    const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+                    if (keep) st.r_keys[__popc(km & ((1u << lane) - 1u))] = rank_key(st.c_cnts[lane], st.c_ids[lane]);
+                    n = __popc(km);
+                    __syncwarp();
+                }
+            }
+            if (rtid == 0) {
+                st.nset = st.ovf = 0;
+                mbar_arrive(&empty[s]); // the stage goes back to the producers
+            }
+            if (rwarp == 0) {
+                if (redo) {
+                    // too many candidates for this path: the exact count-table kernels take the query
+                    if (lane == 0) {
+                        enqueue(a, exact_class_for(w.postings, w.k_eff), w);
+                        if (a.stats) atomicAdd(&a.stats->overflow_requeues, 1ull);
+                    }
+                } else if (n == 0) {
+                    if (lane == 0) a.out_counts[w.q] = 0;
+                } else {
+                    group_sort_keys(W, st.r_keys, n, kMaxCand);
+                    group_emit_results(W, a, w, st.r_keys, n, &st.r_count);
+                }
+                if (lane == 0 && a.stats && !redo) atomicAdd(&a.stats->sketch_queries, 1ull);
+            }
+            R.sync(); // the group's scratch is reused by its next query
         }
         return;
     }
 
-    // ===== counters
-    const Group g{tid, (uint32_t)kSkCounters, 1u};
+    // ===== counters: no CTA barrier — each warp streams its slice of every query and arrives on `counted`
     for (uint32_t it = 0;; ++it) {
         const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
         if (idx >= count) break;
         const uint32_t s = it % kSkStages, b = it & 1u;
-        if (warp == 0) { // one poller; everybody else sleeps in the hardware barrier
-            if (lane == 0) mbar_wait(&full[s], (it / kSkStages) & 1);
-            __syncwarp();
+        if (lane == 0) {
+            mbar_wait(&full[s], (it / kSkStages) & 1);
+            if (it >= 2) mbar_wait(&sk_free[b], ((it >> 1) - 1) & 1); // sketch b cleared, records consumed
         }
-        g.sync();
-        const uint32_t total4 = meta[s].item.total4, n_rows = meta[s].item.n_rows;
+        __syncwarp();
+        const uint32_t total4 = meta[s].item.total4;
         const uint32_t thr_m1 = meta[s].item.min_score - 1u; // min_score >= 2 in this class
         const uint4 *st = stage + (size_t)s * kStageU4;
+        unsigned char *sketch_b = sketch_base + (size_t)b * kSketchWords * 4;
+        uint32_t *rec = rec_base + b * kRecCap;
         // "either 16-bit half >= thr_m1" in two ALU ops: add (0x8000 - thr_m1) to both halves, test bit 15
         // of each (counts stay below 8192, so nothing carries across).  A min_score above 32768 can never be
         // reached by <= 8192 postings: bias 0 then never fires.
         const uint32_t bias = thr_m1 < 0x8000u ? (0x8000u - thr_m1) * 0x10001u : 0u;
 
-        // pass 1: count sketch, two 16-bit counters per word: hash bits 30..18 pick the word, the sign bit
-        // the half.  All four adds of a 16-byte granule are issued before any result is used.  Row padding
-        // is made of unused docids spread over many values, so it needs no test here: it is counted like
-        // anything else, can only make a counter too high, and an exact recount gives it score 0.
+        // count sketch, two 16-bit counters per word: hash bits 30..18 pick the word, the sign bit the half.
+        // All four adds of a 16-byte granule are issued before any result is used.  Row padding is made of
+        // unused docids spread over many values, so it needs no test here: it is counted like anything else,
+        // can only make a counter too high, and an exact recount gives it score 0.
         if (!(a.debug & 1u)) {
 #pragma unroll 2
             for (uint32_t i = tid; i < total4; i += kSkCounters) {
@@ -671,109 +767,23 @@ __global__ void __launch_bounds__(kSkThreads, kCtasPerSm) search_sketch_kernel(B
                     // The true match lands here once per matching row.  After its first record its docid is
                     // "known": neutralise it and re-test, so the repeats leave after a dozen instructions
                     // (a stale s_known only costs a repeated record).
-                    const uint32_t known = s_known;
+                    const uint32_t known = s_known[b];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) t[e] = dd[e] == known ? 0u : t[e];
                     if ((t[0] | t[1] | t[2] | t[3]) & 0x80008000u) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
                             if (t[e] & (hv[e] < 0 ? 0x80000000u : 0x8000u)) { // this posting's own counter
-                                const uint32_t p = atomicAdd(&s_nrec, 1u);
+                                const uint32_t p = atomicAdd(&s_nrec[b], 1u);
                                 if (p < kRecCap) rec[p] = dd[e];
-                                s_known = dd[e];
+                                s_known[b] = dd[e];
                             }
                     }
                 }
             }
         }
-        g.sync();
-        const uint32_t nrec = (a.debug & 2u) ? 0u : s_nrec;
-        // the sketch is no longer needed: clear it for the next query
-        if (!(a.debug & 16u))
-            for (uint32_t i = tid; i < kSketchWords / 4; i += kSkCounters)
-                reinterpret_cast<uint4 *>(sketch_b)[i] = make_uint4(0, 0, 0, 0);
-        if (nrec != 0u) {
-            // distinct candidates (the true match is recorded about once per matching row)
-            if (nrec <= kRecCap) {
-                for (uint32_t i = tid; i < nrec; i += kSkCounters) {
-                    const uint32_t d = rec[i];
-                    uint32_t x = (d * kMult2) >> 26;
-                    for (uint32_t tries = 0;; ++tries) {
-                        const uint32_t old = atomicCAS(set_keys + x, pad, d);
-                        if (old == pad) {
-                            if (atomicAdd(&s_nset, 1u) >= kMaxCand) s_ovf = 1u;
-                            break;
-                        }
-                        if (old == d) break;
-                        x = (x + 1) & (kSetSlots - 1);
-                        if (tries >= kSetSlots || s_ovf) {
-                            s_ovf = 1u;
-                            break;
-                        }
-                    }
-                }
-            } else if (tid == 0) {
-                s_ovf = 1u;
-            }
-            g.sync();
-            // warp 0 compacts the set straight into the ranker's hand-over buffer (and resets the set)
-            if (tid < 32) {
-                if (it >= 2 && lane == 0) mbar_wait(&rank_empty[b], ((it >> 1) - 1) & 1);
-                __syncwarp();
-                uint32_t nc = 0;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const uint32_t k = set_keys[lane + 32 * half];
-                    const bool occ = k != pad;
-                    const uint32_t om = __ballot_sync(0xFFFFFFFFu, occ);
-                    const uint32_t pos = nc + __popc(om & ((1u << lane) - 1u));
-                    if (occ && pos < kMaxCand) {
-                        r_ids[b][pos] = k;
-                        r_cnts[b][pos] = 0;
-                    }
-                    nc += __popc(om);
-                    set_keys[lane + 32 * half] = pad;
-                }
-                if (lane == 0) {
-                    r_n[b] = min(nc, kMaxCand);
-                    r_redo[b] = s_ovf;
-                }
-            }
-            g.sync();
-            if (!s_ovf) {
-                // exact recount: every (candidate, row) pair is an equal-range search in a sorted row
-                const uint32_t *stw = reinterpret_cast<const uint32_t *>(st);
-                const uint32_t nc = r_n[b];
-                for (uint32_t r = tid; r < nc * 128u; r += kSkCounters) { // 128 = kSketchMaxRows
-                    const uint32_t c = r >> 7, row_i = r & 127u;
-                    if (row_i >= n_rows) continue;
-                    const uint32_t d = r_ids[b][c];
-                    const uint32_t *row = stw + meta[s].row_off[row_i];
-                    const uint32_t len = meta[s].row_len[row_i];
-                    // lower bound by halving steps (no data-dependent branches): lo = #elements < d
-                    uint32_t lo = 0;
-                    for (uint32_t step = 1u << (31 - __clz(len | 1u)); step; step >>= 1) {
-                        const uint32_t probe = lo + step;
-                        if (probe <= len && row[probe - 1] < d) lo = probe;
-                    }
-                    uint32_t m = 0;
-                    while (lo + m < len && row[lo + m] == d) ++m; // repeated (hash, id) pairs all count
-                    if (m) atomicAdd(&r_cnts[b][c], m);
-                }
-            }
-        } else if (tid == 0) {
-            if (it >= 2) mbar_wait(&rank_empty[b], ((it >> 1) - 1) & 1);
-            r_n[b] = 0;
-            r_redo[b] = 0;
-        }
-        g.sync();
-        if (tid == 0) {
-            r_item[b] = meta[s].item;
-            mbar_arrive(&empty[s]);     // the stage may be refilled
-            mbar_arrive(&rank_full[b]); // hand-over to the ranker (release)
-            s_nrec = s_nset = s_ovf = 0;
-            s_known = pad;
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&counted[b]); // my slice of query it is in the sketch (release)
     }
 }
 
@@ -1077,9 +1087,7 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_smem_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for<15>());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(search_sketch_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sketch_smem_bytes(2));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(search_sketch_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sketch_smem_bytes(1));
+    e = cudaFuncSetAttribute(search_sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
     return e;
 }
 
@@ -1104,10 +1112,7 @@ void launch_prepare_long(const BatchArgs &a, cudaStream_t st, int n_sms) {
 }
 
 void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms) {
-    if (a.debug & 32u) // experimental: three CTAs per SM with a single stage each
-        search_sketch_kernel<1, 3><<<n_sms * 3, kSkThreads, sketch_smem_bytes(1), st>>>(a);
-    else
-        search_sketch_kernel<2, 2><<<n_sms * 2, kSkThreads, sketch_smem_bytes(2), st>>>(a);
+    search_sketch_kernel<<<n_sms, kSkThreads, kSkSmemBytes, st>>>(a);
 }
 
 void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms) {
