@@ -728,6 +728,14 @@ fpx_status fpx_profile_read(fpx_ctx *ctx, fpx_profile *out) {
         ctx->prof.wide_queries = ds.wide_queries;
         ctx->prof.sketch_queries = ds.sketch_queries;
         ctx->prof.overflow_requeues = ds.overflow_requeues;
+        if (ctx->debug & 512u) {
+            std::fprintf(stderr, "[fpx dbg] producer: wait_empty %.0f iter %.0f clk/query (%llu) | resolver: wait_counted %.0f to_sk_free %.0f iter %.0f (%llu) | counter: wait_full %.0f +sk_free %.0f iter %.0f (%llu)\n",
+                         (double)ds.dbg[0] / (double)(ds.dbg[2] ? ds.dbg[2] : 1), (double)ds.dbg[1] / (double)(ds.dbg[2] ? ds.dbg[2] : 1), ds.dbg[2],
+                         (double)ds.dbg[3] / (double)(ds.dbg[6] ? ds.dbg[6] : 1), (double)ds.dbg[4] / (double)(ds.dbg[6] ? ds.dbg[6] : 1),
+                         (double)ds.dbg[5] / (double)(ds.dbg[6] ? ds.dbg[6] : 1), ds.dbg[6],
+                         (double)ds.dbg[7] / (double)(ds.dbg[10] ? ds.dbg[10] : 1), (double)ds.dbg[8] / (double)(ds.dbg[10] ? ds.dbg[10] : 1),
+                         (double)ds.dbg[9] / (double)(ds.dbg[10] ? ds.dbg[10] : 1), ds.dbg[10]);
+        }
     }
     *out = ctx->prof;
     return FPX_OK;

@@ -422,18 +422,33 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// try_wait with a suspend-time hint: the thread is parked by the hardware until the phase completes (or
-// the hint expires) instead of spinning — spinning lanes would steal issue slots from the ALU-bound counters.
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+// Two flavours of waiting.  try_wait with a suspend-time hint parks the thread in hardware (no issue slots
+// burnt, but the wake-up is not immediate); the plain form returns quickly and is polled.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parity, uint32_t ns) {
     uint32_t ok = 0;
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
                  : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+                 : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
                  : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t mode = 0) {
+    if (mode == 0) {
+        while (!mbar_try_wait_hint(bar, parity, 1000000u)) {
+        }
+    } else if (mode == 1) {
+        while (!mbar_try_wait(bar, parity)) {
+        }
+    } else {
+        while (!mbar_try_wait(bar, parity)) __nanosleep(32);
     }
 }
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) { mbar_wait(bar, parity); }
@@ -468,15 +483,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // counter is already >= min_score-1 and d is recorded.  Its exact count is then taken from the rows.
 // The kernel is bound by integer-ALU issue, not by memory, so everything per posting is kept minimal.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSkCounterWarps = 16;
 constexpr int kSkResolverGroups = 2;
 constexpr int kSkResolverWarps = 4; // per group
-constexpr int kSkProducerWarps = 8; // row r of a query is issued by producer warp r % 8
 constexpr int kSkStages = 4;
-constexpr int kSkFirstResolver = kSkCounterWarps;
-constexpr int kSkFirstProducer = kSkCounterWarps + kSkResolverGroups * kSkResolverWarps;
-constexpr int kSkThreads = (kSkFirstProducer + kSkProducerWarps) * 32;
-constexpr int kSkCounters = kSkCounterWarps * 32;
 constexpr int kSkResolvers = kSkResolverWarps * 32;
 constexpr uint32_t kSketchLog = 14;       // 16384 u16 counters, two per 32-bit word = 32 KB
 constexpr uint32_t kSketchWords = (1u << kSketchLog) / 2;
@@ -498,7 +507,13 @@ struct ResolverState { // private to one resolver group
     uint32_t nset, ovf, c_n, r_count;
 };
 
-__global__ void __launch_bounds__(kSkThreads, 1) search_sketch_kernel(BatchArgs a) {
+template <int kSkCounterWarps, int kSkProducerWarps>
+__global__ void __launch_bounds__((kSkCounterWarps + kSkResolverGroups * kSkResolverWarps + kSkProducerWarps) * 32, 1)
+search_sketch_kernel(BatchArgs a) {
+    constexpr int kSkFirstResolver = kSkCounterWarps;
+    constexpr int kSkFirstProducer = kSkCounterWarps + kSkResolverGroups * kSkResolverWarps;
+    constexpr int kSkThreads = (kSkFirstProducer + kSkProducerWarps) * 32;
+    constexpr int kSkCounters = kSkCounterWarps * 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *sketch_base = smem_raw;                                   // 2 x 32 KB
     uint4 *stage = reinterpret_cast<uint4 *>(smem_raw + 2 * (size_t)kSketchWords * 4);
@@ -512,10 +527,15 @@ __global__ void __launch_bounds__(kSkThreads, 1) search_sketch_kernel(BatchArgs 
     const uint32_t count = a.counters->qcount[kSketchClass];
     const WorkItem *items = a.items + (size_t)kSketchClass * a.n_queries;
     const uint32_t pad = a.snap.pad_id;
+    const uint32_t wm = (a.debug >> 6) & 3u; // wait flavour (profiling knob)
+    const bool timed = (a.debug & 512u) && blockIdx.x == 0 && a.stats != nullptr;
+    auto tick = [&](int slot, long long t0) {
+        if (timed) atomicAdd(&a.stats->dbg[slot], (unsigned long long)(clock64() - t0));
+    };
 
     if (tid == 0) {
         for (int s = 0; s < kSkStages; ++s) {
-            mbar_init(&full[s], kSkProducerWarps);
+            mbar_init(&full[s], 2);
             mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -533,63 +553,67 @@ __global__ void __launch_bounds__(kSkThreads, 1) search_sketch_kernel(BatchArgs 
     __syncthreads();
 
     if (warp >= kSkFirstProducer) {
-        // ===== producers
-        const uint32_t p = warp - kSkFirstProducer;
+        // ===== producers: warp pair `pair` owns stage `pair` and every kSkStages-th query; within the pair
+        // warp `half` issues the even / odd rows.  Each lane holds two row descriptors of its warp's rows.
+        static_assert(kSkProducerWarps == 2 * kSkStages, "one producer warp pair per stage");
+        const uint32_t p = warp - kSkFirstProducer, pair = p >> 1, half = p & 1u;
         const uint4 *docids4 = reinterpret_cast<const uint4 *>(a.snap.docids);
+        const uint32_t s = pair;
+        uint4 *dst = stage + (size_t)s * kStageU4;
         auto item_at = [&](uint32_t it, WorkItem &w) -> bool {
             const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
             if (idx >= count) return false;
             w = items[idx];
             return true;
         };
-        auto rows_of = [&](const WorkItem &w, uint4 (&d)[4]) {
+        auto rows_of = [&](const WorkItem &w, uint4 (&d)[2]) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t r = lane + 32 * j;
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t r = 2u * (lane + 32 * j) + half;
                 d[j] = r < w.n_rows ? a.rows[w.rows_off + r] : make_uint4(0u, 0u, 0u, 0u);
             }
         };
         WorkItem w{}, w1{};
-        uint4 d[4], d1[4];
-        bool have = item_at(0, w);
+        uint4 d[2], d1[2];
+        bool have = item_at(pair, w);
         if (have) rows_of(w, d);
-        for (uint32_t it = 0; have; ++it) {
-            const uint32_t s = it % kSkStages;
-            const bool have1 = item_at(it + 1, w1); // next query's item and rows: in flight during the issue
+        for (uint32_t it = pair, use = 0; have; it += kSkStages, ++use) {
+            const bool have1 = item_at(it + kSkStages, w1); // my next query: in flight during wait + issue
             if (have1) rows_of(w1, d1);
-            if (it >= kSkStages) { // wait until the resolvers released the previous tenant of this stage
-                if (lane == 0) mbar_wait(&empty[s], ((it / kSkStages) - 1) & 1);
+            const long long tp0 = clock64();
+            if (use > 0) { // wait until the resolvers released the previous tenant of my stage
+                if (lane == 0) mbar_wait(&empty[s], (use - 1) & 1, wm);
                 __syncwarp();
             }
-            uint4 *dst = stage + (size_t)s * kStageU4;
-            // the row's place in the stage (d.z) was computed by prepare_kernel; my share = rows r % 8 == p
-            uint32_t mine = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) mine += (lane % kSkProducerWarps == p) ? (d[j].y + 3) >> 2 : 0u;
+            if (p == 0 && lane == 0) tick(0, tp0);
+            // the row's place in the stage (d.z) was computed by prepare_kernel
+            uint32_t mine = ((d[0].y + 3) >> 2) + ((d[1].y + 3) >> 2);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
-            if (p == 0) { // stage directory for the exact recount
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    meta[s].row_off[lane + 32 * j] = d[j].z * 4u;
-                    meta[s].row_len[lane + 32 * j] = d[j].y;
-                }
-                if (lane == 0) meta[s].item = w;
+            for (int j = 0; j < 2; ++j) { // stage directory for the exact recount
+                const uint32_t r = 2u * (lane + 32 * j) + half;
+                meta[s].row_off[r] = d[j].z * 4u;
+                meta[s].row_len[r] = d[j].y;
             }
+            if (half == 0 && lane == 0) meta[s].item = w;
             if (a.debug & 8u) mine = 0;
             __syncwarp();
             if (lane == 0) mbar_expect_tx(&full[s], mine * 16u); // expect_tx precedes my copies (release)
             __syncwarp();
             if (!(a.debug & 8u)) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (d[j].y && (lane % kSkProducerWarps == p))
-                        bulk_g2s(dst + d[j].z, docids4 + d[j].x, ((d[j].y + 3) >> 2) * 16u, &full[s]);
+                for (int j = 0; j < 2; ++j)
+                    if (d[j].y) bulk_g2s(dst + d[j].z, docids4 + d[j].x, ((d[j].y + 3) >> 2) * 16u, &full[s]);
             }
             have = have1;
             w = w1;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) d[j] = d1[j];
+            d[0] = d1[0];
+            d[1] = d1[1];
+            if (p == 0 && lane == 0) {
+                tick(1, tp0);
+                if (timed) atomicAdd(&a.stats->dbg[2], 1ull);
+            }
         }
         return;
     }
@@ -609,11 +633,13 @@ __global__ void __launch_bounds__(kSkThreads, 1) search_sketch_kernel(BatchArgs 
             const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
             if (idx >= count) break;
             const uint32_t s = it % kSkStages;
+            const long long tr0 = clock64();
             if (rwarp == 0) {
-                if (lane == 0) mbar_wait(&counted[b], (it >> 1) & 1); // all counter warps are done with query it
+                if (lane == 0) mbar_wait(&counted[b], (it >> 1) & 1, wm); // all counter warps are done with query it
                 __syncwarp();
             }
             R.sync();
+            if (gidx == 0 && rtid == 0) tick(3, tr0);
             const WorkItem w = meta[s].item;
             const uint32_t nrec = (a.debug & 2u) ? 0u : s_nrec[b];
             // the sketch is no longer needed: clear it for query it+2
@@ -648,6 +674,7 @@ __global__ void __launch_bounds__(kSkThreads, 1) search_sketch_kernel(BatchArgs 
                 s_nrec[b] = 0;
                 s_known[b] = pad;
                 mbar_arrive(&sk_free[b]);
+                if (gidx == 0) tick(4, tr0);
             }
             uint32_t n = 0;
             bool redo = false;
@@ -719,6 +746,10 @@ __global__ void __launch_bounds__(kSkThreads, 1) search_sketch_kernel(BatchArgs 
                 if (lane == 0 && a.stats && !redo) atomicAdd(&a.stats->sketch_queries, 1ull);
             }
             R.sync(); // the group's scratch is reused by its next query
+            if (gidx == 0 && rtid == 0) {
+                tick(5, tr0);
+                if (timed) atomicAdd(&a.stats->dbg[6], 1ull);
+            }
         }
         return;
     }
@@ -728,9 +759,12 @@ __global__ void __launch_bounds__(kSkThreads, 1) search_sketch_kernel(BatchArgs 
         const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
         if (idx >= count) break;
         const uint32_t s = it % kSkStages, b = it & 1u;
+        const long long tc0 = clock64();
         if (lane == 0) {
-            mbar_wait(&full[s], (it / kSkStages) & 1);
-            if (it >= 2) mbar_wait(&sk_free[b], ((it >> 1) - 1) & 1); // sketch b cleared, records consumed
+            mbar_wait(&full[s], (it / kSkStages) & 1, wm);
+            if (warp == 0) tick(7, tc0);
+            if (it >= 2) mbar_wait(&sk_free[b], ((it >> 1) - 1) & 1, wm); // sketch b cleared, records consumed
+            if (warp == 0) tick(8, tc0);
         }
         __syncwarp();
         const uint32_t total4 = meta[s].item.total4;
@@ -784,6 +818,10 @@ __global__ void __launch_bounds__(kSkThreads, 1) search_sketch_kernel(BatchArgs 
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&counted[b]); // my slice of query it is in the sketch (release)
+        if (warp == 0 && lane == 0) {
+            tick(9, tc0);
+            if (timed) atomicAdd(&a.stats->dbg[10], 1ull);
+        }
     }
 }
 
@@ -1087,7 +1125,7 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_smem_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for<15>());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(search_sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
+    e = cudaFuncSetAttribute(search_sketch_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
     return e;
 }
 
@@ -1112,7 +1150,7 @@ void launch_prepare_long(const BatchArgs &a, cudaStream_t st, int n_sms) {
 }
 
 void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms) {
-    search_sketch_kernel<<<n_sms, kSkThreads, kSkSmemBytes, st>>>(a);
+    search_sketch_kernel<16, 8><<<n_sms, 1024, kSkSmemBytes, st>>>(a); // 16 counter + 8 resolver + 8 producer warps
 }
 
 void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms) {

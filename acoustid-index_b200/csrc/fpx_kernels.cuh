@@ -57,6 +57,7 @@ struct BatchCounters {
 
 struct DeviceStats { // accumulated across batches (profiling)
     unsigned long long queries, unique_terms, postings, results, wide_queries, overflow_requeues, sketch_queries;
+    unsigned long long dbg[16]; // phase timers of the sketch kernel (CTA 0 only), FPX_DEBUG_ABLATE bit 9
 };
 
 struct BatchArgs {
