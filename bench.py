@@ -193,6 +193,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sketch", action="store_true", help="A/B: exact count-table kernels only")
+    ap.add_argument("--chunk", type=int, default=0, help="queries per pipelined chunk of the host-buffer call (0 = library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -221,7 +222,8 @@ def main():
     del items
     log("[bench] segment: %d blocks written in %.1fs" % (seg.num_blocks, time.time() - t))
     t = time.time()
-    ctx = pkg.Context(device=local_rank, profile=True, host_threads=host_threads, no_sketch=args.no_sketch)
+    ctx = pkg.Context(device=local_rank, profile=True, host_threads=host_threads, no_sketch=args.no_sketch,
+                      chunk_queries=args.chunk)
     snap = pkg.swap_snapshot(ctx, [seg])
     info = snap.info()
     log("[bench] snapshot: %d terms, %d postings, %.2f GB in HBM, built in %.1fs"
@@ -296,6 +298,7 @@ def main():
     for _ in range(3):
         e2e_step()
     barrier()
+    ctx.profile_reset()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
@@ -306,6 +309,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     e2e_qps = world * nq * args.steps / e2e_s
+    prof_e2e = ctx.profile()
     h2d = int(h_terms.numel() * 4 + h_offs.numel() * 8 + h_opts.numel() * 4)
     d2h = int(h_ids.numel() * 4 + h_sc.numel() * 4 + h_cnt.numel() * 4)
     # the e2e results must equal the device-resident ones
@@ -351,7 +355,11 @@ def main():
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": workload_config(wl, "replicated corpus, query batch per GPU x%d" % world),
         "clocks": clocks,
-        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s / args.steps * 1e3, "h2d_ms_per_step": prof_e2e["h2d_ms"] / args.steps,
+                "d2h_ms_per_step": prof_e2e["d2h_ms"] / args.steps,
+                "kernel_ms_per_step": (prof_e2e["prepare_ms"] + prof_e2e["sketch_ms"] + prof_e2e["search_ms"] +
+                                       prof_e2e["wide_ms"]) / args.steps},
         "gpu_launches": 7 * args.steps,  # prepare, prepare_long, sketch, 3 exact classes, wide
         "roofline": roofline,
     }
