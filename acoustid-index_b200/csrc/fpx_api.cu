@@ -447,6 +447,7 @@ fpx_status fpx_snapshot_commit(fpx_snapshot_builder *b, fpx_snapshot **out) {
     s->dev.table_shift = 32 - log2cap;
     s->dev.docids = s->d_docids;
     s->dev.pad_id = c->pad_id;
+    s->dev.pad_spread = c->pad_spread ? 1u : 0u;
     s->info.n_segments = b->compiler.n_segments();
     s->info.n_terms = nt;
     s->info.n_postings = c->n_postings;
@@ -692,6 +693,20 @@ fpx_status fpx_profile_reset(fpx_ctx *ctx) {
     }
     ctx->pending.clear();
     ctx->prof = fpx_profile{};
+    return FPX_OK;
+}
+
+fpx_status fpx_debug_set(fpx_ctx *ctx, uint32_t bits) {
+    if (!ctx) return set_error(FPX_INVALID_ARGUMENT, "null ctx");
+    ctx->debug = bits;
+    if (const uint32_t g = (bits >> 16) & 0xFFu) { // experiment: L2 fetch granularity hint (32 / 64 / 128 bytes)
+        FPX_CUDA(cudaSetDevice(ctx->device));
+        FPX_CUDA(cudaDeviceSynchronize());
+        FPX_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g));
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        std::fprintf(stderr, "[fpx dbg] L2 fetch granularity limit now %zu\n", got);
+    }
     return FPX_OK;
 }
 

@@ -93,6 +93,7 @@ __device__ uint32_t make_item(const BatchArgs &a, uint32_t q, uint32_t rows_off,
     // expected records = postings that find their counter already at min_score-1 (Poisson, 16384 counters)
     if (o.min_score == 2 && postings > 1500) sketch_ok = false;
     if (o.min_score == 3 && postings > 4500) sketch_ok = false;
+    if ((a.debug & 1024u) && (!a.snap.pad_spread || o.min_score > 0x2000u)) sketch_ok = false; // search_sketch2_kernel
     return sketch_ok ? (uint32_t)kSketchClass : exact_class_for(postings, k_eff);
 }
 
@@ -826,6 +827,399 @@ search_sketch_kernel(BatchArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// sketch path, second generation (FPX variant bit 1024): roles merged, the query held in registers, and a
+// *windowed* sketch.  Two CTAs per SM, each an independent query pipeline of 8 worker warps + 4 producer
+// warps; the hardware interleaves the two pipelines.
+//   producers (4 warps)  all four issue a quarter of every query's row copies (TMA bulk, as above) into one of
+//                        two 32 KB stages
+//   workers   (8 warps)  each thread loads its <= 8 granules (32 docids) of the staged query into registers and
+//                        keeps them: count (16 atomics in flight per thread before any result is looked at) ->
+//                        barrier A, the only rendezvous; the stage goes back to the producers -> every warp
+//                        de-duplicates the few candidate records for itself (warp votes), clears its slice of
+//                        the sketch, compares its register-resident granules with each candidate (exact
+//                        recount) and adds its share to the candidates' counts -> warps 1..7 go straight on to
+//                        the next query; warp 0 waits for the eight shares (mbarrier), checks the heavy
+//                        counters, ranks and writes the results (registers + shuffles).
+//
+// Windowed sketch.  16384 counters of 16 bits (two per word).  The atomic add returns the counter's previous
+// value `old`; with t = min_score-1 a posting is an *event* iff t <= old < t+W (W = 4): two biased adds and one
+// logic op per posting, accumulated per granule.  An event records its docid as a candidate; the event that sees
+// old == t+W-1 also lists the counter as heavy.  Later arrivals at that counter are silent.  Without the
+// window the ~75 postings of a true match would all be events, and since an event costs its whole warp a
+// divergent detour the kernel would spend a third of its time there.
+// Why this is exact: (a) a counter that never left the window recorded every posting that arrived at
+// position >= t, and a doc with >= min_score = t+1 postings in it has such a posting; (b) for a heavy counter
+// the total number of arrivals is its final value, the recorded candidates that hash to it get exact counts
+// from the recount, and what is left over ("hidden") bounds the count of every unrecorded doc in that
+// counter: hidden < min_score means no unrecorded doc can be a result; otherwise the query is re-queued to the
+// exact count-table kernels.  Candidate scores never come from the sketch.
+// The kernel is bound by instruction issue, so the common path is branch-free.
+// Needs row padding above every live docid (SnapshotDev::pad_spread) and min_score-1 < 0x2000.
+// ------------------------------------------------------------------------------------------------
+constexpr int kS2WorkerWarps = 8;
+constexpr int kS2ProducerWarps = 4;
+constexpr int kS2Workers = kS2WorkerWarps * 32;
+constexpr int kS2Threads = (kS2WorkerWarps + kS2ProducerWarps) * 32;
+constexpr int kS2Stages = 2;
+constexpr uint32_t kS2RecCap = 128;   // candidate records per query (with repeats): four per lane of warp 0
+constexpr uint32_t kS2HeavyCap = 32;  // heavy counters per query: one per lane of warp 0
+constexpr uint32_t kS2Window = 4;
+constexpr size_t kS2SmemBytes = (size_t)kS2Stages * kStageU4 * 16; // the stages; the sketch is static shared memory
+static_assert(kStageU4 == 8 * kS2Workers, "a staged query is exactly eight granules per worker thread");
+
+struct S2Shared {
+    uint64_t full[kS2Stages], empty[kS2Stages];
+    WorkItem item[kS2Stages];
+    uint32_t nrec[2], nheavy[2], rec[2][kS2RecCap], heavy[2][kS2HeavyCap]; // per query parity
+    uint32_t c_cnts[2][kMaxCand]; // exact counts of the candidates, per query parity
+    uint64_t cleared, counted;    // per worker warp: my slice of the sketch is clear / my exact counts are added
+};
+static_assert(kMaxCand == 32, "one candidate per lane of warp 0");
+
+// hash bits 31..19 pick the word, bit 18 the half
+__device__ __forceinline__ uint32_t s2_word(uint32_t hv) { return hv >> 19; }
+__device__ __forceinline__ bool s2_upper(uint32_t hv) { return (hv & 0x40000u) != 0u; }
+
+// Rare path (per thread): one of the four postings of granule `v` arrived inside the window of its counter
+// word.  o = previous values of the four words; checks each posting's own counter.
+__device__ __forceinline__ void s2_event(uint4 v, uint4 o, uint32_t thr_m1, uint32_t *nrec, uint32_t *rec,
+                                         uint32_t *nheavy, uint32_t *heavy) {
+#pragma unroll 1
+    for (int e = 0; e < 4; ++e) {
+        const uint32_t hv = v.x * kMult;
+        const uint32_t rel = (s2_upper(hv) ? o.x >> 16 : o.x & 0xFFFFu) - thr_m1; // my own counter, before my add
+        if (rel < kS2Window) {
+            const uint32_t pos = atomicAdd(nrec, 1u);
+            if (pos < kS2RecCap) rec[pos] = v.x;
+            if (rel == kS2Window - 1u) { // the window closes: the counter is heavy
+                const uint32_t hp = atomicAdd(nheavy, 1u);
+                if (hp < kS2HeavyCap) heavy[hp] = hv >> 18; // counter index: word * 2 + half
+            }
+        }
+        v = make_uint4(v.y, v.z, v.w, v.x);
+        o = make_uint4(o.y, o.z, o.w, o.x);
+    }
+}
+
+// One trip of the count: thread `tid` takes granules tid + (4T+k)*256, k = 0..3, keeps them in v[4T+k], adds
+// their sixteen docids to the sketch (all sixteen atomics issued before any result is looked at) and handles
+// events.  FULL: all four granules lie inside the query.  b_lo / b_hi: per 16-bit half, 0x8000 - t and
+// 0x8000 - t - W, so bit 15 of (old + b_lo) & ~(old + b_hi) says t <= old < t+W (counts stay below 0x2000 + t,
+// nothing carries across the halves).
+template <int T, bool FULL>
+__device__ __forceinline__ void s2_trip(uint4 (&v)[8], const uint4 *sg, uint32_t tid, uint32_t total4, uint4 pad4,
+                                        uint32_t *sk, uint32_t b_lo, uint32_t b_hi, uint32_t thr_m1, uint32_t *nrec,
+                                        uint32_t *rec, uint32_t *nheavy, uint32_t *heavy) {
+    uint32_t oo[16];
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t i = tid + (4 * T + k) * kS2Workers;
+        const bool act = FULL || i < total4;
+        v[4 * T + k] = sg[i]; // inside the stage even when outside the query
+        lo[k] = act ? 1u : 0u; // adding 0 leaves the sketch alone
+        hi[k] = act ? 0x10000u : 0u;
+        if (!FULL && !act) v[4 * T + k] = pad4;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t dd[4] = {v[4 * T + k].x, v[4 * T + k].y, v[4 * T + k].z, v[4 * T + k].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t hv = dd[e] * kMult;
+            oo[4 * k + e] = atomicAdd(sk + s2_word(hv), s2_upper(hv) ? hi[k] : lo[k]);
+        }
+    }
+    uint32_t hotg[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc |= (oo[4 * k + e] + b_lo) & ~(oo[4 * k + e] + b_hi);
+        hotg[k] = acc & 0x80008000u;
+    }
+    if (hotg[0] | hotg[1] | hotg[2] | hotg[3]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (hotg[k] && (FULL || lo[k]))
+                s2_event(v[4 * T + k], make_uint4(oo[4 * k], oo[4 * k + 1], oo[4 * k + 2], oo[4 * k + 3]), thr_m1, nrec, rec,
+                         nheavy, heavy);
+    }
+}
+
+__global__ void __launch_bounds__(kS2Threads, 2) search_sketch2_kernel(BatchArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint4 *stage = reinterpret_cast<uint4 *>(smem_raw);
+    __shared__ __align__(16) uint32_t sk[kSketchWords]; // static: its address folds into the ATOMS operand
+    __shared__ S2Shared sh;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t count = a.counters->qcount[kSketchClass];
+    const WorkItem *items = a.items + (size_t)kSketchClass * a.n_queries;
+    const uint32_t pad = a.snap.pad_id;
+
+    if (tid == 0) {
+        for (int s = 0; s < kS2Stages; ++s) {
+            mbar_init(&sh.full[s], kS2ProducerWarps);
+            mbar_init(&sh.empty[s], 1);
+        }
+        mbar_init(&sh.cleared, kS2WorkerWarps);
+        mbar_init(&sh.counted, kS2WorkerWarps);
+        sh.nrec[0] = sh.nrec[1] = 0;
+        sh.nheavy[0] = sh.nheavy[1] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // the sketch, and the stages too: a partial trip reads (and ignores) granules beyond the query
+    for (uint32_t i = tid; i < kS2SmemBytes / 16; i += kS2Threads)
+        reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < kSketchWords / 4; i += kS2Threads) reinterpret_cast<uint4 *>(sk)[i] = make_uint4(0, 0, 0, 0);
+    if (tid < 2 * kMaxCand) sh.c_cnts[tid / kMaxCand][tid % kMaxCand] = 0;
+    __syncthreads();
+
+    if (warp >= kS2WorkerWarps) {
+        // ===== producers: warp p copies rows p, p+4, p+8, ... of every query; lane l holds row 4*l + p
+        const uint32_t p = warp - kS2WorkerWarps;
+        const uint4 *docids4 = reinterpret_cast<const uint4 *>(a.snap.docids);
+        auto item_at = [&](uint32_t it, WorkItem &w) -> bool {
+            const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
+            if (idx >= count) return false;
+            w = items[idx];
+            return true;
+        };
+        auto row_of = [&](const WorkItem &w) -> uint4 {
+            const uint32_t r = (uint32_t)kS2ProducerWarps * lane + p;
+            return r < w.n_rows ? a.rows[w.rows_off + r] : make_uint4(0u, 0u, 0u, 0u);
+        };
+        WorkItem w{}, w1{};
+        uint4 d = make_uint4(0u, 0u, 0u, 0u), d1 = make_uint4(0u, 0u, 0u, 0u);
+        bool have = item_at(0, w);
+        if (have) d = row_of(w);
+        for (uint32_t it = 0; have; ++it) {
+            const uint32_t s = it & 1u;
+            const bool have1 = item_at(it + 1, w1); // next query's descriptors: in flight during wait + issue
+            if (have1) d1 = row_of(w1);
+            if (it >= kS2Stages) { // the workers hold the previous tenant of this stage in registers now
+                if (lane == 0) mbar_wait(&sh.empty[s], ((it >> 1) - 1) & 1);
+                __syncwarp();
+            }
+            uint32_t mine = (d.y + 3) >> 2;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
+            if (p == 0 && lane == 0) sh.item[s] = w;
+            if (a.debug & 8u) mine = 0;
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(&sh.full[s], mine * 16u); // expect_tx precedes my copies (release)
+            __syncwarp();
+            if (!(a.debug & 8u) && d.y)
+                bulk_g2s(stage + (size_t)s * kStageU4 + d.z, docids4 + d.x, ((d.y + 3) >> 2) * 16u, &sh.full[s]);
+            have = have1;
+            w = w1;
+            d = d1;
+        }
+        return;
+    }
+
+    // ===== workers
+    const Group R{tid, (uint32_t)kS2Workers, 1u};
+    uint4 *sk4 = reinterpret_cast<uint4 *>(sk);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t n_res = 0; // queries with candidates so far: phase of `counted`
+    for (uint32_t it = 0;; ++it) {
+        const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
+        if (idx >= count) break;
+        const uint32_t s = it & 1u;
+        if (lane == 0) {
+            mbar_wait(&sh.full[s], (it >> 1) & 1);
+            if (it > 0) mbar_wait(&sh.cleared, (it - 1) & 1); // every warp has cleared its slice of the sketch
+        }
+        __syncwarp();
+        const WorkItem w = sh.item[s];
+        const uint32_t total4 = w.total4;
+        const uint32_t thr_m1 = w.min_score - 1u; // 1 <= min_score-1 < 0x2000 in this class
+        const uint4 *sg = stage + (size_t)s * kStageU4;
+        const uint32_t b_lo = (0x8000u - thr_m1) * 0x10001u, b_hi = b_lo - kS2Window * 0x10001u;
+        // granules beyond the query: four distinct row-padding values (no live docid, no repeated value)
+        const uint4 pad4 = make_uint4(pad, pad + 1, pad + 2, pad + 3);
+
+        // ---- count: thread t owns granules t, t+256, ... of the staged query and keeps them in registers.
+        // Row padding is made of unused docids: counted like anything else, never equal to a candidate.
+        uint4 v[8];
+#define FPX_S2_ARGS v, sg, tid, total4, pad4, sk, b_lo, b_hi, thr_m1, &sh.nrec[s], sh.rec[s], &sh.nheavy[s], sh.heavy[s]
+        if (a.debug & 1u) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = pad4;
+        } else if (total4 >= 8u * kS2Workers) {
+            s2_trip<0, true>(FPX_S2_ARGS);
+            s2_trip<1, true>(FPX_S2_ARGS);
+        } else if (total4 > 4u * kS2Workers) {
+            s2_trip<0, true>(FPX_S2_ARGS);
+            s2_trip<1, false>(FPX_S2_ARGS);
+        } else {
+            s2_trip<0, false>(FPX_S2_ARGS);
+#pragma unroll
+            for (int k = 4; k < 8; ++k) v[k] = pad4;
+        }
+#undef FPX_S2_ARGS
+        R.sync(); // A — the only rendezvous of the eight warps: sketch, registers and records are complete
+        const uint32_t nrec = (a.debug & 2u) ? 0u : sh.nrec[s];
+        const uint32_t r0 = lane < min(nrec, kS2RecCap) ? sh.rec[s][lane] : pad;
+        uint32_t my_heavy = 0, my_total = 0; // warp 0: lane j keeps heavy counter j and its final value = arrivals
+        uint32_t nheavy = 0;
+        bool ovf = nrec > kS2RecCap;
+        if (warp == 0) {
+            if (lane == 0) {
+                mbar_arrive(&sh.empty[s]); // the stage goes back to the producers
+                // the other parity's words: every warp read them before barrier A of this query
+                sh.nrec[s ^ 1u] = 0;
+                sh.nheavy[s ^ 1u] = 0;
+            }
+            if (nrec != 0u) { // final values of the heavy counters, before the sketch is cleared
+                nheavy = sh.nheavy[s];
+                if (nheavy > kS2HeavyCap) {
+                    ovf = true;
+                    nheavy = kS2HeavyCap;
+                }
+                if (lane < nheavy) {
+                    my_heavy = sh.heavy[s][lane];
+                    const uint32_t wv = sk[my_heavy >> 1];
+                    my_total = (my_heavy & 1u) ? wv >> 16 : wv & 0xFFFFu;
+                }
+            }
+            // heavy counters are read: my_total as an operand makes the arrive wait for the load's result
+            asm volatile("bar.arrive 2, %0;" ::"r"(kS2Workers), "r"(my_total) : "memory");
+        }
+        // distinct candidates, computed by every warp for itself (registers + votes): lane c keeps candidate c
+        uint32_t my_cand = pad, nc = 0;
+        if (nrec != 0u) {
+            if (nrec <= 32u) {
+                const uint32_t same = __match_any_sync(0xFFFFFFFFu, r0);
+                const uint32_t lm = __ballot_sync(0xFFFFFFFFu, r0 != pad && (same & lt_mask) == 0u);
+                nc = __popc(lm);
+                my_cand = __shfl_sync(0xFFFFFFFFu, r0, __fns(lm, 0, lane + 1) & 31u);
+                if (lane >= nc) my_cand = pad;
+            } else {
+                uint32_t r[4];
+                r[0] = r0;
+#pragma unroll
+                for (int j = 1; j < 4; ++j) r[j] = (lane + 32 * j < min(nrec, kS2RecCap)) ? sh.rec[s][lane + 32 * j] : pad;
+                for (;;) { // repeatedly take the first record not yet covered
+                    uint32_t cand = pad;
+                    bool found = false;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, r[j] != pad);
+                        if (!found && m != 0u) {
+                            cand = __shfl_sync(0xFFFFFFFFu, r[j], __ffs(m) - 1);
+                            found = true;
+                        }
+                    }
+                    if (!found) break;
+                    if (nc == kMaxCand) {
+                        ovf = true;
+                        break;
+                    }
+                    if (lane == nc) my_cand = cand;
+                    ++nc;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) r[j] = r[j] == cand ? pad : r[j];
+                }
+            }
+        }
+        // the sketch is no longer needed: clear my slice for the next query
+        if (warp != 0) asm volatile("bar.sync 2, %0;" ::"r"(kS2Workers) : "memory"); // warp 0 has read the heavy counters
+        if (!(a.debug & 16u))
+            for (uint32_t i = tid; i < kSketchWords / 4; i += kS2Workers) sk4[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.cleared);
+        if (nrec == 0u) {
+            if (tid == 0) {
+                a.out_counts[w.q] = 0;
+                if (a.stats) atomicAdd(&a.stats->sketch_queries, 1ull);
+            }
+            continue;
+        }
+        if (!ovf) {
+            // exact recount from registers: one "granule contains d" test per granule; a thread that holds a
+            // granule with the same docid twice (a fingerprint with a repeated hash: sorted rows keep the copies
+            // adjacent) counts element by element.  Padding never equals a candidate.
+            bool dup = false;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dup = dup || v[k].x == v[k].y || v[k].y == v[k].z || v[k].z == v[k].w;
+            for (uint32_t c = 0; c < nc; ++c) {
+                const uint32_t d = __shfl_sync(0xFFFFFFFFu, my_cand, c);
+                uint32_t m = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (v[k].x == d || v[k].y == d || v[k].z == d || v[k].w == d) m += 1;
+                if (dup) { // rare: exact multiplicities
+                    m = 0;
+#pragma unroll 1
+                    for (int k = 0; k < 8; ++k) {
+                        m += (v[0].x == d) + (v[0].y == d) + (v[0].z == d) + (v[0].w == d);
+                        const uint4 t0 = v[0];
+#pragma unroll
+                        for (int q = 0; q < 7; ++q) v[q] = v[q + 1];
+                        v[7] = t0;
+                    }
+                }
+                m = __reduce_add_sync(0xFFFFFFFFu, m);
+                if (lane == 0 && m) atomicAdd(&sh.c_cnts[s][c], m);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.counted); // my share of the exact counts is in c_cnts (release)
+        ++n_res;
+        if (warp != 0) continue; // warps 1..7 go on to the next query; warp 0 ranks and writes this one
+        if (lane == 0) mbar_wait(&sh.counted, (n_res - 1) & 1);
+        __syncwarp();
+        const uint32_t sc = sh.c_cnts[s][lane];
+        sh.c_cnts[s][lane] = 0; // for query it+2
+        bool redo = ovf;
+        if (!redo) {
+            // heavy counters: arrivals not explained by the recorded candidates bound every unrecorded doc
+            const uint32_t my_ctr = (my_cand * kMult) >> 18;
+            for (uint32_t j = 0; j < nheavy; ++j) {
+                const uint32_t hc = __shfl_sync(0xFFFFFFFFu, my_heavy, j), tot = __shfl_sync(0xFFFFFFFFu, my_total, j);
+                const uint32_t expl = __reduce_add_sync(0xFFFFFFFFu, (lane < nc && my_ctr == hc) ? sc : 0u);
+                if (tot - expl >= w.min_score) redo = true; // tot >= expl: the candidates' postings all arrived there
+            }
+        }
+        if (redo) {
+            // not decidable here (too many candidates, or a heavy counter hides enough arrivals for another
+            // result): the exact count-table kernels take the query
+            if (lane == 0) {
+                enqueue(a, exact_class_for(w.postings, w.k_eff), w);
+                if (a.stats) atomicAdd(&a.stats->overflow_requeues, 1ull);
+            }
+            __syncwarp();
+            continue;
+        }
+        // rank in registers: lane c holds candidate c.  common.zig:140-171: floor, order (score desc, id asc),
+        // limit, relative cutoff anchored on the best (u32 wrapping product, truncating division; the best is
+        // emitted before the cutoff is raised).
+        const bool keep = lane < nc && sc >= w.min_score;
+        const unsigned long long key = keep ? rank_key(sc, my_cand) : ~0ull;
+        uint32_t rank = 0;
+        for (uint32_t l = 0; l < nc; ++l) rank += (__shfl_sync(0xFFFFFFFFu, key, l) < key) ? 1u : 0u;
+        const uint32_t best = __reduce_max_sync(0xFFFFFFFFu, keep ? sc : 0u);
+        const uint32_t ms = max(w.min_score, (uint32_t)(best * w.min_score_pct) / 100u);
+        const bool emit = keep && rank < w.k_eff && (rank == 0 || sc >= ms);
+        if (emit) {
+            a.out_ids[(size_t)w.q * a.k_stride + rank] = my_cand;
+            a.out_scores[(size_t)w.q * a.k_stride + rank] = sc;
+        }
+        const uint32_t n_out = __popc(__ballot_sync(0xFFFFFFFFu, emit));
+        if (lane == 0) {
+            a.out_counts[w.q] = n_out;
+            if (a.stats) {
+                atomicAdd(&a.stats->results, (unsigned long long)n_out);
+                atomicAdd(&a.stats->sketch_queries, 1ull);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // exact shared-memory path (classes 1..3)
 // ------------------------------------------------------------------------------------------------
 template <int LOG> struct Packed {
@@ -1126,6 +1520,8 @@ cudaError_t configure_kernels() {
     e = cudaFuncSetAttribute(search_smem_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for<15>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_sketch_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(search_sketch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kS2SmemBytes);
     return e;
 }
 
@@ -1150,6 +1546,10 @@ void launch_prepare_long(const BatchArgs &a, cudaStream_t st, int n_sms) {
 }
 
 void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms) {
+    if (a.debug & 1024u) {
+        search_sketch2_kernel<<<2 * n_sms, kS2Threads, kS2SmemBytes, st>>>(a);
+        return;
+    }
     search_sketch_kernel<16, 8><<<n_sms, 1024, kSkSmemBytes, st>>>(a); // 16 counter + 8 resolver + 8 producer warps
 }
 

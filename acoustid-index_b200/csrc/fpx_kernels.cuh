@@ -20,6 +20,7 @@ struct SnapshotDev {
     const uint32_t *docids; // padded rows
     uint32_t pad_id; // a docid no posting uses: "empty" marker of candidate sets (row padding uses other unused
                      // docids, see fpx_snapshot_host.h)
+    uint32_t pad_spread; // 1: pad_id and all row padding are larger than every live docid
 };
 
 struct SearchOpts { // == fpx_search_opts

@@ -64,6 +64,7 @@ struct CompiledCsr {
     std::vector<uint32_t> row_start4; // start of the padded row, in units of 4 docids (16 bytes)
     std::vector<uint32_t> docids;     // padded rows; 4*total4 entries
     uint32_t pad_id = 0;
+    bool pad_spread = false;          // row padding (and pad_id) lies above every live docid
     uint64_t n_postings = 0, n_postings_total = 0, n_unreachable = 0, n_superseded = 0, n_out_of_range = 0;
     uint64_t max_row_len = 0;
     // dense debug copy (fpx_snapshot_csr)
@@ -400,6 +401,7 @@ class SnapshotCompiler {
         }
         const bool spread = max_live < 0xFFFE0000u;
         out->pad_id = spread ? max_live + 1 : choose_pad(*out);
+        out->pad_spread = spread;
         const uint32_t pad_base = max_live + 2;
         parallel_for(nt, threads_, [&](size_t g0, size_t g1, unsigned) {
             for (size_t g = g0; g < g1; ++g) {

@@ -139,6 +139,10 @@ class Context:
             lib().fpx_shutdown(self.h)
             self.h = None
 
+    def debug_set(self, bits):
+        """Profiling only: kernel variant / ablation bits (results are wrong while ablation bits are set)."""
+        check(lib().fpx_debug_set(self.h, int(bits)))
+
     def profile_reset(self):
         check(lib().fpx_profile_reset(self.h))
 

@@ -194,6 +194,9 @@ fpx_status fpx_merge_shard_results(uint32_t n_shards, uint64_t n_queries, uint32
 /* ---- profiling ---- */
 fpx_status fpx_profile_reset(fpx_ctx *ctx);
 fpx_status fpx_profile_read(fpx_ctx *ctx, fpx_profile *out);
+/* Profiling only: kernel variant / ablation bits (same meaning as the FPX_DEBUG_ABLATE environment variable;
+ * results are wrong while ablation bits are set). */
+fpx_status fpx_debug_set(fpx_ctx *ctx, uint32_t bits);
 
 #ifdef __cplusplus
 }
