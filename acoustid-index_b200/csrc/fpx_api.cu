@@ -4,9 +4,12 @@
 // refcounted — mirrors SharedPtr(Segments), src/shared_ptr.zig + src/Index.zig:430-485), upload of the
 // compiled CSR, and the batched search driver (chunked H2D -> kernels -> D2H on rotating streams).
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <new>
 #include <string>
@@ -71,40 +74,100 @@ template <class T> struct DevBuf {
     }
 };
 
+constexpr int kSlots = 3;
+
 struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr; // last use (async device API)
     bool done_pending = false;
-    DevBuf<uint4> rows;
-    DevBuf<WorkItem> items;
-    DevBuf<uint32_t> long_queue;
-    DevBuf<unsigned long long> wide_tables;
-    BatchCounters *counters = nullptr;
+    // Everything one batch (or one chunk of a host batch) writes on the device.  Host batches rotate through
+    // kSlots slots so that chunk c's small trailing kernels can run beside the big ones of the chunks after it.
+    struct Slot {
+        DevBuf<uint4> rows;
+        DevBuf<WorkItem> items;
+        DevBuf<uint32_t> long_queue;
+        BatchCounters *counters = nullptr;
+        DevBuf<uint32_t> d_ids, d_scores, d_counts, d_pack_offsets; // host batches: results before packing
+        cudaEvent_t front_done = nullptr;
+    } slot[kSlots];
+    DevBuf<unsigned long long> wide_tables; // only the (in-order) tail stream touches them
+    cudaStream_t tail_stream = nullptr;
     // staging for host batches
-    DevBuf<uint32_t> d_terms, d_ids, d_scores, d_counts;
+    DevBuf<uint32_t> d_terms;
     DevBuf<uint64_t> d_offsets;
     DevBuf<SearchOpts> d_opts;
     uint32_t *h_error = nullptr; // pinned
+    // packed results of one chunk, written by the GPU into mapped pinned host memory
+    uint32_t *h_counts = nullptr;
+    uint2 *h_pairs = nullptr;
+    size_t h_counts_cap = 0, h_pairs_cap = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_fence = nullptr; // the last host batch's kernels are done with the staging buffers
+    std::vector<cudaEvent_t> h2d_done, chunk_done;
+
+    cudaError_t reserve_events(size_t n) {
+        while (h2d_done.size() < n) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            cudaError_t e = cudaEventCreateWithFlags(&a, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b, cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+            h2d_done.push_back(a);
+            chunk_done.push_back(b);
+        }
+        return cudaSuccess;
+    }
+
+    cudaError_t reserve_host(size_t nq, size_t pairs) {
+        if (nq > h_counts_cap) {
+            if (h_counts) cudaFreeHost(h_counts);
+            h_counts = nullptr;
+            h_counts_cap = 0;
+            cudaError_t e = cudaHostAlloc(&h_counts, (nq + nq / 4 + 64) * sizeof(uint32_t), cudaHostAllocMapped);
+            if (e != cudaSuccess) return e;
+            h_counts_cap = nq + nq / 4 + 64;
+        }
+        if (pairs > h_pairs_cap) {
+            if (h_pairs) cudaFreeHost(h_pairs);
+            h_pairs = nullptr;
+            h_pairs_cap = 0;
+            cudaError_t e = cudaHostAlloc(&h_pairs, (pairs + pairs / 4 + 64) * sizeof(uint2), cudaHostAllocMapped);
+            if (e != cudaSuccess) return e;
+            h_pairs_cap = pairs + pairs / 4 + 64;
+        }
+        return cudaSuccess;
+    }
 
     ~Workspace() {
-        rows.release();
-        items.release();
-        long_queue.release();
+        for (Slot &sl : slot) {
+            sl.rows.release();
+            sl.items.release();
+            sl.long_queue.release();
+            sl.d_ids.release();
+            sl.d_scores.release();
+            sl.d_counts.release();
+            sl.d_pack_offsets.release();
+            if (sl.counters) cudaFree(sl.counters);
+            if (sl.front_done) cudaEventDestroy(sl.front_done);
+        }
         wide_tables.release();
         d_terms.release();
-        d_ids.release();
-        d_scores.release();
-        d_counts.release();
         d_offsets.release();
         d_opts.release();
-        if (counters) cudaFree(counters);
+        if (tail_stream) cudaStreamDestroy(tail_stream);
         if (h_error) cudaFreeHost(h_error);
+        if (h_counts) cudaFreeHost(h_counts);
+        if (h_pairs) cudaFreeHost(h_pairs);
+        for (cudaEvent_t ev : h2d_done) cudaEventDestroy(ev);
+        for (cudaEvent_t ev : chunk_done) cudaEventDestroy(ev);
+        if (copy_fence) cudaEventDestroy(copy_fence);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (done) cudaEventDestroy(done);
         if (stream) cudaStreamDestroy(stream);
     }
 };
 
 constexpr uint32_t kWideCapLog2 = 20;
+constexpr uint32_t kErrSlots = 4096; // per-chunk device error words of a host batch
 
 } // namespace
 
@@ -156,14 +219,20 @@ fpx_status acquire_workspace(fpx_ctx *ctx, Workspace **out) {
     if (!w) return set_error(FPX_OUT_OF_MEMORY, "workspace");
     cudaError_t e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->done, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMalloc(&w->counters, sizeof(BatchCounters));
-    if (e == cudaSuccess) e = cudaMallocHost(&w->h_error, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->copy_fence, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->tail_stream, cudaStreamNonBlocking);
+    for (Workspace::Slot &sl : w->slot) {
+        if (e == cudaSuccess) e = cudaMalloc(&sl.counters, sizeof(BatchCounters));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.front_done, cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaMallocHost(&w->h_error, kErrSlots * sizeof(uint32_t));
     if (e == cudaSuccess) e = w->wide_tables.reserve((size_t)wide_ctas(ctx->n_sms) << kWideCapLog2);
     if (e != cudaSuccess) {
         delete w;
         return cuda_fail(e, "workspace allocation");
     }
-    *w->h_error = 0;
+    std::memset(w->h_error, 0, kErrSlots * sizeof(uint32_t));
     *out = w;
     return FPX_OK;
 }
@@ -194,18 +263,22 @@ struct Timed {
     }
 };
 
-// Enqueue the kernels of one batch on `st`.  All pointers are device pointers.
-fpx_status enqueue_batch(fpx_snapshot *s, Workspace *w, cudaStream_t st, uint64_t n_queries, uint64_t n_terms_total,
-                         const uint32_t *d_terms, const uint64_t *d_offsets, uint64_t term_base,
-                         const SearchOpts *d_opts, uint32_t k_stride, uint32_t *d_ids, uint32_t *d_scores,
-                         uint32_t *d_counts) {
+// Enqueue the kernels of one batch.  All pointers are device pointers.  The "front" (prepare + the persistent
+// sketch kernel) goes on `st`, the "tail" (exact count-table kernels, which also take the sketch kernel's
+// re-queued queries, and the error word) on `ts`; ts == st keeps everything in one stream.
+fpx_status enqueue_batch(fpx_snapshot *s, Workspace *w, Workspace::Slot &sl, cudaStream_t st, cudaStream_t ts,
+                         uint64_t n_queries, uint64_t n_terms_total, const uint32_t *d_terms, const uint64_t *d_offsets,
+                         uint64_t term_base, const SearchOpts *d_opts, uint32_t k_stride, uint32_t *d_ids,
+                         uint32_t *d_scores, uint32_t *d_counts,
+                         cudaEvent_t *trace = nullptr /* 3 events: after prepare, sketch, rest */, uint32_t err_slot = 0,
+                         bool no_long_queries = false) {
     fpx_ctx *ctx = s->ctx;
     if (n_queries == 0) return FPX_OK;
     if (n_queries > 0x7FFFFFFFull || n_terms_total > 0xFFFFFFFFull)
         return set_error(FPX_INVALID_ARGUMENT, "batch too large (split it)");
-    cudaError_t e = w->rows.reserve(n_terms_total + 1);
-    if (e == cudaSuccess) e = w->items.reserve(n_queries * kNumClasses);
-    if (e == cudaSuccess) e = w->long_queue.reserve(n_queries);
+    cudaError_t e = sl.rows.reserve(n_terms_total + 1);
+    if (e == cudaSuccess) e = sl.items.reserve(n_queries * kNumClasses);
+    if (e == cudaSuccess) e = sl.long_queue.reserve(n_queries);
     if (e != cudaSuccess) return cuda_fail(e, "workspace growth");
 
     BatchArgs a{};
@@ -219,36 +292,43 @@ fpx_status enqueue_batch(fpx_snapshot *s, Workspace *w, cudaStream_t st, uint64_
     a.out_ids = d_ids;
     a.out_scores = d_scores;
     a.out_counts = d_counts;
-    a.rows = w->rows.p;
-    a.items = w->items.p;
-    a.long_queue = w->long_queue.p;
-    a.counters = w->counters;
+    a.rows = sl.rows.p;
+    a.items = sl.items.p;
+    a.long_queue = sl.long_queue.p;
+    a.counters = sl.counters;
     a.stats = (ctx->flags & FPX_FLAG_PROFILE) ? ctx->d_stats : nullptr;
     a.wide_tables = w->wide_tables.p;
     a.wide_cap_log2 = kWideCapLog2;
     a.use_sketch = ctx->use_sketch ? 1u : 0u;
     a.debug = ctx->debug;
 
-    FPX_CUDA(cudaMemsetAsync(w->counters, 0, sizeof(BatchCounters), st));
+    FPX_CUDA(cudaMemsetAsync(sl.counters, 0, sizeof(BatchCounters), st));
     {
         Timed t(ctx, st, KK_PREPARE);
         launch_prepare(a, st);
-        launch_prepare_long(a, st, ctx->n_sms);
+        if (!no_long_queries) launch_prepare_long(a, st, ctx->n_sms);
     }
+    if (trace) cudaEventRecord(trace[0], st);
     if (a.use_sketch) {
         Timed t(ctx, st, KK_SKETCH);
         launch_search_sketch(a, st, ctx->n_sms);
     }
-    {
-        Timed t(ctx, st, KK_SEARCH);
-        for (int c = 1; c <= 3; ++c) launch_search_class(a, c, st, ctx->n_sms);
+    if (trace) cudaEventRecord(trace[1], st);
+    if (ts != st) {
+        FPX_CUDA(cudaEventRecord(sl.front_done, st));
+        FPX_CUDA(cudaStreamWaitEvent(ts, sl.front_done, 0));
     }
     {
-        Timed t(ctx, st, KK_WIDE);
-        launch_search_wide(a, st, wide_ctas(ctx->n_sms));
+        Timed t(ctx, ts, KK_SEARCH);
+        for (int c = 1; c <= 3; ++c) launch_search_class(a, c, ts, ctx->n_sms);
     }
+    {
+        Timed t(ctx, ts, KK_WIDE);
+        launch_search_wide(a, ts, wide_ctas(ctx->n_sms));
+    }
+    if (trace) cudaEventRecord(trace[2], ts);
     FPX_CUDA(cudaGetLastError());
-    FPX_CUDA(cudaMemcpyAsync(w->h_error, &w->counters->error, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    FPX_CUDA(cudaMemcpyAsync(w->h_error + err_slot, &sl.counters->error, sizeof(uint32_t), cudaMemcpyDeviceToHost, ts));
     return FPX_OK;
 }
 
@@ -552,8 +632,8 @@ fpx_status fpx_search_batch_device(fpx_snapshot *s, uint64_t n_queries, const ui
         w->done_pending = false;
     }
     // term_offsets index d_terms absolutely; the row workspace is indexed relative to the first offset
-    rc = enqueue_batch(s, w, st, n_queries, last - first, d_terms ? d_terms + first : nullptr, d_term_offsets, first,
-                       reinterpret_cast<const SearchOpts *>(d_opts), k_stride, d_out_ids, d_out_scores, d_out_counts);
+    rc = enqueue_batch(s, w, w->slot[0], st, st, n_queries, last - first, d_terms ? d_terms + first : nullptr, d_term_offsets,
+                       first, reinterpret_cast<const SearchOpts *>(d_opts), k_stride, d_out_ids, d_out_scores, d_out_counts);
     if (rc == FPX_OK) {
         cudaEventRecord(w->done, st);
         w->done_pending = true;
@@ -570,71 +650,261 @@ fpx_status fpx_search_batch(fpx_snapshot *s, uint64_t n_queries, const uint32_t 
     if (!term_offsets || !opts || !out_counts || (k_stride && (!out_ids || !out_scores)))
         return set_error(FPX_INVALID_ARGUMENT, "null buffer");
     if (k_stride > FPX_MAX_RESULTS) return set_error(FPX_UNSUPPORTED, "k_stride exceeds FPX_MAX_RESULTS");
+    if (n_queries > 0x7FFFFFFFull) return set_error(FPX_INVALID_ARGUMENT, "batch too large (split it)");
+    uint64_t longest = 0;
     for (uint64_t q = 0; q < n_queries; ++q) {
         if (term_offsets[q + 1] < term_offsets[q]) return set_error(FPX_INVALID_ARGUMENT, "term_offsets not ascending");
-        if (term_offsets[q + 1] - term_offsets[q] > FPX_MAX_QUERY_TERMS)
-            return set_error(FPX_UNSUPPORTED, "query has more than FPX_MAX_QUERY_TERMS terms");
+        longest = std::max(longest, term_offsets[q + 1] - term_offsets[q]);
     }
-    if (term_offsets[n_queries] > term_offsets[0] && !terms) return set_error(FPX_INVALID_ARGUMENT, "null terms");
+    if (longest > FPX_MAX_QUERY_TERMS) return set_error(FPX_UNSUPPORTED, "query has more than FPX_MAX_QUERY_TERMS terms");
+    const bool no_long_queries = longest <= kWarpQueryTerms; // prepare_long_kernel has nothing to do
+    const uint64_t t_first = term_offsets[0], nt_total = term_offsets[n_queries] - t_first;
+    if (nt_total && !terms) return set_error(FPX_INVALID_ARGUMENT, "null terms");
+    if (nt_total > 0xFFFFFFFFull) return set_error(FPX_INVALID_ARGUMENT, "batch too large (split it)");
     fpx_ctx *ctx = s->ctx;
     FPX_CUDA(cudaSetDevice(ctx->device));
 
-    const uint64_t chunk = ctx->chunk_queries;
-    const uint64_t n_chunks = (n_queries + chunk - 1) / chunk;
-    const int n_ws = (int)std::min<uint64_t>(n_chunks, 3);
-    Workspace *ws[3] = {nullptr, nullptr, nullptr};
-    fpx_status rc = FPX_OK;
-    for (int i = 0; i < n_ws && rc == FPX_OK; ++i) rc = acquire_workspace(ctx, &ws[i]);
+    // Three in-order streams.  The copy stream moves the queries to the device chunk by chunk; the compute stream
+    // runs the big kernels back to back (prepare -> persistent sketch kernel, chunk after chunk); the tail stream
+    // runs each chunk's small trailing kernels (exact count-table kernels, result packing) in the gaps.  Chunks
+    // alternate between two workspace slots.  The packed results ({count per query, (id, score) pairs back to
+    // back}) are written by the GPU straight into mapped pinned host memory, and the calling thread unpacks
+    // chunk c into the caller's arrays while the GPU works on the following chunks.
+    // The first chunks are small so that the kernels start early, the last ones so that little unpacking is left
+    // when the GPU is done.
+    std::vector<uint64_t> bounds; // chunk c = queries [bounds[c], bounds[c+1])
+    uint64_t max_nq = 0, max_nt = 0;
+    {
+        const uint64_t chunk = std::max<uint64_t>(ctx->chunk_queries, (n_queries + kErrSlots - 17) / (kErrSlots - 16));
+        const uint64_t small = std::max<uint64_t>(1024, chunk / 8);
+        uint64_t q = 0, step = small;
+        bounds.push_back(0);
+        while (q < n_queries) {
+            const uint64_t left = n_queries - q;
+            uint64_t take = std::min(step, left);
+            if (left - take < small) take = left;                        // no tiny remainder ...
+            if (take == left && left >= 2 * small) take = left - small;  // ... but a small last chunk
+            const uint64_t q1 = q + take;
+            max_nq = std::max(max_nq, q1 - q);
+            max_nt = std::max(max_nt, term_offsets[q1] - term_offsets[q]);
+            q = q1;
+            bounds.push_back(q);
+            step = std::min(chunk, step * 2);
+        }
+    }
+    const uint64_t n_chunks = bounds.size() - 1;
+    // Results: when the caller's arrays are pinned host memory the k_stride-wide device arrays go there by DMA,
+    // chunk by chunk (the copy engine is otherwise idle and the calling thread has nothing to do).  Otherwise
+    // (pageable memory) the GPU packs them to {count, (id, score) pairs} in the library's own pinned memory and
+    // the calling thread scatters them.
+    bool dma_out = true;
+    {
+        const void *outs[3] = {out_counts, k_stride ? out_ids : out_counts, k_stride ? out_scores : out_counts};
+        for (const void *p : outs) {
+            cudaPointerAttributes at{};
+            if (cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type != cudaMemoryTypeHost) dma_out = false;
+        }
+        cudaGetLastError();
+        if (ctx->debug & 4096u) dma_out = false; // FPX_DEBUG_ABLATE bit 12: force the packed path
+    }
+    Workspace *w = nullptr;
+    fpx_status rc = acquire_workspace(ctx, &w);
+    if (rc != FPX_OK) return rc;
+    cudaStream_t st = w->stream, cs = w->copy_stream, ts = w->tail_stream;
+    cudaError_t e = cudaSuccess;
+    if (w->done_pending) { // the workspace's previous (device-API) batch may still be running on another stream
+        cudaStreamWaitEvent(st, w->done, 0);
+        w->done_pending = false;
+    }
+    // whole-call staging for what the copy stream writes and the GPU -> host packing writes; chunk-sized
+    // buffers for everything that only the (in-order) compute stream touches
+    e = w->d_terms.reserve(nt_total + 1);
+    if (e == cudaSuccess) e = w->d_offsets.reserve(n_queries + n_chunks + 1);
+    if (e == cudaSuccess) e = w->d_opts.reserve(n_queries);
+    for (Workspace::Slot &sl : w->slot) {
+        if (e == cudaSuccess) e = sl.d_ids.reserve(max_nq * (uint64_t)k_stride + 1);
+        if (e == cudaSuccess) e = sl.d_scores.reserve(max_nq * (uint64_t)k_stride + 1);
+        if (e == cudaSuccess) e = sl.d_counts.reserve(max_nq);
+        if (e == cudaSuccess) e = sl.d_pack_offsets.reserve(max_nq + 1);
+        if (e == cudaSuccess) e = sl.rows.reserve(max_nt + 1);
+        if (e == cudaSuccess) e = sl.items.reserve(max_nq * kNumClasses);
+        if (e == cudaSuccess) e = sl.long_queue.reserve(max_nq);
+    }
+    if (e == cudaSuccess && !dma_out) e = w->reserve_host(n_queries, n_queries * (uint64_t)k_stride + 1);
+    if (e == cudaSuccess) e = w->reserve_events(n_chunks);
+    if (e != cudaSuccess) {
+        release_workspace(ctx, w);
+        return cuda_fail(e, "staging buffers");
+    }
+    cudaStreamWaitEvent(cs, w->copy_fence, 0); // the previous call's kernels have read the staging buffers
+
+    // FPX_DEBUG_ABLATE bit 11: print a timeline of this call (GPU events relative to the first, host clock)
+    const bool tracing = (ctx->debug & 2048u) != 0;
+    struct ChunkTrace {
+        cudaEvent_t ev[6]; // start, after H2D, prepare, sketch, exact+wide, pack
+        double host_col0, host_col1;
+    };
+    std::vector<ChunkTrace> tr(tracing ? n_chunks : 0);
+    const auto host0 = std::chrono::steady_clock::now();
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host0).count(); };
+    if (tracing)
+        for (auto &t : tr)
+            for (auto &ev : t.ev) cudaEventCreate(&ev);
+
+    // ---- enqueue everything
+    std::vector<uint64_t> pair_base(n_chunks + 1, 0); // worst-case start of chunk c's pairs in h_pairs
     for (uint64_t c = 0; c < n_chunks && rc == FPX_OK; ++c) {
-        Workspace *w = ws[c % n_ws];
-        cudaStream_t st = w->stream;
-        if (w->done_pending) {
-            cudaStreamWaitEvent(st, w->done, 0);
-            w->done_pending = false;
-        }
-        const uint64_t q0 = c * chunk, q1 = std::min(n_queries, q0 + chunk), nq = q1 - q0;
+        const uint64_t q0 = bounds[c], q1 = bounds[c + 1], nq = q1 - q0;
         const uint64_t t0 = term_offsets[q0], t1 = term_offsets[q1], nt = t1 - t0;
-        cudaError_t e = w->d_terms.reserve(nt + 1);
-        if (e == cudaSuccess) e = w->d_offsets.reserve(nq + 1);
-        if (e == cudaSuccess) e = w->d_opts.reserve(nq);
-        if (e == cudaSuccess) e = w->d_ids.reserve(nq * (uint64_t)k_stride + 1);
-        if (e == cudaSuccess) e = w->d_scores.reserve(nq * (uint64_t)k_stride + 1);
-        if (e == cudaSuccess) e = w->d_counts.reserve(nq);
-        if (e != cudaSuccess) {
-            rc = cuda_fail(e, "staging buffers");
-            break;
-        }
+        pair_base[c + 1] = pair_base[c] + nq * (uint64_t)k_stride;
+        uint64_t *d_off = w->d_offsets.p + q0 + c; // chunk c's nq+1 offsets (absolute term positions)
+        if (tracing) cudaEventRecord(tr[c].ev[0], cs);
         {
-            Timed t(ctx, st, KK_H2D);
-            if (nt) cudaMemcpyAsync(w->d_terms.p, terms + t0, nt * 4, cudaMemcpyHostToDevice, st);
-            cudaMemcpyAsync(w->d_offsets.p, term_offsets + q0, (nq + 1) * 8, cudaMemcpyHostToDevice, st);
-            cudaMemcpyAsync(w->d_opts.p, opts + q0, nq * sizeof(SearchOpts), cudaMemcpyHostToDevice, st);
+            Timed t(ctx, cs, KK_H2D);
+            if (nt) cudaMemcpyAsync(w->d_terms.p + (t0 - t_first), terms + t0, nt * 4, cudaMemcpyHostToDevice, cs);
+            cudaMemcpyAsync(d_off, term_offsets + q0, (nq + 1) * 8, cudaMemcpyHostToDevice, cs);
+            cudaMemcpyAsync(w->d_opts.p + q0, opts + q0, nq * sizeof(SearchOpts), cudaMemcpyHostToDevice, cs);
         }
-        rc = enqueue_batch(s, w, st, nq, nt, w->d_terms.p, w->d_offsets.p, t0, w->d_opts.p, k_stride, w->d_ids.p,
-                           w->d_scores.p, w->d_counts.p);
+        if (tracing) cudaEventRecord(tr[c].ev[1], cs);
+        cudaEventRecord(w->h2d_done[c], cs);
+        cudaStreamWaitEvent(st, w->h2d_done[c], 0);
+        Workspace::Slot &sl = w->slot[c % kSlots];
+        if (c >= (uint64_t)kSlots) cudaStreamWaitEvent(st, w->chunk_done[c - kSlots], 0); // the slot's previous tenant is done
+        rc = enqueue_batch(s, w, sl, st, ts, nq, nt, w->d_terms.p + (t0 - t_first), d_off, t0, w->d_opts.p + q0, k_stride,
+                           sl.d_ids.p, sl.d_scores.p, sl.d_counts.p, tracing ? &tr[c].ev[2] : nullptr, (uint32_t)c, no_long_queries);
         if (rc != FPX_OK) break;
         {
-            Timed t(ctx, st, KK_D2H);
-            if (k_stride) {
-                cudaMemcpyAsync(out_ids + q0 * k_stride, w->d_ids.p, nq * (uint64_t)k_stride * 4, cudaMemcpyDeviceToHost, st);
-                cudaMemcpyAsync(out_scores + q0 * k_stride, w->d_scores.p, nq * (uint64_t)k_stride * 4, cudaMemcpyDeviceToHost, st);
+            Timed t(ctx, ts, KK_D2H);
+            if (dma_out) {
+                if (k_stride) {
+                    cudaMemcpyAsync(out_ids + q0 * k_stride, sl.d_ids.p, nq * (uint64_t)k_stride * 4, cudaMemcpyDeviceToHost, ts);
+                    cudaMemcpyAsync(out_scores + q0 * k_stride, sl.d_scores.p, nq * (uint64_t)k_stride * 4, cudaMemcpyDeviceToHost, ts);
+                }
+                cudaMemcpyAsync(out_counts + q0, sl.d_counts.p, nq * 4, cudaMemcpyDeviceToHost, ts);
+            } else {
+                launch_result_pack(sl.d_ids.p, sl.d_scores.p, sl.d_counts.p, sl.d_pack_offsets.p, (uint32_t)nq, k_stride,
+                                   w->h_counts + q0, w->h_pairs + pair_base[c], ts);
             }
-            cudaMemcpyAsync(out_counts + q0, w->d_counts.p, nq * 4, cudaMemcpyDeviceToHost, st);
         }
+        if (tracing) cudaEventRecord(tr[c].ev[5], ts);
+        cudaEventRecord(w->chunk_done[c], ts);
         if (ctx->flags & FPX_FLAG_PROFILE) {
             std::lock_guard<std::mutex> lk(ctx->mu);
             ctx->prof.h2d_bytes += nt * 4 + (nq + 1) * 8 + nq * sizeof(SearchOpts);
-            ctx->prof.d2h_bytes += nq * (uint64_t)k_stride * 8 + nq * 4;
         }
     }
-    uint32_t dev_err = 0;
-    for (int i = 0; i < n_ws; ++i)
-        if (ws[i]) {
-            cudaError_t e = cudaStreamSynchronize(ws[i]->stream);
-            if (e != cudaSuccess && rc == FPX_OK) rc = cuda_fail(e, "search batch");
-            dev_err |= *ws[i]->h_error;
-            release_workspace(ctx, ws[i]);
+    cudaEventRecord(w->copy_fence, st);
+    const double host_enq = host_ms();
+
+    // ---- collect: wait for chunk c, scatter its packed results into out_ids / out_scores / out_counts.
+    // Scattering is memory-bound host work (two strided cache lines per query); big batches share it among a few
+    // helper threads that live for the duration of the call.
+    struct Job {
+        uint64_t q0, q1;   // queries (absolute)
+        const uint2 *pairs; // first pair of query q0
+    };
+    auto scatter = [&](const Job &j) {
+        const uint2 *hp = j.pairs;
+        for (uint64_t q = j.q0; q < j.q1; ++q) {
+            const uint32_t n = w->h_counts[q];
+            out_counts[q] = n;
+            uint32_t *oi = out_ids + q * k_stride, *os = out_scores + q * k_stride;
+            for (uint32_t i = 0; i < n; ++i) {
+                oi[i] = hp[i].x;
+                os[i] = hp[i].y;
+            }
+            hp += n;
         }
+    };
+    const unsigned n_helpers = (!dma_out && n_queries >= 16384) ? std::min(3u, ctx->host_threads > 1 ? ctx->host_threads - 1 : 0u) : 0u;
+    std::mutex jm;
+    std::condition_variable jcv;
+    std::deque<Job> jobs;
+    bool jobs_closed = false;
+    std::vector<std::thread> helpers;
+    for (unsigned i = 0; i < n_helpers; ++i)
+        helpers.emplace_back([&] {
+            for (;;) {
+                Job j;
+                {
+                    std::unique_lock<std::mutex> lk(jm);
+                    jcv.wait(lk, [&] { return !jobs.empty() || jobs_closed; });
+                    if (jobs.empty()) return;
+                    j = jobs.front();
+                    jobs.pop_front();
+                }
+                scatter(j);
+            }
+        });
+    uint32_t dev_err = 0;
+    uint64_t d2h_bytes = 0;
+    for (uint64_t c = 0; c < n_chunks && rc == FPX_OK; ++c) {
+        if (tracing) tr[c].host_col0 = host_ms();
+        e = cudaEventSynchronize(w->chunk_done[c]);
+        if (e != cudaSuccess) {
+            rc = cuda_fail(e, "search batch");
+            break;
+        }
+        dev_err |= w->h_error[c];
+        const uint64_t q0 = bounds[c], q1 = bounds[c + 1], nq = q1 - q0;
+        if (dma_out) {
+            d2h_bytes += nq * (uint64_t)k_stride * 8 + nq * 4;
+            if (tracing) tr[c].host_col1 = host_ms();
+            continue;
+        }
+        const uint2 *hp = w->h_pairs + pair_base[c];
+        const unsigned parts = (n_helpers && nq >= 4096) ? n_helpers + 1 : 1;
+        Job mine{q0, q1, hp};
+        if (parts > 1) {
+            uint64_t o = 0;
+            std::lock_guard<std::mutex> lk(jm);
+            for (unsigned p = 0; p < parts; ++p) {
+                const uint64_t a0 = q0 + nq * p / parts, a1 = q0 + nq * (p + 1) / parts;
+                const Job j{a0, a1, hp + o};
+                for (uint64_t q = a0; q < a1; ++q) o += w->h_counts[q];
+                if (p + 1 < parts)
+                    jobs.push_back(j);
+                else
+                    mine = j;
+            }
+            d2h_bytes += nq * 4 + o * 8;
+        }
+        if (parts > 1) jcv.notify_all();
+        scatter(mine);
+        if (parts == 1) {
+            uint64_t o = 0;
+            for (uint64_t q = q0; q < q1; ++q) o += w->h_counts[q];
+            d2h_bytes += nq * 4 + o * 8;
+        }
+        if (tracing) tr[c].host_col1 = host_ms();
+    }
+    {
+        std::lock_guard<std::mutex> lk(jm);
+        jobs_closed = true;
+    }
+    jcv.notify_all();
+    for (auto &t : helpers) t.join();
+    if (ctx->flags & FPX_FLAG_PROFILE) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->prof.d2h_bytes += d2h_bytes;
+    }
+    e = cudaStreamSynchronize(ts);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess && rc == FPX_OK) rc = cuda_fail(e, "search batch");
+    if (tracing) {
+        cudaDeviceSynchronize();
+        std::fprintf(stderr, "[fpx trace] %llu chunks enqueued by %.3f ms (host)\n", (unsigned long long)n_chunks, host_enq);
+        for (uint64_t c = 0; c < n_chunks; ++c) {
+            float t[6] = {0, 0, 0, 0, 0, 0};
+            for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&t[i], tr[0].ev[0], tr[c].ev[i]);
+            std::fprintf(stderr, "[fpx trace] chunk %llu q=%llu | gpu: h2d %.3f-%.3f prepare %.3f sketch %.3f rest %.3f pack %.3f | host: collect %.3f-%.3f\n",
+                         (unsigned long long)c, (unsigned long long)(bounds[c + 1] - bounds[c]), t[0], t[1], t[2], t[3], t[4], t[5],
+                         tr[c].host_col0, tr[c].host_col1);
+        }
+        for (auto &t : tr)
+            for (auto &ev : t.ev) cudaEventDestroy(ev);
+    }
+    release_workspace(ctx, w);
     if (rc == FPX_OK && dev_err) rc = set_error((fpx_status)dev_err, "a query in the batch is outside the device path's limits");
     return rc;
 }
@@ -693,6 +963,19 @@ fpx_status fpx_profile_reset(fpx_ctx *ctx) {
     }
     ctx->pending.clear();
     ctx->prof = fpx_profile{};
+    return FPX_OK;
+}
+
+fpx_status fpx_set_chunk_queries(fpx_ctx *ctx, uint32_t chunk_queries) {
+    if (!ctx || chunk_queries == 0) return set_error(FPX_INVALID_ARGUMENT, "null ctx or zero chunk");
+    ctx->chunk_queries = chunk_queries;
+    return FPX_OK;
+}
+
+fpx_status fpx_set_profile(fpx_ctx *ctx, int enabled) {
+    if (!ctx) return set_error(FPX_INVALID_ARGUMENT, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->flags = enabled ? (ctx->flags | FPX_FLAG_PROFILE) : (ctx->flags & ~FPX_FLAG_PROFILE);
     return FPX_OK;
 }
 

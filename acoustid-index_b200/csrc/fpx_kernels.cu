@@ -1285,8 +1285,9 @@ __global__ void __launch_bounds__(kThreads, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1)
     const uint4 *docids4 = reinterpret_cast<const uint4 *>(a.snap.docids);
     uint4 *tab4 = reinterpret_cast<uint4 *>(tab);
 
-    for (uint32_t i = tid; i < P::kSlots / 4; i += kThreads) tab4[i] = make_uint4(0, 0, 0, 0);
     const uint32_t qcount = a.counters->qcount[cls];
+    if (qcount == 0u) return; // nothing queued for this class (the usual case): do not even clear the table
+    for (uint32_t i = tid; i < P::kSlots / 4; i += kThreads) tab4[i] = make_uint4(0, 0, 0, 0);
 
     for (;;) {
         __syncthreads();
@@ -1378,6 +1379,7 @@ __global__ void __launch_bounds__(kThreads) search_wide_kernel(BatchArgs a) {
     unsigned long long *table = a.wide_tables + ((size_t)blockIdx.x << a.wide_cap_log2);
     const uint4 *docids4 = reinterpret_cast<const uint4 *>(a.snap.docids);
     const uint32_t qcount = a.counters->qcount[kWideClass];
+    if (qcount == 0u) return;
 
     for (;;) {
         __syncthreads();
@@ -1506,6 +1508,60 @@ __global__ void __launch_bounds__(kThreads) search_wide_kernel(BatchArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// result packing for host batches: most queries return one or two results, so the k_stride-wide device
+// arrays are packed to {count per query, (id, score) pairs back to back} and written straight into mapped
+// pinned host memory — the device-to-host traffic is the results, not the padding.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) result_offsets_kernel(const uint32_t *counts, uint32_t n, uint32_t k_stride,
+                                                               uint32_t *offsets /* n+1 */) {
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t q = base + tid;
+        const uint32_t c = q < n ? min(counts[q], k_stride) : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += y;
+        }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t ws = warp_sum[lane], wi = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+                if (lane >= (uint32_t)o) wi += y;
+            }
+            warp_sum[lane] = wi - ws; // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const uint32_t c0 = carry;
+        if (q < n) offsets[q] = c0 + warp_sum[warp] + incl - c;
+        __syncthreads();
+        if (tid == 1023) carry = c0 + warp_sum[31] + incl;
+        __syncthreads();
+    }
+    if (tid == 0) offsets[n] = carry;
+}
+
+__global__ void __launch_bounds__(256) result_pack_kernel(const uint32_t *ids, const uint32_t *scores, const uint32_t *counts,
+                                                           const uint32_t *offsets, uint32_t n, uint32_t k_stride,
+                                                           uint32_t *out_counts, uint2 *out_pairs) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const uint32_t c = min(counts[q], k_stride);
+    out_counts[q] = c;
+    const uint32_t o = offsets[q];
+    for (uint32_t j = 0; j < c; ++j)
+        out_pairs[o + j] = make_uint2(ids[(size_t)q * k_stride + j], scores[(size_t)q * k_stride + j]);
+}
+
 } // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -1560,6 +1616,13 @@ void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms
     case 3: search_smem_kernel<15><<<n_sms * 1, kThreads, smem_bytes_for<15>(), st>>>(a); break;
     default: break;
     }
+}
+
+void launch_result_pack(const uint32_t *ids, const uint32_t *scores, const uint32_t *counts, uint32_t *offsets, uint32_t n,
+                        uint32_t k_stride, uint32_t *out_counts, uint2 *out_pairs, cudaStream_t st) {
+    if (n == 0) return;
+    result_offsets_kernel<<<1, 1024, 0, st>>>(counts, n, k_stride, offsets);
+    result_pack_kernel<<<(n + 255) / 256, 256, 0, st>>>(ids, scores, counts, offsets, n, k_stride, out_counts, out_pairs);
 }
 
 int wide_ctas(int n_sms) { return n_sms > 64 ? 64 : n_sms; }

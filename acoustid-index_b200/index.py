@@ -139,6 +139,12 @@ class Context:
             lib().fpx_shutdown(self.h)
             self.h = None
 
+    def set_profile(self, enabled):
+        check(lib().fpx_set_profile(self.h, 1 if enabled else 0))
+
+    def set_chunk_queries(self, n):
+        check(lib().fpx_set_chunk_queries(self.h, int(n)))
+
     def debug_set(self, bits):
         """Profiling only: kernel variant / ablation bits (results are wrong while ablation bits are set)."""
         check(lib().fpx_debug_set(self.h, int(bits)))

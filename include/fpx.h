@@ -191,7 +191,13 @@ fpx_status fpx_merge_shard_results(uint32_t n_shards, uint64_t n_queries, uint32
                                    const fpx_search_opts *opts, uint32_t *out_ids, uint32_t *out_scores,
                                    uint32_t *out_counts);
 
+/* Queries per pipelined H2D / compute / D2H chunk of fpx_search_batch (same as fpx_config.chunk_queries);
+ * takes effect for calls that start afterwards. */
+fpx_status fpx_set_chunk_queries(fpx_ctx *ctx, uint32_t chunk_queries);
+
 /* ---- profiling ---- */
+/* Turn event recording / device counters (FPX_FLAG_PROFILE) on or off for calls that start afterwards. */
+fpx_status fpx_set_profile(fpx_ctx *ctx, int enabled);
 fpx_status fpx_profile_reset(fpx_ctx *ctx);
 fpx_status fpx_profile_read(fpx_ctx *ctx, fpx_profile *out);
 /* Profiling only: kernel variant / ablation bits (same meaning as the FPX_DEBUG_ABLATE environment variable;

@@ -352,3 +352,64 @@ def test_device_resident_api_matches_host_api(ctx, c2):
     mask = np.arange(40)[None, :] < cnt[:, None]
     assert np.array_equal(d_ids.cpu().numpy().view(np.uint32)[mask], want[0][mask])
     assert np.array_equal(d_sc.cpu().numpy().view(np.uint32)[mask], want[1][mask])
+
+
+def test_pinned_dma_and_pageable_packed_paths_agree(ctx, c2):
+    """fpx_search_batch returns results by DMA into pinned caller memory, or — for pageable memory — packed by the
+    GPU into the library's pinned buffers and scattered by the host.  Both must give the same arrays, also when the
+    batch is cut into many chunks (three streams, rotating workspace slots)."""
+    import torch
+    syn, seg, snap, ix = c2
+    reader = pkg.IndexReader(snap)
+    terms, _ = syn.queries(6000, 60, seed=777)
+    nq, T = terms.shape
+    offs = np.arange(nq + 1, dtype=np.uint64) * T
+    opts = np.tile(np.array((40, 3, 10), dtype=np.uint32), (nq, 1))
+    want = _compare_batch(reader, ix, terms.reshape(-1), offs, opts, 40, threads=16)     # pageable numpy: packed path
+    h = [torch.from_numpy(terms.reshape(-1).view(np.int32).copy()).pin_memory(),
+         torch.from_numpy(offs.view(np.int64).copy()).pin_memory(),
+         torch.from_numpy(opts.view(np.int32).copy()).pin_memory()]
+    for chunk in (1024, 8192):       # schedules of 1024.. and 1024-sized chunks: > 3 chunks in flight
+        ctx.set_chunk_queries(chunk)
+        o = [torch.full((nq, 40), -1, dtype=torch.int32).pin_memory(), torch.full((nq, 40), -1, dtype=torch.int32).pin_memory(),
+             torch.full((nq,), -1, dtype=torch.int32).pin_memory()]
+        reader.search_batch_ptr(nq, h[0].data_ptr(), h[1].data_ptr(), h[2].data_ptr(), 40, o[0].data_ptr(),
+                                o[1].data_ptr(), o[2].data_ptr())                        # pinned: DMA path
+        cnt = o[2].numpy().view(np.uint32)
+        assert np.array_equal(cnt, want[2])
+        mask = np.arange(40)[None, :] < cnt[:, None]
+        assert np.array_equal(o[0].numpy().view(np.uint32)[mask], want[0][mask])
+        assert np.array_equal(o[1].numpy().view(np.uint32)[mask], want[1][mask])
+        got = reader.search_batch(terms.reshape(-1), offs, opts, 40)                    # packed path, same chunking
+        assert np.array_equal(got[2], want[2]) and np.array_equal(got[0][mask], want[0][mask]) \
+            and np.array_equal(got[1][mask], want[1][mask])
+    ctx.set_chunk_queries(32768)
+
+
+def test_second_generation_sketch_kernel(ctx, c2):
+    """search_sketch2_kernel (variant bit 1024: register-resident queries, windowed sketch with heavy-counter
+    check) against the oracle: C2 documents as queries, several option sets, and a multi-segment snapshot with
+    duplicate hashes and supersession."""
+    syn, seg, snap, ix = c2
+    reader = pkg.IndexReader(snap)
+    terms, _ = syn.queries(3000, 60, seed=4321)
+    nq, T = terms.shape
+    offs = np.arange(nq + 1, dtype=np.uint64) * T
+    ctx.debug_set(1024)
+    try:
+        for opt in ((40, 5, 10), (40, 2, 0), (100, 3, 50), (512, 7, 10), (3, 4, 100)):
+            opts = np.tile(np.array(opt, dtype=np.uint32), (nq, 1))
+            ctx.profile_reset()
+            _compare_batch(reader, ix, terms.reshape(-1), offs, opts, min(opt[0], 64), threads=16)
+            if opt[1] >= 4:
+                assert ctx.profile()["sketch_queries"] > 0.9 * nq
+        rng = np.random.default_rng(7)
+        ix2, _ = _random_index(rng)
+        snap2 = _snapshot_of(ctx, ix2)
+        queries = [rng.integers(0, 4000, size=int(rng.integers(0, 120))).tolist() for _ in range(500)]
+        t2, o2 = flat_queries(queries)
+        for opt in ((40, 2, 10), (40, 3, 0), (64, 5, 10)):
+            _compare_batch(pkg.IndexReader(snap2), ix2, t2, o2, np.tile(np.array(opt, dtype=np.uint32), (len(queries), 1)), 64)
+        snap2.release()
+    finally:
+        ctx.debug_set(0)
