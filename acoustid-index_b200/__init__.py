@@ -9,4 +9,4 @@ from . import _ffi, index, synth  # noqa: F401  (multi_gpu is imported on demand
 from ._ffi import FpxError, build as build_library, lib  # noqa: F401
 from .index import (Context, FileSegment, IndexReader, MemorySegment, SearchOptions, SearchRequest,  # noqa: F401
                     SearchResult, Snapshot, SnapshotBuilder, merge_shard_results, multi_index_search,
-                    swap_snapshot)
+                    pack_results_device, swap_snapshot, unpack_results)

@@ -920,6 +920,21 @@ fpx_status fpx_search(fpx_snapshot *s, const uint32_t *terms, uint64_t n_terms, 
     return fpx_search_batch(s, 1, terms, offs, opts, cap, out_ids, out_scores, out_count);
 }
 
+fpx_status fpx_pack_results_device(uint64_t n_queries, uint32_t k_stride, const uint32_t *d_ids, const uint32_t *d_scores,
+                                   const uint32_t *d_counts, uint32_t *d_packed, uint32_t capacity_pairs, void *cuda_stream) {
+    if (n_queries == 0) return FPX_OK;
+    if (n_queries > 0x7FFFFFFFull) return set_error(FPX_INVALID_ARGUMENT, "batch too large (split it)");
+    if (!d_counts || !d_packed || (k_stride && (!d_ids || !d_scores))) return set_error(FPX_INVALID_ARGUMENT, "null buffer");
+    // layout of d_packed (u32): [0, n) counts | [n, 2n] row offsets into the pairs, [2n] = pairs needed |
+    //                           then capacity_pairs x (id, score)
+    const uint32_t n = (uint32_t)n_queries;
+    launch_result_pack(d_ids, d_scores, d_counts, d_packed + n, n, k_stride, d_packed,
+                       reinterpret_cast<uint2 *>(d_packed + 2 * (size_t)n + 2), static_cast<cudaStream_t>(cuda_stream),
+                       capacity_pairs);
+    FPX_CUDA(cudaGetLastError());
+    return FPX_OK;
+}
+
 fpx_status fpx_merge_shard_results(uint32_t n_shards, uint64_t n_queries, uint32_t k_stride, const uint32_t *ids,
                                    const uint32_t *scores, const uint32_t *counts, const fpx_search_opts *opts,
                                    uint32_t *out_ids, uint32_t *out_scores, uint32_t *out_counts) {

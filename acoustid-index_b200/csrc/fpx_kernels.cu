@@ -137,7 +137,8 @@ __global__ void build_table_kernel(TermEntry *table, uint32_t mask, uint32_t shi
 // ------------------------------------------------------------------------------------------------
 // prepare: Index.zig:171-172 (sort + dedupSorted => the query is a SET) + term -> row lookup
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) prepare_kernel(BatchArgs a) {
+// 48 registers: five CTAs (40 warps) per SM keep more directory probes in flight than the unconstrained 58
+__global__ void __launch_bounds__(kThreads, 5) prepare_kernel(BatchArgs a) {
     __shared__ uint32_t s_set[kWarps][256]; // per-warp hash set for de-duplication (<= 128 terms, load <= 0.5)
     const uint32_t lane = lane_id();
     uint32_t *set = s_set[threadIdx.x >> 5];
@@ -1552,13 +1553,13 @@ __global__ void __launch_bounds__(1024) result_offsets_kernel(const uint32_t *co
 
 __global__ void __launch_bounds__(256) result_pack_kernel(const uint32_t *ids, const uint32_t *scores, const uint32_t *counts,
                                                            const uint32_t *offsets, uint32_t n, uint32_t k_stride,
-                                                           uint32_t *out_counts, uint2 *out_pairs) {
+                                                           uint32_t *out_counts, uint2 *out_pairs, uint32_t capacity) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     const uint32_t c = min(counts[q], k_stride);
     out_counts[q] = c;
     const uint32_t o = offsets[q];
-    for (uint32_t j = 0; j < c; ++j)
+    for (uint32_t j = 0; j < c && o + j < capacity; ++j)
         out_pairs[o + j] = make_uint2(ids[(size_t)q * k_stride + j], scores[(size_t)q * k_stride + j]);
 }
 
@@ -1593,7 +1594,7 @@ void launch_build_table(TermEntry *table, uint32_t log2cap, const uint32_t *term
 void launch_prepare(const BatchArgs &a, cudaStream_t st) {
     if (a.n_queries == 0) return;
     unsigned long long blocks = ((unsigned long long)a.n_queries + kWarps - 1) / kWarps;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > 148 * 10) blocks = 148 * 10;
     prepare_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(a);
 }
 
@@ -1619,10 +1620,11 @@ void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms
 }
 
 void launch_result_pack(const uint32_t *ids, const uint32_t *scores, const uint32_t *counts, uint32_t *offsets, uint32_t n,
-                        uint32_t k_stride, uint32_t *out_counts, uint2 *out_pairs, cudaStream_t st) {
+                        uint32_t k_stride, uint32_t *out_counts, uint2 *out_pairs, cudaStream_t st, uint32_t capacity) {
     if (n == 0) return;
     result_offsets_kernel<<<1, 1024, 0, st>>>(counts, n, k_stride, offsets);
-    result_pack_kernel<<<(n + 255) / 256, 256, 0, st>>>(ids, scores, counts, offsets, n, k_stride, out_counts, out_pairs);
+    result_pack_kernel<<<(n + 255) / 256, 256, 0, st>>>(ids, scores, counts, offsets, n, k_stride, out_counts, out_pairs,
+                                                        capacity);
 }
 
 int wide_ctas(int n_sms) { return n_sms > 64 ? 64 : n_sms; }

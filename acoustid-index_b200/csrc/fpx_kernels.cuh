@@ -100,9 +100,11 @@ void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms);
 void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms);
 void launch_search_wide(const BatchArgs &a, cudaStream_t st, int n_ctas);
 // pack the k_stride-wide result arrays of n queries: out_counts[q] and the (id, score) pairs back to back
-// (out_* may be mapped pinned host memory); offsets = n+1 words of device scratch
+// (out_* may be mapped pinned host memory); offsets = n+1 words of device scratch, offsets[n] = number of pairs;
+// pairs beyond `capacity` are dropped
 void launch_result_pack(const uint32_t *ids, const uint32_t *scores, const uint32_t *counts, uint32_t *offsets, uint32_t n,
-                        uint32_t k_stride, uint32_t *out_counts, uint2 *out_pairs, cudaStream_t st);
+                        uint32_t k_stride, uint32_t *out_counts, uint2 *out_pairs, cudaStream_t st,
+                        uint32_t capacity = 0xFFFFFFFFu);
 cudaError_t configure_kernels();
 int wide_ctas(int n_sms);
 

@@ -308,6 +308,28 @@ def multi_index_search(reader: IndexReader, request: SearchRequest, clamp_http=T
     return reader.search(request.query, SearchOptions(limit, min_score, request.score_pct))
 
 
+def pack_results_device(nq, k_stride, d_ids, d_scores, d_counts, d_packed, capacity_pairs, stream=0):
+    """Device pointers (ints).  Packs a batch's result arrays for an exchange between GPUs (see fpx.h)."""
+    check(lib().fpx_pack_results_device(nq, k_stride, d_ids, d_scores, d_counts, d_packed, capacity_pairs, stream))
+
+
+def unpack_results(packed, nq, k_stride, capacity_pairs):
+    """numpy view of one rank's packed results -> (ids, scores, counts) in the k_stride-wide layout."""
+    packed = np.asarray(packed).view(np.uint32)
+    counts = packed[:nq].copy()
+    offs = packed[nq:2 * nq + 1].astype(np.int64)
+    if int(offs[nq]) > capacity_pairs:
+        raise FpxError(_ffi.FPX_UNSUPPORTED, "packed results exceed the exchange capacity")
+    pairs = packed[2 * nq + 2:2 * nq + 2 + 2 * int(offs[nq])].reshape(-1, 2)
+    ids = np.zeros((nq, k_stride), np.uint32)
+    sc = np.zeros((nq, k_stride), np.uint32)
+    rows = np.repeat(np.arange(nq), counts)
+    cols = np.arange(len(rows)) - np.repeat(offs[:nq], counts)
+    ids[rows, cols] = pairs[:, 0]
+    sc[rows, cols] = pairs[:, 1]
+    return ids, sc, counts
+
+
 def merge_shard_results(ids, scores, counts, opts, k_stride):
     """ids/scores: [n_shards, nq, k_stride]; counts: [n_shards, nq]; opts: [nq, 3] -> merged (ids, scores, counts)."""
     ids, scores, counts, opts = _u32(ids), _u32(scores), _u32(counts), _u32(opts)

@@ -241,18 +241,19 @@ def main():
     d_sc = torch.zeros((nq, K_STRIDE), dtype=torch.int32, device=dev)
     d_cnt = torch.zeros(nq, dtype=torch.int32, device=dev)
     gather_buf = None
+    PACK_CAP = 4 * nq     # exchange capacity in (id, score) pairs; checked after the timed region
     if world > 1:
-        packed = torch.empty((nq, 2 * K_STRIDE + 1), dtype=torch.int32, device=dev)
-        gather_buf = torch.empty((world * nq, 2 * K_STRIDE + 1), dtype=torch.int32, device=dev)
+        packed = torch.zeros(2 * nq + 2 + 2 * PACK_CAP, dtype=torch.int32, device=dev)
+        gather_buf = torch.empty((world, packed.numel()), dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream()
 
     def step():
         reader.search_batch_device(nq, d_terms.data_ptr(), d_offs.data_ptr(), d_opts.data_ptr(), K_STRIDE,
                                    d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(), stream.cuda_stream)
-        if world > 1:  # the one exchange step: collect every rank's per-query result lists (NCCL over NVLink)
-            packed[:, :K_STRIDE] = d_ids
-            packed[:, K_STRIDE:2 * K_STRIDE] = d_sc
-            packed[:, 2 * K_STRIDE] = d_cnt
+        if world > 1:  # the one exchange step: collect every rank's per-query result lists (NCCL over NVLink),
+            # packed to {counts, (id, score) pairs} by fpx_pack_results_device
+            pkg.pack_results_device(nq, K_STRIDE, d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(),
+                                    packed.data_ptr(), PACK_CAP, stream.cuda_stream)
             dist.all_gather_into_tensor(gather_buf, packed)
 
     def barrier():
@@ -282,6 +283,12 @@ def main():
         ms_total = float(tt.item())
     ms_per_step = ms_total / args.steps
     value = world * nq / (ms_per_step * 1e-3)
+    if world > 1:  # what was gathered must be this rank's answers (checked on every rank for its own slice)
+        g_ids, g_sc, g_cnt = pkg.unpack_results(gather_buf[rank].cpu().numpy(), nq, K_STRIDE, PACK_CAP)
+        own_cnt = d_cnt.cpu().numpy().view(np.uint32)
+        _mm = np.arange(K_STRIDE)[None, :] < own_cnt[:, None]
+        assert np.array_equal(g_cnt, own_cnt) and np.array_equal(g_ids[_mm], d_ids.cpu().numpy().view(np.uint32)[_mm]) \
+            and np.array_equal(g_sc[_mm], d_sc.cpu().numpy().view(np.uint32)[_mm]), "gathered results differ"
 
     # ---- e2e through the host-buffer C-ABI call, pinned host memory, copies inside the timed region
     h_terms = torch.from_numpy(terms.reshape(-1).view(np.int32).copy()).pin_memory()

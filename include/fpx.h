@@ -182,6 +182,16 @@ fpx_status fpx_search_batch_device(fpx_snapshot *s, uint64_t n_queries, const ui
                                    uint32_t k_stride, uint32_t *d_out_ids, uint32_t *d_out_scores,
                                    uint32_t *d_out_counts, void *cuda_stream);
 
+/* Pack the k_stride-wide device result arrays of a batch for an exchange between GPUs (most queries return one
+ * or two results): d_packed, 2*n_queries + 2 + 2*capacity_pairs u32 words, receives
+ *   [0, n) counts | [n, 2n] row offsets into the pairs, word 2n = number of pairs needed | word 2n+1 unused |
+ *   capacity_pairs x (id, score).
+ * Pairs beyond capacity_pairs are dropped: the receiver compares word 2n with its capacity.  Asynchronous on
+ * `cuda_stream`. */
+fpx_status fpx_pack_results_device(uint64_t n_queries, uint32_t k_stride, const uint32_t *d_ids,
+                                   const uint32_t *d_scores, const uint32_t *d_counts, uint32_t *d_packed,
+                                   uint32_t capacity_pairs, void *cuda_stream);
+
 /* Merge per-shard top-k lists (docid-range sharded corpus): for each query take the global best
  * min(max_results, k_stride) under (score desc, id asc), then apply the relative cutoff anchored on the
  * global best (common.zig:153-166).  Shards must have been searched with min_score_pct = 0.

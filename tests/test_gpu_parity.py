@@ -413,3 +413,32 @@ def test_second_generation_sketch_kernel(ctx, c2):
         snap2.release()
     finally:
         ctx.debug_set(0)
+
+
+def test_pack_results_for_exchange(ctx, c2):
+    """fpx_pack_results_device + unpack_results round-trip the k_stride-wide result arrays (multi-GPU exchange)."""
+    import torch
+    syn, seg, snap, ix = c2
+    reader = pkg.IndexReader(snap)
+    terms, _ = syn.queries(5000, 100, seed=99)
+    nq, T = terms.shape
+    offs = np.arange(nq + 1, dtype=np.uint64) * T
+    opts = np.tile(np.array((40, 1, 0), dtype=np.uint32), (nq, 1))     # floor 1: many results per query
+    opts[::2] = (40, 5, 10)
+    want = reader.search_batch(terms.reshape(-1), offs, opts, 40)
+    dev = torch.device("cuda:0")
+    d = [torch.from_numpy(np.ascontiguousarray(x).view(np.int32)).to(dev) for x in want]
+    cap = int(want[2].sum()) + 7
+    packed = torch.zeros(2 * nq + 2 + 2 * cap, dtype=torch.int32, device=dev)
+    pkg.pack_results_device(nq, 40, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), packed.data_ptr(), cap,
+                            torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ids, sc, cnt = pkg.unpack_results(packed.cpu().numpy(), nq, 40, cap)
+    mask = np.arange(40)[None, :] < want[2][:, None]
+    assert np.array_equal(cnt, want[2]) and np.array_equal(ids[mask], want[0][mask]) and np.array_equal(sc[mask], want[1][mask])
+    small = torch.zeros(2 * nq + 2 + 2 * 10, dtype=torch.int32, device=dev)           # too small: must say so
+    pkg.pack_results_device(nq, 40, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), small.data_ptr(), 10,
+                            torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    with pytest.raises(pkg.FpxError):
+        pkg.unpack_results(small.cpu().numpy(), nq, 40, 10)
