@@ -9,4 +9,5 @@ from . import _ffi, index, synth  # noqa: F401  (multi_gpu is imported on demand
 from ._ffi import FpxError, build as build_library, lib  # noqa: F401
 from .index import (Context, FileSegment, IndexReader, MemorySegment, SearchOptions, SearchRequest,  # noqa: F401
                     SearchResult, Snapshot, SnapshotBuilder, merge_shard_results, multi_index_search,
-                    pack_results_device, swap_snapshot, unpack_results)
+                    open_index_dir, pack_results_device, parse_manifest, segment_file_bytes, segment_file_name,
+                    SegmentFile, swap_snapshot, unpack_results)

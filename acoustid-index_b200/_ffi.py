@@ -57,6 +57,11 @@ class MemorySegmentDesc(C.Structure):
                 ("n_docs", C.c_uint64)]
 
 
+class SegmentInfo(C.Structure):  # fpx_segment_info
+    _fields_ = [("commit_id", C.c_uint64), ("merges", C.c_uint64), ("version", C.c_uint64),
+                ("has_version", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class SnapshotInfo(C.Structure):
     _fields_ = [("n_segments", C.c_uint64), ("n_terms", C.c_uint64), ("n_postings", C.c_uint64),
                 ("n_postings_total", C.c_uint64), ("n_dropped_unreachable", C.c_uint64),
@@ -92,6 +97,9 @@ EXPORTS = [
     "fpx_segment_write", "fpx_segment_buf_blocks", "fpx_segment_buf_block_index",
     "fpx_segment_buf_num_blocks", "fpx_segment_buf_num_items", "fpx_segment_buf_block_size",
     "fpx_segment_buf_free", "fpx_block_decode",
+    "fpx_segment_file_parse", "fpx_segment_file_read", "fpx_segment_file_view", "fpx_segment_file_num_items",
+    "fpx_segment_file_metadata_count", "fpx_segment_file_metadata_get", "fpx_segment_file_close",
+    "fpx_segment_file_serialize", "fpx_bytes_free", "fpx_segment_file_name", "fpx_manifest_parse", "fpx_crc64_xz",
 ]
 
 _LIB = None
@@ -146,6 +154,24 @@ def lib():
     L.fpx_set_chunk_queries.argtypes = [vp, C.c_uint32]
     L.fpx_set_profile.argtypes = [vp, C.c_int]
     L.fpx_pack_results_device.argtypes = [C.c_uint64, C.c_uint32, vp, vp, vp, vp, C.c_uint32, vp]
+    L.fpx_segment_file_parse.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
+    L.fpx_segment_file_read.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.fpx_segment_file_view.argtypes = [vp, C.POINTER(FileSegmentDesc), C.POINTER(SegmentInfo)]
+    L.fpx_segment_file_num_items.argtypes = [vp]
+    L.fpx_segment_file_num_items.restype = C.c_uint64
+    L.fpx_segment_file_metadata_count.argtypes = [vp]
+    L.fpx_segment_file_metadata_count.restype = C.c_uint64
+    L.fpx_segment_file_metadata_get.argtypes = [vp, C.c_uint64, C.POINTER(vp), u64p, C.POINTER(vp), u64p]
+    L.fpx_segment_file_close.argtypes = [vp]
+    L.fpx_segment_file_close.restype = None
+    L.fpx_segment_file_serialize.argtypes = [C.POINTER(FileSegmentDesc), C.POINTER(SegmentInfo), C.POINTER(vp), u64p]
+    L.fpx_bytes_free.argtypes = [vp]
+    L.fpx_bytes_free.restype = None
+    L.fpx_segment_file_name.argtypes = [C.c_uint64, C.c_uint64, C.c_char_p, C.c_uint64]
+    L.fpx_segment_file_name.restype = C.c_int32
+    L.fpx_manifest_parse.argtypes = [vp, C.c_uint64, C.POINTER(SegmentInfo), C.c_uint64, u64p]
+    L.fpx_crc64_xz.argtypes = [vp, C.c_uint64]
+    L.fpx_crc64_xz.restype = C.c_uint64
     L.fpx_segment_write.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
     L.fpx_segment_buf_blocks.argtypes = [vp]
     L.fpx_segment_buf_blocks.restype = vp

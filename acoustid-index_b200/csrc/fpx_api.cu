@@ -171,6 +171,10 @@ constexpr uint32_t kErrSlots = 4096; // per-chunk device error words of a host b
 
 } // namespace
 
+namespace fpx {
+void set_last_error(const std::string &msg) { g_error = msg; } // for the other translation units
+} // namespace fpx
+
 struct fpx_ctx {
     int device = 0;
     int n_sms = 148;

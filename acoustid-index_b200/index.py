@@ -94,6 +94,88 @@ class FileSegment:
         return d
 
 
+class SegmentFile:
+    """A segment file (.data) loaded into memory: src/filefmt.zig:209-285 readSegment.  `.segment` is the FileSegment
+    view (valid while this object lives), `.info` = (commit_id, merges, version or None)."""
+
+    def __init__(self, h):
+        self.h = h
+        d, si = _ffi.FileSegmentDesc(), _ffi.SegmentInfo()
+        check(lib().fpx_segment_file_view(h, C.byref(d), C.byref(si)))
+        self.info = (si.commit_id, si.merges, si.version if si.has_version else None)
+        self.num_items = lib().fpx_segment_file_num_items(h)
+        nb, bs, nd = int(d.num_blocks), int(d.block_size), int(d.n_docs)
+        blocks = np.ctypeslib.as_array(C.cast(d.blocks, _ffi.u8p), shape=((nb + 1) * bs,))
+        index = np.ctypeslib.as_array(C.cast(d.block_index, _ffi.u32p), shape=(nb,)) if nb else np.zeros(0, np.uint32)
+        ids = np.ctypeslib.as_array(C.cast(d.doc_ids, _ffi.u32p), shape=(nd,)) if nd else np.zeros(0, np.uint32)
+        alive = np.ctypeslib.as_array(C.cast(d.doc_alive, _ffi.u8p), shape=(nd,)) if nd else np.zeros(0, np.uint8)
+        self.segment = FileSegment(d.commit_id, d.merges, d.min_doc_id, bs, blocks, nb, index, ids.copy(), alive.copy(),
+                                   _owner=self)
+        self.metadata = {}
+        for i in range(lib().fpx_segment_file_metadata_count(h)):
+            k, v, kl, vl = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
+            check(lib().fpx_segment_file_metadata_get(h, i, C.byref(k), C.byref(kl), C.byref(v), C.byref(vl)))
+            self.metadata[C.string_at(k, kl.value)] = C.string_at(v, vl.value)
+
+    @staticmethod
+    def parse(data: bytes):
+        h = C.c_void_p()
+        buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+        check(lib().fpx_segment_file_parse(C.cast(buf, C.c_void_p), len(data), C.byref(h)))
+        return SegmentFile(h)
+
+    @staticmethod
+    def read(path):
+        h = C.c_void_p()
+        check(lib().fpx_segment_file_read(str(path).encode(), C.byref(h)))
+        return SegmentFile(h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().fpx_segment_file_close(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def segment_file_bytes(seg: "FileSegment", version=None) -> bytes:
+    """The bytes filefmt.writeSegment (filefmt.zig:143-178) puts on disk for `seg` (empty metadata)."""
+    d = seg._desc()
+    si = _ffi.SegmentInfo(seg.commit_id, seg.merges, version or 0, 1 if version is not None else 0, 0)
+    out, n = C.c_void_p(), C.c_uint64()
+    check(lib().fpx_segment_file_serialize(C.byref(d), C.byref(si), C.byref(out), C.byref(n)))
+    try:
+        return C.string_at(out, n.value)
+    finally:
+        lib().fpx_bytes_free(out)
+
+
+def segment_file_name(commit_id, merges=0) -> str:
+    buf = C.create_string_buffer(64)
+    n = lib().fpx_segment_file_name(commit_id, merges, buf, 64)
+    assert n > 0
+    return buf.value.decode()
+
+
+def parse_manifest(data: bytes):
+    """manifest.zig:17-39 -> list of (commit_id, merges, version or None)."""
+    arr = (_ffi.SegmentInfo * 4096)()
+    n = C.c_uint64()
+    buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+    check(lib().fpx_manifest_parse(C.cast(buf, C.c_void_p), len(data), arr, 4096, C.byref(n)))
+    return [(arr[i].commit_id, arr[i].merges, arr[i].version if arr[i].has_version else None) for i in range(n.value)]
+
+
+def open_index_dir(path):
+    """Load every file segment the manifest in `path` lists (Index.open, Index.zig:271-315): SegmentFile objects,
+    oldest first."""
+    import os
+    mp = os.path.join(path, "manifest")
+    infos = parse_manifest(open(mp, "rb").read()) if os.path.exists(mp) else []
+    return [SegmentFile.read(os.path.join(path, segment_file_name(c, m))) for c, m, _ in infos]
+
+
 class _SegmentBuf:
     def __init__(self, h):
         self.h = h
