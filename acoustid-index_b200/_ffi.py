@@ -57,6 +57,15 @@ class MemorySegmentDesc(C.Structure):
                 ("n_docs", C.c_uint64)]
 
 
+class BatcherConfig(C.Structure):
+    _fields_ = [("max_batch", C.c_uint32), ("max_wait_us", C.c_uint32)]
+
+
+class BatcherStats(C.Structure):
+    _fields_ = [("batches", C.c_uint64), ("queries", C.c_uint64), ("max_batch_seen", C.c_uint64),
+                ("timeouts", C.c_uint64)]
+
+
 class SegmentInfo(C.Structure):  # fpx_segment_info
     _fields_ = [("commit_id", C.c_uint64), ("merges", C.c_uint64), ("version", C.c_uint64),
                 ("has_version", C.c_uint32), ("reserved", C.c_uint32)]
@@ -97,6 +106,8 @@ EXPORTS = [
     "fpx_segment_write", "fpx_segment_buf_blocks", "fpx_segment_buf_block_index",
     "fpx_segment_buf_num_blocks", "fpx_segment_buf_num_items", "fpx_segment_buf_block_size",
     "fpx_segment_buf_free", "fpx_block_decode",
+    "fpx_batcher_create", "fpx_batcher_set_snapshot", "fpx_batcher_search", "fpx_batcher_get_stats",
+    "fpx_batcher_destroy",
     "fpx_segment_file_parse", "fpx_segment_file_read", "fpx_segment_file_view", "fpx_segment_file_num_items",
     "fpx_segment_file_metadata_count", "fpx_segment_file_metadata_get", "fpx_segment_file_close",
     "fpx_segment_file_serialize", "fpx_bytes_free", "fpx_segment_file_name", "fpx_manifest_parse", "fpx_crc64_xz",
@@ -154,6 +165,12 @@ def lib():
     L.fpx_set_chunk_queries.argtypes = [vp, C.c_uint32]
     L.fpx_set_profile.argtypes = [vp, C.c_int]
     L.fpx_pack_results_device.argtypes = [C.c_uint64, C.c_uint32, vp, vp, vp, vp, C.c_uint32, vp]
+    L.fpx_batcher_create.argtypes = [vp, C.POINTER(BatcherConfig), C.POINTER(vp)]
+    L.fpx_batcher_set_snapshot.argtypes = [vp, vp]
+    L.fpx_batcher_search.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32, vp, vp, C.c_uint32, u32p]
+    L.fpx_batcher_get_stats.argtypes = [vp, C.POINTER(BatcherStats)]
+    L.fpx_batcher_destroy.argtypes = [vp]
+    L.fpx_batcher_destroy.restype = None
     L.fpx_segment_file_parse.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
     L.fpx_segment_file_read.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.fpx_segment_file_view.argtypes = [vp, C.POINTER(FileSegmentDesc), C.POINTER(SegmentInfo)]

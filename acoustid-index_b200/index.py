@@ -379,6 +379,45 @@ class IndexReader:
                                             d_counts, stream))
 
 
+class Batcher:
+    """Request micro-batcher: what a host would put behind MultiIndex.search (MultiIndex.zig:287-330).  search() is
+    thread-safe and blocking; concurrent callers are answered by shared GPU batches."""
+
+    def __init__(self, ctx: Context, max_batch=0, max_wait_us=100):
+        cfg = _ffi.BatcherConfig(max_batch, max_wait_us)
+        self.h = C.c_void_p()
+        check(lib().fpx_batcher_create(ctx.h, C.byref(cfg), C.byref(self.h)))
+
+    def set_snapshot(self, snapshot: Optional[Snapshot]):
+        """Index.swapSnapshot hook (Index.zig:469-485)."""
+        check(lib().fpx_batcher_set_snapshot(self.h, snapshot.h if snapshot is not None else None))
+
+    def search(self, request: SearchRequest, clamp_http=True) -> List[SearchResult]:
+        limit = request.limit
+        if clamp_http:
+            limit = max(min(limit, max_search_limit), min_search_limit)   # server.zig:192
+        min_score = request.min_score
+        if min_score is None:
+            min_score = lib().fpx_default_min_score(len(request.query))   # MultiIndex.zig:304, RAW length
+        q = _u32([int(x) & 0xFFFFFFFF for x in request.query])
+        opts = np.array([limit, min_score, request.score_pct], dtype=np.uint32)
+        cap = max(1, min(int(limit), _ffi.FPX_MAX_RESULTS))
+        ids, sc, n = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32), C.c_uint32(0)
+        check(lib().fpx_batcher_search(self.h, q.ctypes.data if len(q) else None, len(q), opts.ctypes.data,
+                                       int(request.timeout), ids.ctypes.data, sc.ctypes.data, cap, C.byref(n)))
+        return [SearchResult(int(ids[i]), int(sc[i])) for i in range(n.value)]
+
+    def stats(self):
+        s = _ffi.BatcherStats()
+        check(lib().fpx_batcher_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in _ffi.BatcherStats._fields_}
+
+    def close(self):
+        if self.h:
+            lib().fpx_batcher_destroy(self.h)
+            self.h = None
+
+
 def multi_index_search(reader: IndexReader, request: SearchRequest, clamp_http=True) -> List[SearchResult]:
     """MultiIndex.search option mapping (MultiIndex.zig:302-306); clamp_http applies server.zig:192-193."""
     limit = request.limit

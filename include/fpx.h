@@ -201,6 +201,30 @@ fpx_status fpx_merge_shard_results(uint32_t n_shards, uint64_t n_queries, uint32
                                    const fpx_search_opts *opts, uint32_t *out_ids, uint32_t *out_scores,
                                    uint32_t *out_counts);
 
+/* ---- request micro-batcher: the single-query seam of MultiIndex.search (MultiIndex.zig:287-330) ----
+ * Many host threads (the reference runs one coroutine per request on `executors=.auto` OS threads,
+ * main.zig:272-276) call fpx_batcher_search concurrently; a worker thread turns whatever has accumulated into
+ * one fpx_search_batch call on the snapshot that is current at that moment.  fpx_batcher_set_snapshot is the
+ * Index.swapSnapshot hook: it never waits for searches, batches in flight keep the old snapshot alive. */
+typedef struct fpx_batcher fpx_batcher;
+typedef struct fpx_batcher_config {
+    uint32_t max_batch;   /* queries per GPU batch; 0 = 4096 */
+    uint32_t max_wait_us; /* how long an idle worker lets a batch fill before launching it (default 100) */
+} fpx_batcher_config;
+typedef struct fpx_batcher_stats {
+    uint64_t batches, queries, max_batch_seen, timeouts;
+} fpx_batcher_stats;
+fpx_status fpx_batcher_create(fpx_ctx *ctx, const fpx_batcher_config *config /* may be NULL */, fpx_batcher **out);
+fpx_status fpx_batcher_set_snapshot(fpx_batcher *b, fpx_snapshot *snapshot /* NULL = none */);
+/* One query, blocking, thread-safe.  timeout_ms as api.SearchRequest.timeout (api.zig:7-8): 0 = no bound;
+ * FPX_TIMEOUT mirrors error.SearchTimeout (MultiIndex.zig:320).  At most `capacity` results. */
+fpx_status fpx_batcher_search(fpx_batcher *b, const uint32_t *terms, uint64_t n_terms, const fpx_search_opts *opts,
+                              uint32_t timeout_ms, uint32_t *out_ids, uint32_t *out_scores, uint32_t capacity,
+                              uint32_t *out_count);
+fpx_status fpx_batcher_get_stats(fpx_batcher *b, fpx_batcher_stats *out);
+/* Answers what is still queued, then stops the worker.  No fpx_batcher_search may be running or start. */
+void fpx_batcher_destroy(fpx_batcher *b);
+
 /* Queries per pipelined H2D / compute / D2H chunk of fpx_search_batch (same as fpx_config.chunk_queries);
  * takes effect for calls that start afterwards. */
 fpx_status fpx_set_chunk_queries(fpx_ctx *ctx, uint32_t chunk_queries);

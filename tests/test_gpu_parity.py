@@ -442,3 +442,54 @@ def test_pack_results_for_exchange(ctx, c2):
     torch.cuda.synchronize()
     with pytest.raises(pkg.FpxError):
         pkg.unpack_results(small.cpu().numpy(), nq, 40, 10)
+
+
+def test_micro_batcher_concurrent_single_queries(ctx, c2):
+    """fpx_batcher: 16 threads issue single queries (the MultiIndex.search seam); every answer must equal the
+    oracle's HTTP-default answer, the worker must actually batch, a snapshot swap mid-stream must not disturb
+    running searches, and an already expired deadline gives FPX_TIMEOUT (error.SearchTimeout)."""
+    import threading
+    syn, seg, snap, ix = c2
+    terms, _ = syn.queries(1500, 100, seed=555)
+    want = [ix.search_http(terms[q].tolist()) for q in range(200)]
+    b = pkg.Batcher(ctx, max_batch=256, max_wait_us=200)
+    b.set_snapshot(snap)
+    got, errs = [None] * len(terms), []
+
+    def client(t):
+        try:
+            for q in range(t, len(terms), 16):
+                got[q] = [tuple(r) for r in b.search(pkg.SearchRequest(terms[q].tolist(), timeout=0))]
+                if q == 700:
+                    b.set_snapshot(snap)      # swap (to an equal snapshot) while others are searching
+        except Exception as e:                # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=client, args=(t,)) for t in range(16)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs[:1]
+    assert got[:200] == want
+    batch_ids, batch_sc, batch_cnt = pkg.IndexReader(snap).search_batch(terms.reshape(-1), np.arange(len(terms) + 1, dtype=np.uint64) * 100,
+                                                                        pkg.synth.http_opts(len(terms), 100), 40)
+    for q in range(len(terms)):
+        n = int(batch_cnt[q])
+        assert got[q] == list(zip(batch_ids[q, :n].tolist(), batch_sc[q, :n].tolist()))
+    st = b.stats()
+    assert st["queries"] == len(terms) and st["batches"] < len(terms) and st["max_batch_seen"] > 1, st
+    # limits and errors travel per request
+    assert b.search(pkg.SearchRequest([], timeout=0)) == []
+    with pytest.raises(pkg.FpxError) as e:
+        b.search(pkg.SearchRequest(list(range(9000)), timeout=0))
+    assert e.value.status == 7                                                   # FPX_UNSUPPORTED
+    b.set_snapshot(None)
+    with pytest.raises(pkg.FpxError):
+        b.search(pkg.SearchRequest([1, 2, 3], timeout=0))
+    b.set_snapshot(snap)
+    b.close()
+    slow = pkg.Batcher(ctx, max_batch=4096, max_wait_us=300000)                  # an idle worker waits 0.3 s for company
+    slow.set_snapshot(snap)
+    with pytest.raises(pkg.FpxError) as e:
+        slow.search(pkg.SearchRequest(terms[0].tolist(), timeout=20))
+    assert e.value.status == 4 and slow.stats()["timeouts"] == 1                 # FPX_TIMEOUT
+    slow.close()
