@@ -25,6 +25,7 @@ STATUS_NAMES = {
 FPX_FLAG_PROFILE = 1
 FPX_FLAG_HOST_ONLY = 2
 FPX_FLAG_NO_SKETCH = 4
+FPX_FLAG_HOST_BUILD = 8
 FPX_MAX_QUERY_TERMS = 8192
 FPX_MAX_RESULTS = 1024
 
@@ -101,7 +102,7 @@ EXPORTS = [
     "fpx_snapshot_begin", "fpx_snapshot_add_file_segment", "fpx_snapshot_add_memory_segment",
     "fpx_snapshot_set_doc_range", "fpx_snapshot_compile", "fpx_snapshot_csr", "fpx_snapshot_commit",
     "fpx_snapshot_abort", "fpx_snapshot_acquire", "fpx_snapshot_release", "fpx_snapshot_get_info",
-    "fpx_snapshot_row_lengths", "fpx_default_min_score", "fpx_search", "fpx_search_batch",
+    "fpx_snapshot_row_lengths", "fpx_snapshot_read_row", "fpx_default_min_score", "fpx_search", "fpx_search_batch",
     "fpx_search_batch_device", "fpx_merge_shard_results", "fpx_profile_reset", "fpx_profile_read", "fpx_debug_set", "fpx_set_chunk_queries", "fpx_set_profile", "fpx_pack_results_device",
     "fpx_segment_write", "fpx_segment_buf_blocks", "fpx_segment_buf_block_index",
     "fpx_segment_buf_num_blocks", "fpx_segment_buf_num_items", "fpx_segment_buf_block_size",
@@ -153,6 +154,7 @@ def lib():
     L.fpx_snapshot_release.argtypes = [vp]
     L.fpx_snapshot_get_info.argtypes = [vp, C.POINTER(SnapshotInfo)]
     L.fpx_snapshot_row_lengths.argtypes = [vp, vp, C.c_uint64, vp]
+    L.fpx_snapshot_read_row.argtypes = [vp, C.c_uint32, vp, C.c_uint64, u64p]
     L.fpx_default_min_score.argtypes = [C.c_uint64]
     L.fpx_default_min_score.restype = C.c_uint32
     L.fpx_search.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, C.c_uint32, u32p]

@@ -10,6 +10,7 @@
 #include <condition_variable>
 #include <cstring>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -19,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/fpx.h"
+#include "fpx_gpu_build.h"
 #include "fpx_kernels.cuh"
 #include "fpx_snapshot_host.h"
 
@@ -194,7 +196,8 @@ struct fpx_ctx {
 
 struct fpx_snapshot_builder {
     fpx_ctx *ctx;
-    SnapshotCompiler compiler;
+    SnapshotCompiler compiler;                 // host build (and the debug CSR view)
+    std::unique_ptr<GpuSnapshotBuilder> gpu;   // device build: the default on a device context
     explicit fpx_snapshot_builder(fpx_ctx *c) : ctx(c), compiler(c->host_threads) {}
 };
 
@@ -205,7 +208,7 @@ struct fpx_snapshot {
     TermEntry *d_table = nullptr;
     uint32_t *d_docids = nullptr;
     fpx_snapshot_info info{};
-    std::vector<uint32_t> h_terms, h_row_len; // host copy of the term directory
+    std::vector<uint32_t> h_terms, h_row_len, h_row_start4; // host copy of the term directory (ascending terms)
 };
 
 namespace {
@@ -336,6 +339,71 @@ fpx_status enqueue_batch(fpx_snapshot *s, Workspace *w, Workspace::Slot &sl, cud
     return FPX_OK;
 }
 
+// fpx_snapshot_commit for a device-built snapshot (fpx_gpu_build.cu)
+fpx_status commit_gpu_built(fpx_snapshot_builder *b, fpx_snapshot **out) {
+    fpx_ctx *ctx = b->ctx;
+    FPX_CUDA(cudaSetDevice(ctx->device));
+    GpuCsr csr;
+    if (!b->gpu->build(csr)) {
+        if (csr.d_docids) cudaFree(csr.d_docids);
+        if (csr.d_terms) cudaFree(csr.d_terms);
+        if (csr.d_row_len) cudaFree(csr.d_row_len);
+        if (csr.d_row_start4) cudaFree(csr.d_row_start4);
+        if (b->gpu->oom) return set_error(FPX_OUT_OF_MEMORY, b->gpu->error);
+        if (b->gpu->unsupported) return set_error(FPX_UNSUPPORTED, b->gpu->error + " (use FPX_FLAG_HOST_BUILD)");
+        return set_error(FPX_INVALID_SEGMENT, b->gpu->error);
+    }
+    fpx_snapshot *s = new (std::nothrow) fpx_snapshot();
+    const uint64_t nt = csr.n_terms;
+    uint32_t log2cap = 4;
+    while ((1ull << log2cap) < 2 * nt) ++log2cap;
+    cudaError_t e = cudaSuccess;
+    if (!s || log2cap > 31) e = cudaErrorMemoryAllocation;
+    const size_t cap = (size_t)1 << log2cap;
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_table, cap * sizeof(TermEntry));
+    if (e == cudaSuccess) e = cudaMemset(s->d_table, 0, cap * sizeof(TermEntry));
+    if (e == cudaSuccess && nt) {
+        launch_build_table(s->d_table, log2cap, csr.d_terms, csr.d_row_len, csr.d_row_start4, nt, nullptr);
+        e = cudaDeviceSynchronize();
+    }
+    if (csr.d_terms) cudaFree(csr.d_terms);
+    if (csr.d_row_len) cudaFree(csr.d_row_len);
+    if (csr.d_row_start4) cudaFree(csr.d_row_start4);
+    if (e != cudaSuccess) {
+        if (s && s->d_table) cudaFree(s->d_table);
+        cudaFree(csr.d_docids);
+        delete s;
+        return cuda_fail(e, "snapshot table build");
+    }
+    s->ctx = ctx;
+    s->d_docids = csr.d_docids;
+    s->dev.table = s->d_table;
+    s->dev.table_mask = (uint32_t)(cap - 1);
+    s->dev.table_shift = 32 - log2cap;
+    s->dev.docids = s->d_docids;
+    s->dev.pad_id = csr.pad_id;
+    s->dev.pad_spread = csr.pad_spread ? 1u : 0u;
+    s->info.n_segments = b->gpu->n_segments();
+    s->info.n_terms = nt;
+    s->info.n_postings = csr.n_postings;
+    s->info.n_postings_total = csr.n_postings_total;
+    s->info.n_dropped_unreachable = csr.n_unreachable;
+    s->info.n_dropped_superseded = csr.n_superseded;
+    s->info.n_dropped_out_of_range = csr.n_out_of_range;
+    s->info.device_bytes = cap * sizeof(TermEntry) + std::max<uint64_t>(csr.total4 * 4, 4) * sizeof(uint32_t);
+    s->info.max_row_len = csr.max_row_len;
+    s->info.pad_id = csr.pad_id;
+    s->info.table_log2 = log2cap;
+    s->info.doc_lo = b->gpu->doc_lo();
+    s->info.doc_hi = b->gpu->doc_hi();
+    s->h_terms = std::move(csr.h_terms);
+    s->h_row_len = std::move(csr.h_row_len);
+    s->h_row_start4 = std::move(csr.h_row_start4);
+    delete b;
+    *out = s;
+    return FPX_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -416,12 +484,24 @@ void fpx_shutdown(fpx_ctx *ctx) {
 fpx_status fpx_snapshot_begin(fpx_ctx *ctx, fpx_snapshot_builder **out) {
     if (!ctx || !out) return set_error(FPX_INVALID_ARGUMENT, "null argument");
     *out = new (std::nothrow) fpx_snapshot_builder(ctx);
-    return *out ? FPX_OK : set_error(FPX_OUT_OF_MEMORY, "builder");
+    if (!*out) return set_error(FPX_OUT_OF_MEMORY, "builder");
+    if (!ctx->host_only && !(ctx->flags & FPX_FLAG_HOST_BUILD)) {
+        FPX_CUDA(cudaSetDevice(ctx->device));
+        (*out)->gpu.reset(new (std::nothrow) GpuSnapshotBuilder());
+    }
+    return FPX_OK;
 }
 
 fpx_status fpx_snapshot_add_file_segment(fpx_snapshot_builder *b, const fpx_file_segment *seg) {
     if (!b || !seg) return set_error(FPX_INVALID_ARGUMENT, "null argument");
     if (seg->n_docs && !seg->doc_ids) return set_error(FPX_INVALID_ARGUMENT, "null doc_ids");
+    if (b->gpu) {
+        cudaSetDevice(b->ctx->device);
+        if (!b->gpu->add_file_segment(seg->commit_id, seg->merges, seg->min_doc_id, seg->block_size, seg->blocks, seg->num_blocks,
+                                      seg->block_index, seg->doc_ids, seg->n_docs))
+            return set_error(b->gpu->oom ? FPX_OUT_OF_MEMORY : FPX_INVALID_SEGMENT, b->gpu->error);
+        return FPX_OK;
+    }
     try {
         if (!b->compiler.add_file_segment(seg->commit_id, seg->merges, seg->min_doc_id, seg->block_size, seg->blocks,
                                           seg->num_blocks, seg->block_index, seg->doc_ids, seg->n_docs))
@@ -435,6 +515,12 @@ fpx_status fpx_snapshot_add_file_segment(fpx_snapshot_builder *b, const fpx_file
 fpx_status fpx_snapshot_add_memory_segment(fpx_snapshot_builder *b, const fpx_memory_segment *seg) {
     if (!b || !seg) return set_error(FPX_INVALID_ARGUMENT, "null argument");
     if (seg->n_docs && !seg->doc_ids) return set_error(FPX_INVALID_ARGUMENT, "null doc_ids");
+    if (b->gpu) {
+        cudaSetDevice(b->ctx->device);
+        if (!b->gpu->add_memory_segment(seg->commit_id, seg->merges, seg->items, seg->n_items, seg->doc_ids, seg->n_docs))
+            return set_error(b->gpu->oom ? FPX_OUT_OF_MEMORY : FPX_INVALID_SEGMENT, b->gpu->error);
+        return FPX_OK;
+    }
     try {
         if (!b->compiler.add_memory_segment(seg->commit_id, seg->merges, seg->items, seg->n_items, seg->doc_ids,
                                             seg->n_docs))
@@ -449,11 +535,14 @@ fpx_status fpx_snapshot_set_doc_range(fpx_snapshot_builder *b, uint32_t lo, uint
     if (!b) return set_error(FPX_INVALID_ARGUMENT, "null argument");
     if (hi < lo) return set_error(FPX_INVALID_ARGUMENT, "hi < lo");
     b->compiler.set_doc_range(lo, hi);
+    if (b->gpu) b->gpu->set_doc_range(lo, hi);
     return FPX_OK;
 }
 
 fpx_status fpx_snapshot_compile(fpx_snapshot_builder *b) {
     if (!b) return set_error(FPX_INVALID_ARGUMENT, "null argument");
+    if (b->gpu)
+        return set_error(FPX_UNSUPPORTED, "the host-side CSR view needs a host-built snapshot (FPX_FLAG_HOST_BUILD or FPX_FLAG_HOST_ONLY)");
     try {
         if (!b->compiler.compile()) return set_error(FPX_INVALID_SEGMENT, b->compiler.error);
     } catch (const std::bad_alloc &) {
@@ -482,6 +571,7 @@ fpx_status fpx_snapshot_commit(fpx_snapshot_builder *b, fpx_snapshot **out) {
     *out = nullptr;
     fpx_ctx *ctx = b->ctx;
     if (ctx->host_only) return set_error(FPX_BACKEND_UNAVAILABLE, "context was created with FPX_FLAG_HOST_ONLY");
+    if (b->gpu) return commit_gpu_built(b, out);
     fpx_status st = fpx_snapshot_compile(b);
     if (st != FPX_OK) return st;
     CompiledCsr *c = b->compiler.compiled();
@@ -547,6 +637,7 @@ fpx_status fpx_snapshot_commit(fpx_snapshot_builder *b, fpx_snapshot **out) {
     s->info.doc_hi = b->compiler.doc_hi();
     s->h_terms = std::move(c->terms);
     s->h_row_len = std::move(c->row_len);
+    s->h_row_start4 = std::move(c->row_start4);
     delete b;
     *out = s;
     return FPX_OK;
@@ -585,6 +676,20 @@ fpx_status fpx_snapshot_row_lengths(const fpx_snapshot *s, const uint32_t *terms
             out_lengths[i] = (it != t.end() && *it == terms[i]) ? s->h_row_len[(size_t)(it - t.begin())] : 0u;
         }
     });
+    return FPX_OK;
+}
+
+fpx_status fpx_snapshot_read_row(const fpx_snapshot *s, uint32_t term, uint32_t *out_docids, uint64_t capacity, uint64_t *out_len) {
+    if (!s || !out_len) return set_error(FPX_INVALID_ARGUMENT, "null argument");
+    *out_len = 0;
+    auto it = std::lower_bound(s->h_terms.begin(), s->h_terms.end(), term);
+    if (it == s->h_terms.end() || *it != term) return FPX_OK;
+    const size_t g = (size_t)(it - s->h_terms.begin());
+    const uint64_t len = s->h_row_len[g];
+    *out_len = len;
+    if (len > capacity || (len && !out_docids)) return set_error(FPX_INVALID_ARGUMENT, "row does not fit the buffer");
+    FPX_CUDA(cudaSetDevice(s->ctx->device));
+    FPX_CUDA(cudaMemcpy(out_docids, s->d_docids + (size_t)s->h_row_start4[g] * 4, len * 4, cudaMemcpyDeviceToHost));
     return FPX_OK;
 }
 

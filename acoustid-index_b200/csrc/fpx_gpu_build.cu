@@ -1,0 +1,693 @@
+// fpx_gpu_build.cu — snapshot build on the device.
+//
+// The reference swaps snapshots on every update (Index.zig:469-485), so rebuilding the HBM mirror has to keep pace
+// with checkpoints and merges.  The host compiler (fpx_snapshot_host.h) decodes ~10^9 postings on CPU threads;
+// here the segments' raw bytes are uploaded as they are and everything else happens on the GPU:
+//   decode_blocks_kernel   one warp per 512-byte block: StreamVByte 0124 (hash deltas) and 1234 (docid deltas
+//                          that restart at min_doc_id on every hash change) — block.zig:66-312,
+//                          streamvbyte.zig:76-412 — with warp scans instead of pshufb tables
+//   run_state / reach      the per-hash scan caps of FileSegment.search (FileSegment.zig:25-26, 156-175): the run
+//                          that is open at a block's first item is tracked by a scan over blocks, every other run
+//                          starts inside its block and is reachable
+//   liveness               "no newer segment mentions the id" (Index.zig:133-149 + common.zig:121-129) through a
+//                          device hash map id -> newest mentioning segment
+//   select / sort / rows   CUB select of the kept postings, radix sort of (hash << 32 | docid) when several
+//                          segments feed the snapshot, run-length encoding into terms + row lengths, padded rows
+// CUB is library code used for the non-hot build path only.  The result is identical to the host compiler's
+// (tests/test_gpu_parity.py compares rows and runs the whole parity suite on GPU-built snapshots).
+#include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "fpx_codec.h"
+#include "fpx_gpu_build.h"
+
+namespace fpx {
+
+namespace {
+
+constexpr uint32_t kMaxBlocksPerHashDev = 4;   // FileSegment.zig:25
+constexpr uint32_t kMaxDocsPerHashDev = 1000;  // FileSegment.zig:26
+constexpr int kDecodeWarps = 4;
+
+struct BlockMeta { // per block, written by the decoder
+    uint32_t first_hash, last_hash;
+    uint32_t n_items;
+    uint32_t last_run_start; // index (within the block) of the first item whose hash is last_hash
+};
+
+struct RunState { // the run that is open at some point of the block sequence
+    unsigned long long start; // item index (within the segment) of the run's first item
+    uint32_t block;           // block that holds it
+    uint32_t is_const;        // scan: 1 = this element sets the state, 0 = it passes the previous one on
+};
+struct RunStateOp {
+    __device__ __forceinline__ RunState operator()(const RunState &a, const RunState &b) const { return b.is_const ? b : a; }
+};
+
+struct BuildCounters {
+    unsigned long long unreachable, superseded, out_of_range;
+    uint32_t error; // 1 corrupt block, 2 block_index mismatch, 3 hashes not ascending, 4 items not sorted
+    uint32_t max_row_len;
+};
+
+__global__ void block_counts_kernel(const uint8_t *blocks, uint32_t block_size, unsigned long long n_blocks, uint32_t *counts,
+                                    BuildCounters *ctr) {
+    const unsigned long long b = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const uint8_t *p = blocks + b * block_size;
+    const uint32_t n = (uint32_t)p[4] | ((uint32_t)p[5] << 8);
+    if (n == 0 || n > kWriterWindow) ctr->error = 1; // empty block inside the segment / impossible count
+    counts[b] = n;
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (lane >= (uint32_t)o) v += y;
+    }
+    return v;
+}
+
+// Decode one StreamVByte column of `n` values (ceil(n/4) control bytes at `ctrl`, data right after) into out[].
+// kVariant1234: lengths {1,2,3,4}, else {0,1,2,4}.  Returns false if the data runs past `limit`.
+template <bool kVariant1234>
+__device__ bool decode_column(const uint8_t *blk, uint32_t ctrl, uint32_t n, uint32_t limit, uint32_t *out, uint32_t lane) {
+    const uint32_t quads = (n + 3) >> 2;
+    uint32_t data = ctrl + quads;
+    bool ok = data <= limit;
+    for (uint32_t q0 = 0; q0 < quads; q0 += 32) {
+        const uint32_t q = q0 + lane;
+        const uint32_t c = (q < quads && ok) ? blk[ctrl + q] : 0u;
+        uint32_t len[4], tot = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t code = (c >> (2 * k)) & 3u;
+            len[k] = kVariant1234 ? code + 1u : (code == 3u ? 4u : code);
+            if (q >= quads) len[k] = 0;
+            tot += len[k];
+        }
+        const uint32_t incl = warp_incl_scan(tot, lane);
+        uint32_t off = data + incl - tot;
+        if (q < quads) {
+            if (off + tot > limit) ok = false;
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t v = 0;
+                    for (uint32_t j = 0; j < len[k]; ++j) v |= (uint32_t)blk[off + j] << (8 * j);
+                    off += len[k];
+                    if (4 * q + k < n) out[4 * q + k] = v;
+                }
+            }
+        }
+        data += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    return __all_sync(0xFFFFFFFFu, ok);
+}
+
+// One warp per block.  smem per warp: the block's bytes + two u32 arrays of max_items.
+__global__ void __launch_bounds__(kDecodeWarps * 32)
+decode_blocks_kernel(const uint8_t *blocks, uint32_t block_size, unsigned long long n_blocks, const unsigned long long *blk_off,
+                     const uint32_t *block_index, uint32_t min_doc_id, uint32_t max_items, unsigned long long *keys,
+                     BlockMeta *meta, BuildCounters *ctr) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t per_warp = ((size_t)block_size + 15) / 16 * 16 + (size_t)max_items * 8;
+    uint8_t *blk = smem + warp * per_warp;
+    uint32_t *hs = reinterpret_cast<uint32_t *>(blk + ((size_t)block_size + 15) / 16 * 16);
+    uint32_t *ds = hs + max_items;
+    for (unsigned long long b = blockIdx.x * (unsigned long long)kDecodeWarps + warp; b < n_blocks;
+         b += (unsigned long long)gridDim.x * kDecodeWarps) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(blocks + b * block_size); // block_size is a multiple of 16
+        for (uint32_t i = lane; i < block_size / 16; i += 32) reinterpret_cast<uint4 *>(blk)[i] = src[i];
+        __syncwarp();
+        const uint32_t min_hash = (uint32_t)blk[0] | ((uint32_t)blk[1] << 8) | ((uint32_t)blk[2] << 16) | ((uint32_t)blk[3] << 24);
+        const uint32_t n = (uint32_t)blk[4] | ((uint32_t)blk[5] << 8);
+        const uint32_t doff = (uint32_t)blk[6] | ((uint32_t)blk[7] << 8);
+        bool ok = n > 0 && n <= max_items && kBlockHeaderBytes + doff <= block_size;
+        if (ok) ok = decode_column<false>(blk, kBlockHeaderBytes, n, block_size, hs, lane);
+        if (ok) ok = decode_column<true>(blk, kBlockHeaderBytes + doff, n, block_size, ds, lane);
+        if (!ok) {
+            if (lane == 0) ctr->error = 1;
+            __syncwarp();
+            continue;
+        }
+        __syncwarp();
+        // hashes: prefix sum of the deltas from min_hash; docids: the delta chain restarts at min_doc_id at the
+        // block's first item and whenever the hash changes (block.zig:235-265, 438-495)
+        uint32_t h_carry = min_hash, d_carry = min_doc_id, last_start = 0;
+        const unsigned long long base = blk_off[b];
+        for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const uint32_t hd = i < n ? hs[i] : 0u;
+            const bool head = i < n && (i == 0 || hd != 0u);
+            const uint32_t h = h_carry + warp_incl_scan(hd, lane);
+            uint32_t v = i < n ? ds[i] + (head ? min_doc_id : 0u) : 0u;
+            uint32_t f = head ? 1u : 0u; // "a head lies in (start of my summed range, me]"
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v2 = __shfl_up_sync(0xFFFFFFFFu, v, o), f2 = __shfl_up_sync(0xFFFFFFFFu, f, o);
+                if (lane >= (uint32_t)o && !f) {
+                    v += v2;
+                    f |= f2;
+                }
+            }
+            if (!f) v += d_carry; // my run started in an earlier chunk of this block
+            if (i < n) keys[base + i] = ((unsigned long long)h << 32) | v;
+            const uint32_t hm = __ballot_sync(0xFFFFFFFFu, head);
+            if (hm) last_start = i0 + (31 - __clz(hm));
+            const uint32_t last_lane = min(31u, n - 1 - i0);
+            h_carry = __shfl_sync(0xFFFFFFFFu, h, last_lane);
+            d_carry = __shfl_sync(0xFFFFFFFFu, v, last_lane);
+        }
+        if (lane == 0) {
+            BlockMeta m;
+            m.first_hash = min_hash + hs[0];
+            m.last_hash = h_carry;
+            m.n_items = n;
+            m.last_run_start = last_start;
+            meta[b] = m;
+            if (block_index[b] != h_carry) ctr->error = 2; // filefmt.zig:117: block_index[b] = hash of the last item
+        }
+        __syncwarp();
+    }
+}
+
+// element b of the scan over blocks: the run open at the END of block b
+__global__ void run_state_kernel(const BlockMeta *meta, const unsigned long long *blk_off, unsigned long long n_blocks,
+                                 RunState *st, BuildCounters *ctr) {
+    const unsigned long long b = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const BlockMeta m = meta[b];
+    const bool is_new = b == 0 || meta[b - 1].last_hash != m.first_hash;
+    if (b > 0 && meta[b - 1].last_hash > m.first_hash) ctr->error = 3; // hashes must ascend across the segment
+    const bool single = m.first_hash == m.last_hash;
+    RunState s;
+    if (!single) {
+        s.start = blk_off[b] + m.last_run_start;
+        s.block = (uint32_t)b;
+        s.is_const = 1;
+    } else if (is_new) {
+        s.start = blk_off[b];
+        s.block = (uint32_t)b;
+        s.is_const = 1;
+    } else {
+        s.start = 0;
+        s.block = 0;
+        s.is_const = 0; // passes the previous block's state on
+    }
+    st[b] = s;
+}
+
+struct NewestMap { // open addressing: id -> 1-based index of the newest segment that mentions it
+    uint32_t *keys;
+    uint32_t *vals;
+    uint32_t mask;
+};
+__device__ __forceinline__ uint32_t newest_slot(uint32_t id, uint32_t mask) { return (id * 0x9E3779B1u) & mask; }
+
+__global__ void newest_insert_kernel(NewestMap m, const uint32_t *ids, unsigned long long n, uint32_t seg1) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t id = ids[i];
+    uint32_t s = newest_slot(id, m.mask);
+    for (;;) {
+        const uint32_t old = atomicCAS(m.keys + s, 0xFFFFFFFFu, id);
+        if (old == 0xFFFFFFFFu || old == id) {
+            atomicMax(m.vals + s, seg1);
+            return;
+        }
+        s = (s + 1) & m.mask;
+    }
+}
+__device__ __forceinline__ uint32_t newest_lookup(const NewestMap &m, uint32_t id) {
+    uint32_t s = newest_slot(id, m.mask);
+    for (;;) {
+        const uint32_t k = m.keys[s];
+        if (k == id) return m.vals[s];
+        if (k == 0xFFFFFFFFu) return 0;
+        s = (s + 1) & m.mask;
+    }
+}
+
+// keep flags of one segment's items.  File segments: one warp per block (the caps concern the block's first run
+// only); memory segments: blocks == nullptr, plain grid-stride.
+__global__ void keep_flags_kernel(const unsigned long long *keys, unsigned long long n_items, const BlockMeta *meta,
+                                  const unsigned long long *blk_off, const RunState *st, unsigned long long n_blocks,
+                                  NewestMap newest, uint32_t seg1, uint32_t use_newest, uint32_t lo, uint32_t hi,
+                                  uint8_t *flags, BuildCounters *ctr) {
+    unsigned long long unreach = 0, sup = 0, oor = 0;
+    const bool ranged = !(lo == 0 && hi == 0);
+    auto classify = [&](unsigned long long key, bool reachable) -> uint8_t {
+        if (!reachable) {
+            ++unreach;
+            return 0;
+        }
+        const uint32_t id = (uint32_t)key;
+        if (use_newest && newest_lookup(newest, id) > seg1) { // a newer segment mentions the id
+            ++sup;
+            return 0;
+        }
+        if (ranged && !(id >= lo && id < hi)) {
+            ++oor;
+            return 0;
+        }
+        return 1;
+    };
+    if (meta) {
+        const uint32_t lane = threadIdx.x & 31;
+        const unsigned long long warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+        for (unsigned long long b = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < n_blocks; b += warps) {
+            const BlockMeta m = meta[b];
+            const unsigned long long base = blk_off[b];
+            // the run open at this block's first item
+            RunState open;
+            const bool is_new = b == 0 || meta[b - 1].last_hash != m.first_hash;
+            if (is_new) {
+                open.start = base;
+                open.block = (uint32_t)b;
+            } else {
+                open = st[b - 1];
+            }
+            const bool first_run_ok = ((uint32_t)b - open.block) < kMaxBlocksPerHashDev && (base - open.start) <= kMaxDocsPerHashDev;
+            for (uint32_t i = lane; i < m.n_items; i += 32) {
+                const unsigned long long key = keys[base + i];
+                const bool reachable = (uint32_t)(key >> 32) != m.first_hash || first_run_ok;
+                flags[base + i] = classify(key, reachable);
+            }
+        }
+    } else {
+        for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_items;
+             i += (unsigned long long)gridDim.x * blockDim.x) {
+            const unsigned long long key = keys[i];
+            if (i > 0 && keys[i - 1] > key) ctr->error = 4; // MemorySegment items are sorted (segment.zig:87-106)
+            flags[i] = classify(key, true);
+        }
+    }
+    // warp-reduce the statistics
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unreach += __shfl_xor_sync(0xFFFFFFFFu, unreach, o);
+        sup += __shfl_xor_sync(0xFFFFFFFFu, sup, o);
+        oor += __shfl_xor_sync(0xFFFFFFFFu, oor, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (unreach) atomicAdd(&ctr->unreachable, unreach);
+        if (sup) atomicAdd(&ctr->superseded, sup);
+        if (oor) atomicAdd(&ctr->out_of_range, oor);
+    }
+}
+
+struct HashOf {
+    __host__ __device__ __forceinline__ uint32_t operator()(const unsigned long long &k) const { return (uint32_t)(k >> 32); }
+};
+struct DocOf {
+    __host__ __device__ __forceinline__ uint32_t operator()(const unsigned long long &k) const { return (uint32_t)k; }
+};
+struct Quads { // 64-bit so that the scan accumulates in 64 bits
+    __host__ __device__ __forceinline__ unsigned long long operator()(const uint32_t &len) const { return (len + 3) >> 2; }
+};
+
+// one warp per row: copy the docids of row g into its padded place; padding = unused docids above max_live,
+// varying from row to row (fpx_snapshot_host.h, same formula)
+__global__ void scatter_rows_kernel(const unsigned long long *keys, const unsigned long long *row_first, const uint32_t *row_len,
+                                    const uint32_t *row_start4, unsigned long long n_rows, uint32_t pad_base, uint32_t *docids,
+                                    BuildCounters *ctr) {
+    const uint32_t lane = threadIdx.x & 31;
+    const unsigned long long warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    uint32_t longest = 0;
+    for (unsigned long long g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_rows; g += warps) {
+        const uint32_t len = row_len[g];
+        const unsigned long long first = row_first[g];
+        uint32_t *dst = docids + (size_t)row_start4[g] * 4;
+        const uint32_t padded = (len + 3) & ~3u;
+        for (uint32_t j = lane; j < padded; j += 32)
+            dst[j] = j < len ? (uint32_t)keys[first + j] : pad_base + (uint32_t)((g * 3 + j) & 0xFFFFu);
+        longest = max(longest, len);
+    }
+    if (lane == 0 && longest) atomicMax(&ctr->max_row_len, longest);
+}
+
+__global__ void narrow_kernel(const unsigned long long *in, uint32_t *out, unsigned long long n) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)in[i];
+}
+
+template <class T> struct Dev {
+    T *p = nullptr;
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
+    void free() {
+        if (p) cudaFree(p);
+        p = nullptr;
+    }
+    ~Dev() { free(); }
+};
+
+#define GB_CUDA(call)                                                   \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);           \
+    } while (0)
+
+} // namespace
+
+struct GpuSnapshotBuilder::Segment {
+    bool is_file = false;
+    uint64_t commit_id = 0, merges = 0;
+    uint32_t min_doc_id = 0, block_size = 0;
+    uint64_t num_blocks = 0, n_items = 0, n_docs = 0;
+    uint8_t *d_blocks = nullptr;
+    uint32_t *d_block_index = nullptr;
+    unsigned long long *d_items = nullptr;
+    uint32_t *d_doc_ids = nullptr;
+    ~Segment() {
+        if (d_blocks) cudaFree(d_blocks);
+        if (d_block_index) cudaFree(d_block_index);
+        if (d_items) cudaFree(d_items);
+        if (d_doc_ids) cudaFree(d_doc_ids);
+    }
+};
+
+GpuSnapshotBuilder::GpuSnapshotBuilder() = default;
+GpuSnapshotBuilder::~GpuSnapshotBuilder() {
+    for (Segment *s : segs_) delete s;
+}
+
+bool GpuSnapshotBuilder::cuda_fail(cudaError_t e, const char *what) {
+    error = std::string(what) + ": " + cudaGetErrorString(e);
+    oom = e == cudaErrorMemoryAllocation;
+    cudaGetLastError();
+    return false;
+}
+
+bool GpuSnapshotBuilder::check_order(uint64_t commit_id, bool is_file) {
+    if (!segs_.empty()) {
+        const Segment &last = *segs_.back();
+        if (is_file && !last.is_file) return fail("file segments must precede memory segments (Index.zig:33-41)");
+        if (commit_id <= last.commit_id) return fail("segments must be added oldest to newest (ascending commit_id)");
+    }
+    return true;
+}
+
+bool GpuSnapshotBuilder::add_file_segment(uint64_t commit_id, uint64_t merges, uint32_t min_doc_id, uint32_t block_size,
+                                          const uint8_t *blocks, uint64_t num_blocks, const uint32_t *block_index,
+                                          const uint32_t *doc_ids, uint64_t n_docs) {
+    if (!check_order(commit_id, true)) return false;
+    if (block_size < kMinBlockSize || block_size > kMaxBlockSize || block_size % 16) return fail("block_size out of range");
+    if (num_blocks && (!blocks || !block_index)) return fail("null blocks / block_index");
+    if (num_blocks > 0xFFFFFFF0ull) return fail("too many blocks");
+    Segment *s = new Segment();
+    segs_.push_back(s);
+    s->is_file = true;
+    s->commit_id = commit_id;
+    s->merges = merges;
+    s->min_doc_id = min_doc_id;
+    s->block_size = block_size;
+    s->num_blocks = num_blocks;
+    s->n_docs = n_docs;
+    if (num_blocks) {
+        GB_CUDA(cudaMalloc(&s->d_blocks, num_blocks * block_size));
+        GB_CUDA(cudaMalloc(&s->d_block_index, num_blocks * 4));
+        GB_CUDA(cudaMemcpy(s->d_blocks, blocks, num_blocks * block_size, cudaMemcpyHostToDevice));
+        GB_CUDA(cudaMemcpy(s->d_block_index, block_index, num_blocks * 4, cudaMemcpyHostToDevice));
+    }
+    if (n_docs) {
+        GB_CUDA(cudaMalloc(&s->d_doc_ids, n_docs * 4));
+        GB_CUDA(cudaMemcpy(s->d_doc_ids, doc_ids, n_docs * 4, cudaMemcpyHostToDevice));
+    }
+    return true;
+}
+
+bool GpuSnapshotBuilder::add_memory_segment(uint64_t commit_id, uint64_t merges, const uint64_t *items, uint64_t n_items,
+                                            const uint32_t *doc_ids, uint64_t n_docs) {
+    if (!check_order(commit_id, false)) return false;
+    if (n_items && !items) return fail("null items");
+    Segment *s = new Segment();
+    segs_.push_back(s);
+    s->commit_id = commit_id;
+    s->merges = merges;
+    s->n_items = n_items;
+    s->n_docs = n_docs;
+    if (n_items) {
+        GB_CUDA(cudaMalloc(&s->d_items, n_items * 8));
+        GB_CUDA(cudaMemcpy(s->d_items, items, n_items * 8, cudaMemcpyHostToDevice));
+    }
+    if (n_docs) {
+        GB_CUDA(cudaMalloc(&s->d_doc_ids, n_docs * 4));
+        GB_CUDA(cudaMemcpy(s->d_doc_ids, doc_ids, n_docs * 4, cudaMemcpyHostToDevice));
+    }
+    return true;
+}
+
+bool GpuSnapshotBuilder::build(GpuCsr &out) {
+    const size_t ns = segs_.size();
+    const bool multi = ns > 1;
+    Dev<BuildCounters> ctr;
+    GB_CUDA(ctr.alloc(1));
+    GB_CUDA(cudaMemset(ctr.p, 0, sizeof(BuildCounters)));
+
+    // ---- id -> newest mentioning segment (only needed when several segments feed the snapshot)
+    NewestMap newest{nullptr, nullptr, 0};
+    Dev<uint32_t> nk, nv;
+    if (multi) {
+        uint64_t total_docs = 0;
+        for (Segment *s : segs_) total_docs += s->n_docs;
+        uint64_t cap = 16;
+        while (cap < 2 * total_docs + 2) cap <<= 1;
+        if (cap > 0x80000000ull) return fail("too many docs for the device liveness map");
+        GB_CUDA(nk.alloc(cap));
+        GB_CUDA(nv.alloc(cap));
+        GB_CUDA(cudaMemset(nk.p, 0xFF, cap * 4));
+        GB_CUDA(cudaMemset(nv.p, 0, cap * 4));
+        newest = NewestMap{nk.p, nv.p, (uint32_t)(cap - 1)};
+        for (size_t si = 0; si < ns; ++si)
+            if (segs_[si]->n_docs)
+                newest_insert_kernel<<<(unsigned)((segs_[si]->n_docs + 255) / 256), 256>>>(newest, segs_[si]->d_doc_ids,
+                                                                                          segs_[si]->n_docs, (uint32_t)si + 1);
+    }
+
+    // ---- per segment: decode, flag, count
+    std::vector<unsigned long long *> seg_keys(ns, nullptr);
+    std::vector<uint8_t *> seg_flags(ns, nullptr);
+    struct Cleanup {
+        std::vector<unsigned long long *> &k;
+        std::vector<uint8_t *> &f;
+        ~Cleanup() {
+            for (auto p : k)
+                if (p) cudaFree(p);
+            for (auto p : f)
+                if (p) cudaFree(p);
+        }
+    } cleanup{seg_keys, seg_flags};
+    uint64_t n_total = 0;
+    for (size_t si = 0; si < ns; ++si) {
+        Segment &s = *segs_[si];
+        Dev<BlockMeta> meta;
+        Dev<unsigned long long> blk_off;
+        Dev<RunState> st;
+        if (s.is_file) {
+            const uint64_t nb = s.num_blocks;
+            Dev<uint32_t> counts;
+            GB_CUDA(counts.alloc(nb));
+            GB_CUDA(blk_off.alloc(nb + 1));
+            GB_CUDA(meta.alloc(nb));
+            GB_CUDA(st.alloc(nb));
+            if (nb) {
+                block_counts_kernel<<<(unsigned)((nb + 255) / 256), 256>>>(s.d_blocks, s.block_size, nb, counts.p, ctr.p);
+                size_t tmp_bytes = 0;
+                cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.p, blk_off.p, (int)nb);
+                Dev<uint8_t> tmp;
+                GB_CUDA(tmp.alloc(tmp_bytes));
+                GB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, counts.p, blk_off.p, (int)nb));
+                unsigned long long last_off = 0;
+                uint32_t last_cnt = 0;
+                GB_CUDA(cudaMemcpy(&last_off, blk_off.p + (nb - 1), 8, cudaMemcpyDeviceToHost));
+                GB_CUDA(cudaMemcpy(&last_cnt, counts.p + (nb - 1), 4, cudaMemcpyDeviceToHost));
+                s.n_items = last_off + last_cnt;
+                GB_CUDA(cudaMemcpy(blk_off.p + nb, &s.n_items, 8, cudaMemcpyHostToDevice));
+            } else {
+                s.n_items = 0;
+            }
+            GB_CUDA(cudaMalloc(&seg_keys[si], std::max<uint64_t>(s.n_items, 1) * 8));
+            if (nb) {
+                // items per block: every quad costs two control-byte shares and >= 4 docid bytes (block.zig:479-485)
+                const uint32_t max_items = std::min<uint32_t>(kWriterWindow, 4 * ((s.block_size - kBlockHeaderBytes) / 6 + 1));
+                const size_t per_warp = ((size_t)s.block_size + 15) / 16 * 16 + (size_t)max_items * 8;
+                const size_t smem = per_warp * kDecodeWarps;
+                GB_CUDA(cudaFuncSetAttribute(decode_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                const unsigned grid = (unsigned)std::min<uint64_t>((nb + kDecodeWarps - 1) / kDecodeWarps, 148ull * 32);
+                decode_blocks_kernel<<<grid, kDecodeWarps * 32, smem>>>(s.d_blocks, s.block_size, nb, blk_off.p, s.d_block_index,
+                                                                       s.min_doc_id, max_items, seg_keys[si], meta.p, ctr.p);
+                run_state_kernel<<<(unsigned)((nb + 255) / 256), 256>>>(meta.p, blk_off.p, nb, st.p, ctr.p);
+                size_t tmp_bytes = 0;
+                cub::DeviceScan::InclusiveScan(nullptr, tmp_bytes, st.p, st.p, RunStateOp(), (int)nb);
+                Dev<uint8_t> tmp;
+                GB_CUDA(tmp.alloc(tmp_bytes));
+                GB_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, tmp_bytes, st.p, st.p, RunStateOp(), (int)nb));
+            }
+            // the raw blocks are not needed any more
+            cudaFree(s.d_blocks);
+            s.d_blocks = nullptr;
+        } else {
+            seg_keys[si] = s.d_items; // (hash << 32) | id already
+            s.d_items = nullptr;
+            if (!seg_keys[si]) GB_CUDA(cudaMalloc(&seg_keys[si], 8));
+        }
+        GB_CUDA(cudaMalloc(&seg_flags[si], std::max<uint64_t>(s.n_items, 1)));
+        if (s.n_items) {
+            const unsigned grid = 148 * 8;
+            keep_flags_kernel<<<grid, 256>>>(seg_keys[si], s.n_items, s.is_file ? meta.p : nullptr, blk_off.p, st.p, s.num_blocks,
+                                             newest, (uint32_t)si + 1, multi ? 1u : 0u, lo_, hi_, seg_flags[si], ctr.p);
+        }
+        GB_CUDA(cudaDeviceSynchronize());
+        n_total += s.n_items;
+    }
+    BuildCounters hc{};
+    GB_CUDA(cudaMemcpy(&hc, ctr.p, sizeof hc, cudaMemcpyDeviceToHost));
+    switch (hc.error) {
+    case 0: break;
+    case 1: return fail("corrupt block (stream overruns the block)");
+    case 2: return fail("block_index does not match the blocks");
+    case 3: return fail("hashes not ascending");
+    default: return fail("memory segment items not sorted");
+    }
+    if (n_total >= 0x7FFFFFFFull) return fail_unsupported("too many postings for the device build");
+
+    // ---- kept postings of all segments, back to back
+    const uint64_t n_kept_max = n_total - hc.unreachable - hc.superseded - hc.out_of_range;
+    Dev<unsigned long long> all;
+    GB_CUDA(all.alloc(n_kept_max + 1));
+    uint64_t n_kept = 0;
+    {
+        Dev<unsigned long long> d_num;
+        GB_CUDA(d_num.alloc(1));
+        for (size_t si = 0; si < ns; ++si) {
+            const uint64_t n = segs_[si]->n_items;
+            if (n == 0) continue;
+            size_t tmp_bytes = 0;
+            cub::DeviceSelect::Flagged(nullptr, tmp_bytes, seg_keys[si], seg_flags[si], all.p + n_kept, d_num.p, (int)n);
+            Dev<uint8_t> tmp;
+            GB_CUDA(tmp.alloc(tmp_bytes));
+            GB_CUDA(cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, seg_keys[si], seg_flags[si], all.p + n_kept, d_num.p, (int)n));
+            unsigned long long got = 0;
+            GB_CUDA(cudaMemcpy(&got, d_num.p, 8, cudaMemcpyDeviceToHost));
+            n_kept += got;
+            cudaFree(seg_keys[si]);
+            seg_keys[si] = nullptr;
+            cudaFree(seg_flags[si]);
+            seg_flags[si] = nullptr;
+        }
+    }
+    if (n_kept != n_kept_max) return fail("internal: kept-posting count mismatch");
+    unsigned long long *sorted = all.p;
+    Dev<unsigned long long> alt;
+    if (multi && n_kept) { // rows fed by several segments: one global order by (hash, docid)
+        GB_CUDA(alt.alloc(n_kept));
+        cub::DoubleBuffer<unsigned long long> db(all.p, alt.p);
+        size_t tmp_bytes = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, db, (int)n_kept);
+        Dev<uint8_t> tmp;
+        GB_CUDA(tmp.alloc(tmp_bytes));
+        GB_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, db, (int)n_kept));
+        sorted = db.Current();
+    }
+
+    // ---- rows: terms, lengths, padded starts
+    Dev<uint32_t> terms, lens, start4;
+    Dev<unsigned long long> row_first;
+    uint64_t n_rows = 0, total4 = 0;
+    uint32_t max_live = 0;
+    if (n_kept) {
+        GB_CUDA(terms.alloc(n_kept));
+        GB_CUDA(lens.alloc(n_kept));
+        Dev<unsigned long long> d_runs;
+        GB_CUDA(d_runs.alloc(1));
+        auto hashes = thrust::make_transform_iterator(static_cast<const unsigned long long *>(sorted), HashOf());
+        size_t tmp_bytes = 0;
+        cub::DeviceRunLengthEncode::Encode(nullptr, tmp_bytes, hashes, terms.p, lens.p, d_runs.p, (int)n_kept);
+        {
+            Dev<uint8_t> tmp;
+            GB_CUDA(tmp.alloc(tmp_bytes));
+            GB_CUDA(cub::DeviceRunLengthEncode::Encode(tmp.p, tmp_bytes, hashes, terms.p, lens.p, d_runs.p, (int)n_kept));
+        }
+        unsigned long long runs = 0;
+        GB_CUDA(cudaMemcpy(&runs, d_runs.p, 8, cudaMemcpyDeviceToHost));
+        n_rows = runs;
+        GB_CUDA(start4.alloc(n_rows + 1));
+        GB_CUDA(row_first.alloc(n_rows + 1));
+        auto q4 = thrust::make_transform_iterator(static_cast<const uint32_t *>(lens.p), Quads());
+        Dev<unsigned long long> start4_64;
+        GB_CUDA(start4_64.alloc(n_rows + 1));
+        tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, q4, start4_64.p, (int)n_rows);
+        {
+            Dev<uint8_t> tmp;
+            GB_CUDA(tmp.alloc(tmp_bytes));
+            GB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, q4, start4_64.p, (int)n_rows));
+            GB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, lens.p, row_first.p, (int)n_rows));
+        }
+        unsigned long long last4 = 0;
+        uint32_t last_len = 0;
+        GB_CUDA(cudaMemcpy(&last4, start4_64.p + (n_rows - 1), 8, cudaMemcpyDeviceToHost));
+        GB_CUDA(cudaMemcpy(&last_len, lens.p + (n_rows - 1), 4, cudaMemcpyDeviceToHost));
+        total4 = last4 + ((last_len + 3) >> 2);
+        if (total4 > 0xFFFFFFFFull) return fail_unsupported("snapshot exceeds 2^32 16-byte granules");
+        narrow_kernel<<<(unsigned)((n_rows + 255) / 256), 256>>>(start4_64.p, start4.p, n_rows);
+        // largest live docid
+        Dev<uint32_t> d_max;
+        GB_CUDA(d_max.alloc(1));
+        auto ids = thrust::make_transform_iterator(static_cast<const unsigned long long *>(sorted), DocOf());
+        tmp_bytes = 0;
+        cub::DeviceReduce::Max(nullptr, tmp_bytes, ids, d_max.p, (int)n_kept);
+        Dev<uint8_t> tmp;
+        GB_CUDA(tmp.alloc(tmp_bytes));
+        GB_CUDA(cub::DeviceReduce::Max(tmp.p, tmp_bytes, ids, d_max.p, (int)n_kept));
+        GB_CUDA(cudaMemcpy(&max_live, d_max.p, 4, cudaMemcpyDeviceToHost));
+    }
+    if (max_live >= 0xFFFE0000u) return fail_unsupported("docids reach the top of the u32 range (host build picks the padding)");
+
+    // ---- padded rows
+    out.pad_id = max_live + 1;
+    out.pad_spread = true;
+    out.n_terms = n_rows;
+    out.total4 = total4;
+    out.n_postings = n_kept;
+    out.n_postings_total = n_total;
+    out.n_unreachable = hc.unreachable;
+    out.n_superseded = hc.superseded;
+    out.n_out_of_range = hc.out_of_range;
+    GB_CUDA(cudaMalloc(&out.d_docids, std::max<uint64_t>(total4 * 4, 4) * 4));
+    if (n_rows) {
+        scatter_rows_kernel<<<148 * 8, 256>>>(sorted, row_first.p, lens.p, start4.p, n_rows, max_live + 2, out.d_docids, ctr.p);
+        GB_CUDA(cudaDeviceSynchronize());
+        GB_CUDA(cudaMemcpy(&hc, ctr.p, sizeof hc, cudaMemcpyDeviceToHost));
+    }
+    out.max_row_len = hc.max_row_len;
+    // hand the row directory arrays over (the caller builds the term hash table from them and frees them)
+    out.d_terms = terms.p;
+    out.d_row_len = lens.p;
+    out.d_row_start4 = start4.p;
+    terms.p = lens.p = start4.p = nullptr;
+    try {
+        out.h_terms.resize(n_rows);
+        out.h_row_len.resize(n_rows);
+        out.h_row_start4.resize(n_rows);
+    } catch (const std::bad_alloc &) {
+        oom = true;
+        return fail("host copy of the term directory");
+    }
+    if (n_rows) {
+        GB_CUDA(cudaMemcpy(out.h_terms.data(), out.d_terms, n_rows * 4, cudaMemcpyDeviceToHost));
+        GB_CUDA(cudaMemcpy(out.h_row_len.data(), out.d_row_len, n_rows * 4, cudaMemcpyDeviceToHost));
+        GB_CUDA(cudaMemcpy(out.h_row_start4.data(), out.d_row_start4, n_rows * 4, cudaMemcpyDeviceToHost));
+    }
+    return true;
+}
+
+} // namespace fpx

@@ -209,10 +209,11 @@ class MemorySegment:
 
 
 class Context:
-    def __init__(self, device=-1, profile=False, host_only=False, host_threads=0, chunk_queries=0, no_sketch=False):
+    def __init__(self, device=-1, profile=False, host_only=False, host_threads=0, chunk_queries=0, no_sketch=False,
+                 host_build=False):
         cfg = _ffi.Config(device, host_threads, chunk_queries,
                           (_ffi.FPX_FLAG_PROFILE if profile else 0) | (_ffi.FPX_FLAG_HOST_ONLY if host_only else 0) |
-                          (_ffi.FPX_FLAG_NO_SKETCH if no_sketch else 0))
+                          (_ffi.FPX_FLAG_NO_SKETCH if no_sketch else 0) | (_ffi.FPX_FLAG_HOST_BUILD if host_build else 0))
         self.h = C.c_void_p()
         check(lib().fpx_init(C.byref(cfg), C.byref(self.h)))
 
@@ -307,6 +308,13 @@ class Snapshot:
         if len(terms):
             check(lib().fpx_snapshot_row_lengths(self.h, terms.ctypes.data, len(terms), out.ctypes.data))
         return out
+
+    def read_row(self, term, capacity=1 << 20):
+        """The row of `term` as it lies in HBM (debug / tests)."""
+        out = np.zeros(capacity, dtype=np.uint32)
+        n = C.c_uint64(0)
+        check(lib().fpx_snapshot_read_row(self.h, int(term) & 0xFFFFFFFF, out.ctypes.data, capacity, C.byref(n)))
+        return out[:n.value].copy()
 
     def acquire(self):
         check(lib().fpx_snapshot_acquire(self.h))

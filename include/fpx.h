@@ -61,6 +61,7 @@ typedef struct fpx_config {
 #define FPX_FLAG_PROFILE 1u    /* record CUDA events around every kernel (fpx_profile_read) */
 #define FPX_FLAG_HOST_ONLY 2u  /* no device: only snapshot compilation / introspection work (CPU tests) */
 #define FPX_FLAG_NO_SKETCH 4u  /* route every query through the exact count-table kernels (A/B testing) */
+#define FPX_FLAG_HOST_BUILD 8u /* compile snapshots on host threads instead of on the device */
 
 /* An immutable file segment exactly as FileSegment holds it in RAM (FileSegment.zig:33-53). */
 typedef struct fpx_file_segment {
@@ -138,13 +139,14 @@ void fpx_shutdown(fpx_ctx *ctx);
 /* ---- snapshot build: called where Index.swapSnapshot installs a new Segments ---- */
 fpx_status fpx_snapshot_begin(fpx_ctx *ctx, fpx_snapshot_builder **out);
 /* Segments must be added oldest -> newest, all file segments before all memory segments
- * (Index.zig:33-41).  Input is fully consumed (decoded) during the call. */
+ * (Index.zig:33-41).  Input is fully consumed (uploaded or decoded) during the call. */
 fpx_status fpx_snapshot_add_file_segment(fpx_snapshot_builder *b, const fpx_file_segment *seg);
 fpx_status fpx_snapshot_add_memory_segment(fpx_snapshot_builder *b, const fpx_memory_segment *seg);
 /* Restrict the snapshot to docids in [lo, hi) (multi-GPU docid-range sharding).  The scan caps and
  * supersession rules are applied on the whole snapshot first, so shards union to the full result. */
 fpx_status fpx_snapshot_set_doc_range(fpx_snapshot_builder *b, uint32_t lo, uint32_t hi);
-/* Compile to CSR on the host (idempotent; commit calls it if needed). */
+/* Compile to CSR on the host (idempotent).  Host-built snapshots only (FPX_FLAG_HOST_BUILD / FPX_FLAG_HOST_ONLY):
+ * by default a device context decodes the segments and assembles the rows on the GPU at commit. */
 fpx_status fpx_snapshot_compile(fpx_snapshot_builder *b);
 fpx_status fpx_snapshot_csr(fpx_snapshot_builder *b, fpx_csr_view *out);
 /* Upload to HBM; consumes the builder on success.  refcount starts at 1. */
@@ -154,6 +156,10 @@ void fpx_snapshot_abort(fpx_snapshot_builder *b);
 fpx_status fpx_snapshot_acquire(fpx_snapshot *s);
 fpx_status fpx_snapshot_release(fpx_snapshot *s);
 fpx_status fpx_snapshot_get_info(const fpx_snapshot *s, fpx_snapshot_info *out);
+/* The row of `term` as it lies in HBM (without padding): debug / tests.  *out_len receives the row length (0 if the
+ * term is absent); FPX_INVALID_ARGUMENT if it does not fit `capacity`. */
+fpx_status fpx_snapshot_read_row(const fpx_snapshot *s, uint32_t term, uint32_t *out_docids, uint64_t capacity,
+                                 uint64_t *out_len);
 /* Row length of each term (0 if absent) from the host-side copy of the term directory. */
 fpx_status fpx_snapshot_row_lengths(const fpx_snapshot *s, const uint32_t *terms, uint64_t n,
                                     uint32_t *out_lengths);

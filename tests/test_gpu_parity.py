@@ -493,3 +493,47 @@ def test_micro_batcher_concurrent_single_queries(ctx, c2):
         slow.search(pkg.SearchRequest(terms[0].tolist(), timeout=20))
     assert e.value.status == 4 and slow.stats()["timeouts"] == 1                 # FPX_TIMEOUT
     slow.close()
+
+
+def test_device_built_snapshot_equals_host_built(ctx, c2):
+    """fpx_gpu_build.cu (StreamVByte block decode, scan caps, liveness, row assembly on the GPU — the default for a
+    device context) against the host compiler: same statistics, same term directory, same rows, on a multi-segment
+    index with updates, deletes, duplicate hashes and hot terms that hit both scan caps, with and without a docid
+    range, and on C2."""
+    host_ctx = pkg.Context(device=0, host_build=True)
+    rng = np.random.default_rng(2024)
+    ix, ids = _random_index(rng, rounds=9, n_docs=700, H=40, vocab=3000)
+    ix.update([("insert", int(ids[3]), [1, 2, 3]), ("delete", int(ids[4]))])       # a memory segment on top
+    files, mems = segments_from_oracle(ix)
+    assert len(files) == 3 and len(mems) == 1
+    for doc_range in (None, (100, 900)):
+        a = pkg.swap_snapshot(ctx, files, mems, doc_range=doc_range)               # device build
+        b = pkg.swap_snapshot(host_ctx, files, mems, doc_range=doc_range)          # host build
+        ia, ib = a.info(), b.info()
+        for k in ("n_segments", "n_terms", "n_postings", "n_postings_total", "n_dropped_unreachable",
+                  "n_dropped_superseded", "n_dropped_out_of_range", "max_row_len", "pad_id", "doc_lo", "doc_hi"):
+            assert ia[k] == ib[k], (k, ia[k], ib[k])
+        assert ia["n_dropped_unreachable"] > 0 and ia["n_dropped_superseded"] > 0
+        terms = np.arange(0, 3000, dtype=np.uint32)
+        assert np.array_equal(a.row_lengths(terms), b.row_lengths(terms))
+        for t in list(range(0, 3000, 37)) + [7, 8]:                               # 7, 8: the hot terms
+            assert np.array_equal(a.read_row(t), b.read_row(t)), t
+        a.release(), b.release()
+    syn, seg, snap, _ = c2                                                          # `snap` was built on the device
+    hb = pkg.swap_snapshot(host_ctx, [seg])
+    ia, ib = snap.info(), hb.info()
+    assert all(ia[k] == ib[k] for k in ("n_terms", "n_postings", "max_row_len", "pad_id", "device_bytes"))
+    sample = syn.queries(50, 100, seed=5)[0].reshape(-1)
+    assert np.array_equal(snap.row_lengths(sample), hb.row_lengths(sample))
+    for t in sample[:300]:
+        assert np.array_equal(snap.read_row(int(t)), hb.read_row(int(t)))
+    hb.release()
+    # a corrupt block is reported, not decoded
+    bad = pkg.FileSegment(seg.commit_id, 0, seg.min_doc_id, seg.block_size, seg.blocks[:4 * 512].copy(), 4,
+                          seg.block_index[:4].copy(), seg.doc_ids, seg.doc_alive)
+    bad.blocks[512 + 6] = 0xFF
+    bad.blocks[512 + 7] = 0xFF                                                       # docids_offset beyond the block
+    with pytest.raises(pkg.FpxError) as e:
+        pkg.swap_snapshot(ctx, [bad])
+    assert e.value.status == 3
+    host_ctx.close()
