@@ -1267,18 +1267,27 @@ template <int LOG> __device__ __forceinline__ uint32_t table_docid(uint32_t word
     return ((home << P::kRemBits) | rem) * kMultInv;
 }
 
-template <int LOG> constexpr size_t smem_bytes_for() {
-    return (size_t)Packed<LOG>::kSlots * 4 + kFastKbuf * 8 + kRowsChunk * 16;
+constexpr uint32_t kSmemRowsChunk = 128; // row descriptors staged per round by the shared-memory kernels
+template <int THREADS> struct SmemKbuf { static constexpr uint32_t kCap = THREADS <= 512 ? 1024u : 2048u; }; // >= kFastKbuf + THREADS
+template <int LOG, int THREADS> constexpr size_t smem_bytes_for() {
+    return (size_t)Packed<LOG>::kSlots * 4 + (size_t)SmemKbuf<THREADS>::kCap * 8 + kSmemRowsChunk * 16;
 }
 
-template <int LOG>
-__global__ void __launch_bounds__(kThreads, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))) search_smem_kernel(BatchArgs a) {
+// THREADS: 256 for the two small tables (4 and 3 CTAs per SM); the 128 KB table leaves room for one CTA per SM
+// only, which then runs 1024 threads to keep enough loads in flight.
+template <int LOG, int THREADS>
+__global__ void __launch_bounds__(THREADS, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))) search_smem_kernel(BatchArgs a) {
+    constexpr int kThreads = THREADS, kWarps = THREADS / 32; // shadow the file-level constants
     using P = Packed<LOG>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem_raw);
+    // candidate buffer: the up to kFastKbuf best so far + one scan round (one slot per thread); a power of two
+    constexpr uint32_t kKbufCap = SmemKbuf<THREADS>::kCap;
+    constexpr uint32_t kRows = kSmemRowsChunk;
     unsigned long long *kbuf = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)P::kSlots * 4);
-    uint4 *rows_s = reinterpret_cast<uint4 *>(smem_raw + (size_t)P::kSlots * 4 + kFastKbuf * 8);
-    __shared__ uint32_t s_idx, s_ncand, s_ovf, s_count;
+    uint4 *rows_s = reinterpret_cast<uint4 *>(smem_raw + (size_t)P::kSlots * 4 + kKbufCap * 8);
+    __shared__ uint32_t s_idx, s_ncand, s_ovf, s_count, s_qual;
+    __shared__ unsigned long long s_kth; // running threshold: only keys below it can still make the top k_eff
 
     constexpr int cls = LOG - 12;
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
@@ -1296,11 +1305,14 @@ __global__ void __launch_bounds__(kThreads, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1)
             s_idx = atomicAdd(&a.counters->qhead[cls], 1u);
             s_ncand = 0;
             s_ovf = 0;
+            s_qual = 0;
+            s_kth = ~0ull;
         }
         __syncthreads();
         if (s_idx >= qcount) break;
         const WorkItem w = a.items[(size_t)cls * a.n_queries + s_idx];
         const uint32_t thr = max(w.min_score, 1u); // a doc in the table has score >= 1
+        const uint32_t k_eff = min(w.k_eff, kFastKbuf);
         const uint4 *rows = a.rows + w.rows_off;
         uint32_t passes = 1;
         if (LOG == 15)
@@ -1308,8 +1320,8 @@ __global__ void __launch_bounds__(kThreads, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1)
         const uint32_t pmask = passes - 1u;
 
         for (uint32_t pass = 0; pass < passes; ++pass) {
-            for (uint32_t r0 = 0; r0 < w.n_rows; r0 += kRowsChunk) {
-                const uint32_t nr = min(kRowsChunk, w.n_rows - r0);
+            for (uint32_t r0 = 0; r0 < w.n_rows; r0 += kRows) {
+                const uint32_t nr = min(kRows, w.n_rows - r0);
                 __syncthreads();
                 for (uint32_t i = tid; i < nr; i += kThreads) rows_s[i] = rows[r0 + i];
                 __syncthreads();
@@ -1335,33 +1347,82 @@ __global__ void __launch_bounds__(kThreads, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1)
                 }
             }
             __syncthreads();
-            // scan + clear; candidates are docs with score >= max(min_score,1)  (common.zig:140-145)
-            for (uint32_t i = tid; i < P::kSlots / 4; i += kThreads) {
+            // scan + clear; candidates are docs with score >= max(min_score,1)  (common.zig:140-145) whose key
+            // can still make the top k_eff.  First count them ...
+            const unsigned long long kth = s_kth;
+            // (skipped when the candidates of this pass fit for sure: at most postings / thr docs can reach thr)
+            const bool sure = passes == 1 && w.postings / thr <= kKbufCap;
+            uint32_t mine = 0;
+            for (uint32_t i = tid; i < P::kSlots / 4 && !sure; i += kThreads) {
                 const uint4 wd = tab4[i];
                 if ((wd.x | wd.y | wd.z | wd.w) == 0u) continue;
-                tab4[i] = make_uint4(0, 0, 0, 0);
                 const uint32_t ws[4] = {wd.x, wd.y, wd.z, wd.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const uint32_t cnt = ws[e] & P::kCntMask;
-                    if (ws[e] != 0u && cnt >= thr) {
-                        const uint32_t pos = atomicAdd(&s_ncand, 1u);
-                        if (pos < kFastKbuf) kbuf[pos] = rank_key(cnt, table_docid<LOG>(ws[e], i * 4 + e));
+                    if (ws[e] != 0u && cnt >= thr && rank_key(cnt, table_docid<LOG>(ws[e], i * 4 + e)) < kth) ++mine;
+                }
+            }
+            if (mine) atomicAdd(&s_qual, mine);
+            __syncthreads();
+            const uint32_t qual = s_qual, have = s_ncand;
+            __syncthreads();
+            if (tid == 0) s_qual = 0;
+            if (have + qual <= kKbufCap) {
+                // ... the usual case: they all fit
+                for (uint32_t i = tid; i < P::kSlots / 4; i += kThreads) {
+                    const uint4 wd = tab4[i];
+                    if ((wd.x | wd.y | wd.z | wd.w) == 0u) continue;
+                    tab4[i] = make_uint4(0, 0, 0, 0);
+                    const uint32_t ws[4] = {wd.x, wd.y, wd.z, wd.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t cnt = ws[e] & P::kCntMask;
+                        if (ws[e] != 0u && cnt >= thr) {
+                            const unsigned long long key = rank_key(cnt, table_docid<LOG>(ws[e], i * 4 + e));
+                            if (key < kth) kbuf[atomicAdd(&s_ncand, 1u)] = key;
+                        }
                     }
+                }
+            } else {
+                // ... many candidates (hot, capped rows share their low docids): one slot per thread and round;
+                // whenever another round might not fit, keep the k_eff best and raise the bar
+                auto shrink = [&](uint32_t n) {
+                    group_sort_keys(g, kbuf, n, kKbufCap);
+                    __syncthreads();
+                    if (tid == 0) {
+                        s_ncand = min(n, k_eff);
+                        if (n >= k_eff && k_eff > 0) s_kth = kbuf[k_eff - 1];
+                    }
+                    __syncthreads();
+                };
+                if (have + kThreads > kKbufCap) shrink(have);
+                for (uint32_t base = 0; base < P::kSlots; base += kThreads) {
+                    const uint32_t slot = base + tid;
+                    const uint32_t wv = tab[slot];
+                    tab[slot] = 0u;
+                    const uint32_t cnt = wv & P::kCntMask;
+                    if (wv != 0u && cnt >= thr) {
+                        const unsigned long long key = rank_key(cnt, table_docid<LOG>(wv, slot));
+                        if (key < s_kth) kbuf[atomicAdd(&s_ncand, 1u)] = key;
+                    }
+                    __syncthreads();
+                    const uint32_t n = s_ncand;
+                    if (n + kThreads > kKbufCap) shrink(n);
                 }
             }
         }
         __syncthreads();
         const uint32_t n = s_ncand;
-        if (s_ovf || n > kFastKbuf) {
-            // not representable here: hand the query to the global-memory path (still exact)
+        if (s_ovf) {
+            // not representable here (count or probe field overflow): the global-memory path takes the query
             if (tid == 0) {
                 enqueue(a, kWideClass, w);
                 if (a.stats) atomicAdd(&a.stats->overflow_requeues, 1ull);
             }
             continue;
         }
-        group_sort_keys(g, kbuf, n, kFastKbuf);
+        group_sort_keys(g, kbuf, n, kKbufCap);
         group_emit_results(g, a, w, kbuf, n, &s_count);
     }
 }
@@ -1570,11 +1631,11 @@ __global__ void __launch_bounds__(256) result_pack_kernel(const uint32_t *ids, c
 // ------------------------------------------------------------------------------------------------
 cudaError_t configure_kernels() {
     cudaError_t e;
-    e = cudaFuncSetAttribute(search_smem_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for<13>());
+    e = cudaFuncSetAttribute(search_smem_kernel<13, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for<13, 256>());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(search_smem_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for<14>());
+    e = cudaFuncSetAttribute(search_smem_kernel<14, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for<14, 256>());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(search_smem_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for<15>());
+    e = cudaFuncSetAttribute(search_smem_kernel<15, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for<15, 1024>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_sketch_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
     if (e != cudaSuccess) return e;
@@ -1612,9 +1673,9 @@ void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms) {
 
 void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms) {
     switch (cls) {
-    case 1: search_smem_kernel<13><<<n_sms * 4, kThreads, smem_bytes_for<13>(), st>>>(a); break;
-    case 2: search_smem_kernel<14><<<n_sms * 3, kThreads, smem_bytes_for<14>(), st>>>(a); break;
-    case 3: search_smem_kernel<15><<<n_sms * 1, kThreads, smem_bytes_for<15>(), st>>>(a); break;
+    case 1: search_smem_kernel<13, 256><<<n_sms * 4, 256, smem_bytes_for<13, 256>(), st>>>(a); break;
+    case 2: search_smem_kernel<14, 256><<<n_sms * 3, 256, smem_bytes_for<14, 256>(), st>>>(a); break;
+    case 3: search_smem_kernel<15, 1024><<<n_sms * 1, 1024, smem_bytes_for<15, 1024>(), st>>>(a); break;
     default: break;
     }
 }
