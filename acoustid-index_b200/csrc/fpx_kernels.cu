@@ -520,7 +520,7 @@ search_sketch_kernel(BatchArgs a) {
     unsigned char *sketch_base = smem_raw;                                   // 2 x 32 KB
     uint4 *stage = reinterpret_cast<uint4 *>(smem_raw + 2 * (size_t)kSketchWords * 4);
     uint32_t *rec_base = reinterpret_cast<uint32_t *>(smem_raw + 2 * (size_t)kSketchWords * 4 + (size_t)kSkStages * kStageU4 * 16);
-    __shared__ uint64_t full[kSkStages], empty[kSkStages], counted[2], sk_free[2];
+    __shared__ uint64_t full[kSkStages]; // TMA completion; every other hand-over is a named barrier (ids 1..14)
     __shared__ StageMeta meta[kSkStages];
     __shared__ uint32_t s_nrec[2], s_known[2];
     __shared__ ResolverState rs[kSkResolverGroups];
@@ -538,11 +538,8 @@ search_sketch_kernel(BatchArgs a) {
     if (tid == 0) {
         for (int s = 0; s < kSkStages; ++s) {
             mbar_init(&full[s], 2);
-            mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&counted[b], kSkCounterWarps);
-            mbar_init(&sk_free[b], 1);
             s_nrec[b] = 0;
             s_known[b] = pad;
         }
@@ -583,10 +580,8 @@ search_sketch_kernel(BatchArgs a) {
             const bool have1 = item_at(it + kSkStages, w1); // my next query: in flight during wait + issue
             if (have1) rows_of(w1, d1);
             const long long tp0 = clock64();
-            if (use > 0) { // wait until the resolvers released the previous tenant of my stage
-                if (lane == 0) mbar_wait(&empty[s], (use - 1) & 1, wm);
-                __syncwarp();
-            }
+            if (use > 0) // wait until the resolvers released the previous tenant of my stage
+                asm volatile("bar.sync %0, 96;" ::"r"(7u + s) : "memory"); // my pair (64) + the resolvers' warp 0 (32)
             if (p == 0 && lane == 0) tick(0, tp0);
             // the row's place in the stage (d.z) was computed by prepare_kernel
             uint32_t mine = ((d[0].y + 3) >> 2) + ((d[1].y + 3) >> 2);
@@ -636,11 +631,8 @@ search_sketch_kernel(BatchArgs a) {
             if (idx >= count) break;
             const uint32_t s = it % kSkStages;
             const long long tr0 = clock64();
-            if (rwarp == 0) {
-                if (lane == 0) mbar_wait(&counted[b], (it >> 1) & 1, wm); // all counter warps are done with query it
-                __syncwarp();
-            }
-            R.sync();
+            // all counter warps are done with query it (they arrive, this group waits)
+            asm volatile("bar.sync %0, %1;" ::"r"(11u + b), "r"(kSkCounters + kSkResolvers) : "memory");
             if (gidx == 0 && rtid == 0) tick(3, tr0);
             const WorkItem w = meta[s].item;
             const uint32_t nrec = (a.debug & 2u) ? 0u : s_nrec[b];
@@ -675,9 +667,9 @@ search_sketch_kernel(BatchArgs a) {
             if (rtid == 0) { // sketch cleared, records consumed: the counters may start query it+2 on them
                 s_nrec[b] = 0;
                 s_known[b] = pad;
-                mbar_arrive(&sk_free[b]);
                 if (gidx == 0) tick(4, tr0);
             }
+            if (rwarp == 0) asm volatile("bar.arrive %0, %1;" ::"r"(13u + b), "r"(kSkCounters + 32) : "memory");
             uint32_t n = 0;
             bool redo = false;
             if (nrec != 0u) {
@@ -728,10 +720,8 @@ search_sketch_kernel(BatchArgs a) {
                     __syncwarp();
                 }
             }
-            if (rtid == 0) {
-                st.nset = st.ovf = 0;
-                mbar_arrive(&empty[s]); // the stage goes back to the producers
-            }
+            if (rtid == 0) st.nset = st.ovf = 0;
+            if (rwarp == 0) asm volatile("bar.arrive %0, 96;" ::"r"(7u + s) : "memory"); // the stage goes back to the producers
             if (rwarp == 0) {
                 if (redo) {
                     // too many candidates for this path: the exact count-table kernels take the query
@@ -762,13 +752,19 @@ search_sketch_kernel(BatchArgs a) {
         if (idx >= count) break;
         const uint32_t s = it % kSkStages, b = it & 1u;
         const long long tc0 = clock64();
-        if (lane == 0) {
-            mbar_wait(&full[s], (it / kSkStages) & 1, wm);
-            if (warp == 0) tick(7, tc0);
-            if (it >= 2) mbar_wait(&sk_free[b], ((it >> 1) - 1) & 1, wm); // sketch b cleared, records consumed
-            if (warp == 0) tick(8, tc0);
+        // Hand-overs between the roles are named barriers (arrive / sync): parked warps cost no issue slots, polling
+        // loops do, and the kernel is issue bound.  Only the TMA completion needs an mbarrier: one counter warp
+        // polls it, the other fifteen wait on a named barrier.
+        if (it >= 2) // sketch b cleared, records consumed by the resolvers of query it-2
+            asm volatile("bar.sync %0, %1;" ::"r"(13u + b), "r"(kSkCounters + 32) : "memory");
+        if (warp == 0) {
+            if (lane == 0) {
+                mbar_wait(&full[s], (it / kSkStages) & 1, wm);
+                tick(7, tc0);
+            }
+            __syncwarp();
         }
-        __syncwarp();
+        asm volatile("bar.sync 6, %0;" ::"r"(kSkCounters) : "memory");
         const uint32_t total4 = meta[s].item.total4;
         const uint32_t thr_m1 = meta[s].item.min_score - 1u; // min_score >= 2 in this class
         const uint4 *st = stage + (size_t)s * kStageU4;
@@ -819,7 +815,8 @@ search_sketch_kernel(BatchArgs a) {
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&counted[b]); // my slice of query it is in the sketch (release)
+        // my slice of query it is in the sketch
+        asm volatile("bar.arrive %0, %1;" ::"r"(11u + b), "r"(kSkCounters + kSkResolvers) : "memory");
         if (warp == 0 && lane == 0) {
             tick(9, tc0);
             if (timed) atomicAdd(&a.stats->dbg[10], 1ull);
