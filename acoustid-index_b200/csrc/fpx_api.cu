@@ -1151,6 +1151,9 @@ fpx_status fpx_profile_read(fpx_ctx *ctx, fpx_profile *out) {
         ctx->prof.sketch_queries = ds.sketch_queries;
         ctx->prof.overflow_requeues = ds.overflow_requeues;
         if (ctx->debug & 512u) {
+            const double rq = (double)(ds.dbg[6] ? ds.dbg[6] : 1);
+            std::fprintf(stderr, "[fpx dbg] resolver detail (clk from start of iteration): compacted %.0f recounted %.0f emitted %.0f end %.0f\n",
+                         (double)ds.dbg[11] / rq, (double)ds.dbg[12] / rq, (double)ds.dbg[13] / rq, (double)ds.dbg[5] / rq);
             std::fprintf(stderr, "[fpx dbg] producer: wait_empty %.0f iter %.0f clk/query (%llu) | resolver: wait_counted %.0f to_sk_free %.0f iter %.0f (%llu) | counter: wait_full %.0f +sk_free %.0f iter %.0f (%llu)\n",
                          (double)ds.dbg[0] / (double)(ds.dbg[2] ? ds.dbg[2] : 1), (double)ds.dbg[1] / (double)(ds.dbg[2] ? ds.dbg[2] : 1), ds.dbg[2],
                          (double)ds.dbg[3] / (double)(ds.dbg[6] ? ds.dbg[6] : 1), (double)ds.dbg[4] / (double)(ds.dbg[6] ? ds.dbg[6] : 1),

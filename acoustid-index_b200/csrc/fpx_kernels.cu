@@ -344,7 +344,10 @@ __device__ __forceinline__ unsigned long long rank_key(uint32_t score, uint32_t 
 struct Group {
     uint32_t tid, size, bar; // thread index in the group, group size (multiple of 32), named barrier id
     __device__ __forceinline__ void sync() const {
-        asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(size) : "memory");
+        if (size == 32u)
+            __syncwarp(); // a single warp needs no barrier resource
+        else
+            asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(size) : "memory");
     }
 };
 
@@ -485,7 +488,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // counter is already >= min_score-1 and d is recorded.  Its exact count is then taken from the rows.
 // The kernel is bound by integer-ALU issue, not by memory, so everything per posting is kept minimal.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSkResolverGroups = 2;
 constexpr int kSkResolverWarps = 4; // per group
 constexpr int kSkStages = 4;
 constexpr int kSkResolvers = kSkResolverWarps * 32;
@@ -509,9 +511,14 @@ struct ResolverState { // private to one resolver group
     uint32_t nset, ovf, c_n, r_count;
 };
 
-template <int kSkCounterWarps, int kSkProducerWarps>
+// named barrier ids (0 is __syncthreads): resolver groups 1..3, counters 4, stage release 5..8, "counted" 9..11 (one
+// per resolver group: two groups must never wait on the same id), "sketch free" 12..13 (one per sketch)
+constexpr uint32_t kBarGroup = 1, kBarCounters = 4, kBarStage = 5, kBarCounted = 9, kBarSkFree = 12;
+
+template <int kSkCounterWarps, int kSkResolverGroups, int kSkProducerWarps>
 __global__ void __launch_bounds__((kSkCounterWarps + kSkResolverGroups * kSkResolverWarps + kSkProducerWarps) * 32, 1)
 search_sketch_kernel(BatchArgs a) {
+    static_assert(kSkResolverGroups >= 2 && kSkResolverGroups <= 3, "barrier ids");
     constexpr int kSkFirstResolver = kSkCounterWarps;
     constexpr int kSkFirstProducer = kSkCounterWarps + kSkResolverGroups * kSkResolverWarps;
     constexpr int kSkThreads = (kSkFirstProducer + kSkProducerWarps) * 32;
@@ -537,7 +544,7 @@ search_sketch_kernel(BatchArgs a) {
 
     if (tid == 0) {
         for (int s = 0; s < kSkStages; ++s) {
-            mbar_init(&full[s], 2);
+            mbar_init(&full[s], kSkProducerWarps / kSkStages);
         }
         for (int b = 0; b < 2; ++b) {
             s_nrec[b] = 0;
@@ -554,8 +561,10 @@ search_sketch_kernel(BatchArgs a) {
     if (warp >= kSkFirstProducer) {
         // ===== producers: warp pair `pair` owns stage `pair` and every kSkStages-th query; within the pair
         // warp `half` issues the even / odd rows.  Each lane holds two row descriptors of its warp's rows.
-        static_assert(kSkProducerWarps == 2 * kSkStages, "one producer warp pair per stage");
-        const uint32_t p = warp - kSkFirstProducer, pair = p >> 1, half = p & 1u;
+        // (kPW = 1: one warp per stage, four descriptors per lane.)
+        constexpr int kPW = kSkProducerWarps / kSkStages, kDesc = 4 / kPW; // kPW * 32 * kDesc = kSketchMaxRows
+        static_assert(kSkProducerWarps == kPW * kSkStages && (kPW == 1 || kPW == 2), "one or two producer warps per stage");
+        const uint32_t p = warp - kSkFirstProducer, pair = p / kPW, half = p % kPW;
         const uint4 *docids4 = reinterpret_cast<const uint4 *>(a.snap.docids);
         const uint32_t s = pair;
         uint4 *dst = stage + (size_t)s * kStageU4;
@@ -565,31 +574,33 @@ search_sketch_kernel(BatchArgs a) {
             w = items[idx];
             return true;
         };
-        auto rows_of = [&](const WorkItem &w, uint4 (&d)[2]) {
+        auto rows_of = [&](const WorkItem &w, uint4 (&d)[kDesc]) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const uint32_t r = 2u * (lane + 32 * j) + half;
+            for (int j = 0; j < kDesc; ++j) {
+                const uint32_t r = (uint32_t)kPW * (lane + 32 * j) + half;
                 d[j] = r < w.n_rows ? a.rows[w.rows_off + r] : make_uint4(0u, 0u, 0u, 0u);
             }
         };
         WorkItem w{}, w1{};
-        uint4 d[2], d1[2];
+        uint4 d[kDesc], d1[kDesc];
         bool have = item_at(pair, w);
         if (have) rows_of(w, d);
         for (uint32_t it = pair, use = 0; have; it += kSkStages, ++use) {
             const bool have1 = item_at(it + kSkStages, w1); // my next query: in flight during wait + issue
             if (have1) rows_of(w1, d1);
             const long long tp0 = clock64();
-            if (use > 0) // wait until the resolvers released the previous tenant of my stage
-                asm volatile("bar.sync %0, 96;" ::"r"(7u + s) : "memory"); // my pair (64) + the resolvers' warp 0 (32)
+            if (use > 0) // wait until the resolvers released the previous tenant of my stage: my warp(s) + their warp 0
+                asm volatile("bar.sync %0, %1;" ::"r"(kBarStage + s), "r"(32 * kPW + 32) : "memory");
             if (p == 0 && lane == 0) tick(0, tp0);
             // the row's place in the stage (d.z) was computed by prepare_kernel
-            uint32_t mine = ((d[0].y + 3) >> 2) + ((d[1].y + 3) >> 2);
+            uint32_t mine = 0;
+#pragma unroll
+            for (int j = 0; j < kDesc; ++j) mine += (d[j].y + 3) >> 2;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
 #pragma unroll
-            for (int j = 0; j < 2; ++j) { // stage directory for the exact recount
-                const uint32_t r = 2u * (lane + 32 * j) + half;
+            for (int j = 0; j < kDesc; ++j) { // stage directory for the exact recount
+                const uint32_t r = (uint32_t)kPW * (lane + 32 * j) + half;
                 meta[s].row_off[r] = d[j].z * 4u;
                 meta[s].row_len[r] = d[j].y;
             }
@@ -600,13 +611,13 @@ search_sketch_kernel(BatchArgs a) {
             __syncwarp();
             if (!(a.debug & 8u)) {
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
+                for (int j = 0; j < kDesc; ++j)
                     if (d[j].y) bulk_g2s(dst + d[j].z, docids4 + d[j].x, ((d[j].y + 3) >> 2) * 16u, &full[s]);
             }
             have = have1;
             w = w1;
-            d[0] = d1[0];
-            d[1] = d1[1];
+#pragma unroll
+            for (int j = 0; j < kDesc; ++j) d[j] = d1[j];
             if (p == 0 && lane == 0) {
                 tick(1, tp0);
                 if (timed) atomicAdd(&a.stats->dbg[2], 1ull);
@@ -616,23 +627,22 @@ search_sketch_kernel(BatchArgs a) {
     }
 
     if (warp >= kSkFirstResolver) {
-        // ===== resolvers: group gidx owns sketch / record buffer gidx and every second query
+        // ===== resolvers: group gidx takes every kSkResolverGroups-th query; query `it` used sketch / record buffer it & 1
         const uint32_t gidx = (warp - kSkFirstResolver) / kSkResolverWarps;
         const uint32_t rwarp = (warp - kSkFirstResolver) % kSkResolverWarps;
         const uint32_t rtid = rwarp * 32 + lane;
-        const Group R{rtid, (uint32_t)kSkResolvers, 1u + gidx};
-        const Group W{lane, 32u, 3u + gidx};
+        const Group R{rtid, (uint32_t)kSkResolvers, kBarGroup + gidx};
+        const Group W{lane, 32u, 0u};
         ResolverState &st = rs[gidx];
-        const uint32_t b = gidx;
-        uint4 *sk4 = reinterpret_cast<uint4 *>(sketch_base + (size_t)b * kSketchWords * 4);
-        const uint32_t *rec = rec_base + b * kRecCap;
         for (uint32_t it = gidx;; it += kSkResolverGroups) {
             const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
             if (idx >= count) break;
-            const uint32_t s = it % kSkStages;
+            const uint32_t s = it % kSkStages, b = it & 1u;
+            uint4 *sk4 = reinterpret_cast<uint4 *>(sketch_base + (size_t)b * kSketchWords * 4);
+            const uint32_t *rec = rec_base + b * kRecCap;
             const long long tr0 = clock64();
             // all counter warps are done with query it (they arrive, this group waits)
-            asm volatile("bar.sync %0, %1;" ::"r"(11u + b), "r"(kSkCounters + kSkResolvers) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(kBarCounted + gidx), "r"(kSkCounters + kSkResolvers) : "memory");
             if (gidx == 0 && rtid == 0) tick(3, tr0);
             const WorkItem w = meta[s].item;
             const uint32_t nrec = (a.debug & 2u) ? 0u : s_nrec[b];
@@ -669,7 +679,7 @@ search_sketch_kernel(BatchArgs a) {
                 s_known[b] = pad;
                 if (gidx == 0) tick(4, tr0);
             }
-            if (rwarp == 0) asm volatile("bar.arrive %0, %1;" ::"r"(13u + b), "r"(kSkCounters + 32) : "memory");
+            if (rwarp == 0) asm volatile("bar.arrive %0, %1;" ::"r"(kBarSkFree + b), "r"(kSkCounters + 32) : "memory");
             uint32_t n = 0;
             bool redo = false;
             if (nrec != 0u) {
@@ -691,6 +701,7 @@ search_sketch_kernel(BatchArgs a) {
                     if (lane == 0) st.c_n = min(nc, kMaxCand);
                 }
                 R.sync();
+                if (gidx == 0 && rtid == 0) tick(11, tr0);
                 redo = st.ovf != 0u;
                 const uint32_t nc = st.c_n;
                 if (!redo && rtid < w.n_rows) {
@@ -712,6 +723,7 @@ search_sketch_kernel(BatchArgs a) {
                     }
                 }
                 R.sync();
+                if (gidx == 0 && rtid == 0) tick(12, tr0);
                 if (rwarp == 0 && !redo) {
                     const bool keep = lane < nc && st.c_cnts[lane] >= w.min_score; // common.zig:140-145
                     const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
@@ -721,7 +733,8 @@ search_sketch_kernel(BatchArgs a) {
                 }
             }
             if (rtid == 0) st.nset = st.ovf = 0;
-            if (rwarp == 0) asm volatile("bar.arrive %0, 96;" ::"r"(7u + s) : "memory"); // the stage goes back to the producers
+            if (rwarp == 0) // the stage goes back to the producers
+                asm volatile("bar.arrive %0, %1;" ::"r"(kBarStage + s), "r"(32 * (kSkProducerWarps / kSkStages) + 32) : "memory");
             if (rwarp == 0) {
                 if (redo) {
                     // too many candidates for this path: the exact count-table kernels take the query
@@ -737,6 +750,7 @@ search_sketch_kernel(BatchArgs a) {
                 }
                 if (lane == 0 && a.stats && !redo) atomicAdd(&a.stats->sketch_queries, 1ull);
             }
+            if (gidx == 0 && rtid == 0) tick(13, tr0);
             R.sync(); // the group's scratch is reused by its next query
             if (gidx == 0 && rtid == 0) {
                 tick(5, tr0);
@@ -756,7 +770,7 @@ search_sketch_kernel(BatchArgs a) {
         // loops do, and the kernel is issue bound.  Only the TMA completion needs an mbarrier: one counter warp
         // polls it, the other fifteen wait on a named barrier.
         if (it >= 2) // sketch b cleared, records consumed by the resolvers of query it-2
-            asm volatile("bar.sync %0, %1;" ::"r"(13u + b), "r"(kSkCounters + 32) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(kBarSkFree + b), "r"(kSkCounters + 32) : "memory");
         if (warp == 0) {
             if (lane == 0) {
                 mbar_wait(&full[s], (it / kSkStages) & 1, wm);
@@ -764,7 +778,7 @@ search_sketch_kernel(BatchArgs a) {
             }
             __syncwarp();
         }
-        asm volatile("bar.sync 6, %0;" ::"r"(kSkCounters) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(kBarCounters), "r"(kSkCounters) : "memory");
         const uint32_t total4 = meta[s].item.total4;
         const uint32_t thr_m1 = meta[s].item.min_score - 1u; // min_score >= 2 in this class
         const uint4 *st = stage + (size_t)s * kStageU4;
@@ -816,7 +830,7 @@ search_sketch_kernel(BatchArgs a) {
         }
         __syncwarp();
         // my slice of query it is in the sketch
-        asm volatile("bar.arrive %0, %1;" ::"r"(11u + b), "r"(kSkCounters + kSkResolvers) : "memory");
+        asm volatile("bar.arrive %0, %1;" ::"r"(kBarCounted + it % kSkResolverGroups), "r"(kSkCounters + kSkResolvers) : "memory");
         if (warp == 0 && lane == 0) {
             tick(9, tc0);
             if (timed) atomicAdd(&a.stats->dbg[10], 1ull);
@@ -1634,7 +1648,7 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_smem_kernel<15, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for<15, 1024>());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(search_sketch_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
+    e = cudaFuncSetAttribute(search_sketch_kernel<16, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_sketch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kS2SmemBytes);
     return e;
@@ -1665,7 +1679,9 @@ void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms) {
         search_sketch2_kernel<<<2 * n_sms, kS2Threads, kS2SmemBytes, st>>>(a);
         return;
     }
-    search_sketch_kernel<16, 8><<<n_sms, 1024, kSkSmemBytes, st>>>(a); // 16 counter + 8 resolver + 8 producer warps
+    // 16 counter + 2 x 4 resolver + 8 producer warps.  (16 + 3 x 4 + 4 was measured slower: one producer warp per
+    // stage needs 7.6 K cycles to issue a query's 100 bulk copies and becomes the bottleneck.)
+    search_sketch_kernel<16, 2, 8><<<n_sms, 1024, kSkSmemBytes, st>>>(a);
 }
 
 void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms) {
