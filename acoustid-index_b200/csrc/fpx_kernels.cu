@@ -710,16 +710,30 @@ search_sketch_kernel(BatchArgs a) {
                     const uint32_t *row = reinterpret_cast<const uint32_t *>(stage + (size_t)s * kStageU4) + meta[s].row_off[rtid];
                     const uint32_t len = meta[s].row_len[rtid];
                     const uint32_t top = 1u << (31 - __clz(len | 1u));
-                    for (uint32_t c = 0; c < nc; ++c) {
-                        const uint32_t d = st.c_ids[c];
-                        uint32_t lo = 0; // lower bound by halving steps: lo = #elements < d
-                        for (uint32_t step = top; step; step >>= 1) {
-                            const uint32_t probe = lo + step;
-                            if (probe <= len && row[probe - 1] < d) lo = probe;
+                    // four candidates at a time: the same halving steps for all (they depend on the row length only),
+                    // so the four chains of dependent loads overlap
+                    for (uint32_t c = 0; c < nc; c += 4) {
+                        uint32_t d[4], lo[4], m[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            d[j] = st.c_ids[min(c + j, nc - 1)];
+                            lo[j] = 0; // lower bound by halving steps: lo = #elements < d
                         }
-                        uint32_t m = 0;
-                        while (lo + m < len && row[lo + m] == d) ++m; // repeated (hash, id) pairs all count
-                        if (m) atomicAdd(&st.c_cnts[c], m);
+                        for (uint32_t step = top; step; step >>= 1) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t probe = lo[j] + step;
+                                if (probe <= len && row[probe - 1] < d[j]) lo[j] = probe;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            m[j] = 0;
+                            while (lo[j] + m[j] < len && row[lo[j] + m[j]] == d[j]) ++m[j]; // repeated (hash, id) pairs all count
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (m[j] && c + j < nc) atomicAdd(&st.c_cnts[c + j], m[j]);
                     }
                 }
                 R.sync();
