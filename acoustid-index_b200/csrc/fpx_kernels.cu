@@ -544,7 +544,7 @@ search_sketch_kernel(BatchArgs a) {
 
     if (tid == 0) {
         for (int s = 0; s < kSkStages; ++s) {
-            mbar_init(&full[s], kSkProducerWarps / kSkStages);
+            mbar_init(&full[s], kSkProducerWarps); // every producer warp arrives with its share of the bytes
         }
         for (int b = 0; b < 2; ++b) {
             s_nrec[b] = 0;
@@ -559,15 +559,14 @@ search_sketch_kernel(BatchArgs a) {
     __syncthreads();
 
     if (warp >= kSkFirstProducer) {
-        // ===== producers: warp pair `pair` owns stage `pair` and every kSkStages-th query; within the pair
-        // warp `half` issues the even / odd rows.  Each lane holds two row descriptors of its warp's rows.
-        // (kPW = 1: one warp per stage, four descriptors per lane.)
-        constexpr int kPW = kSkProducerWarps / kSkStages, kDesc = 4 / kPW; // kPW * 32 * kDesc = kSketchMaxRows
-        static_assert(kSkProducerWarps == kPW * kSkStages && (kPW == 1 || kPW == 2), "one or two producer warps per stage");
-        const uint32_t p = warp - kSkFirstProducer, pair = p / kPW, half = p % kPW;
+        // ===== producers: ALL producer warps fill one stage at a time, query after query (stage = it % kSkStages);
+        // warp p issues rows p, p + P, p + 2P, ... (lane l holds row P*l + p: one descriptor per lane, four with
+        // P = 8 for a 100-row query).  Issuing a bulk copy costs ~80 cycles of a warp, so spreading a query over
+        // every producer warp fills its stage in ~1 K cycles instead of ~4 K with a warp pair per stage: the stages
+        // turn over faster, and with four stages that is what bounds the kernel (Little's law).
+        constexpr int kP = kSkProducerWarps, kDesc = (kSketchMaxRows + 32 * kP - 1) / (32 * kP);
+        const uint32_t p = warp - kSkFirstProducer;
         const uint4 *docids4 = reinterpret_cast<const uint4 *>(a.snap.docids);
-        const uint32_t s = pair;
-        uint4 *dst = stage + (size_t)s * kStageU4;
         auto item_at = [&](uint32_t it, WorkItem &w) -> bool {
             const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
             if (idx >= count) return false;
@@ -577,20 +576,22 @@ search_sketch_kernel(BatchArgs a) {
         auto rows_of = [&](const WorkItem &w, uint4 (&d)[kDesc]) {
 #pragma unroll
             for (int j = 0; j < kDesc; ++j) {
-                const uint32_t r = (uint32_t)kPW * (lane + 32 * j) + half;
+                const uint32_t r = (uint32_t)kP * (lane + 32 * j) + p;
                 d[j] = r < w.n_rows ? a.rows[w.rows_off + r] : make_uint4(0u, 0u, 0u, 0u);
             }
         };
         WorkItem w{}, w1{};
         uint4 d[kDesc], d1[kDesc];
-        bool have = item_at(pair, w);
+        bool have = item_at(0, w);
         if (have) rows_of(w, d);
-        for (uint32_t it = pair, use = 0; have; it += kSkStages, ++use) {
-            const bool have1 = item_at(it + kSkStages, w1); // my next query: in flight during wait + issue
+        for (uint32_t it = 0; have; ++it) {
+            const uint32_t s = it % kSkStages;
+            uint4 *dst = stage + (size_t)s * kStageU4;
+            const bool have1 = item_at(it + 1, w1); // the next query: in flight during wait + issue
             if (have1) rows_of(w1, d1);
             const long long tp0 = clock64();
-            if (use > 0) // wait until the resolvers released the previous tenant of my stage: my warp(s) + their warp 0
-                asm volatile("bar.sync %0, %1;" ::"r"(kBarStage + s), "r"(32 * kPW + 32) : "memory");
+            if (it >= kSkStages) // wait until the resolvers released the previous tenant of this stage: us + their warp 0
+                asm volatile("bar.sync %0, %1;" ::"r"(kBarStage + s), "r"(32 * kP + 32) : "memory");
             if (p == 0 && lane == 0) tick(0, tp0);
             // the row's place in the stage (d.z) was computed by prepare_kernel
             uint32_t mine = 0;
@@ -600,11 +601,13 @@ search_sketch_kernel(BatchArgs a) {
             for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
 #pragma unroll
             for (int j = 0; j < kDesc; ++j) { // stage directory for the exact recount
-                const uint32_t r = (uint32_t)kPW * (lane + 32 * j) + half;
-                meta[s].row_off[r] = d[j].z * 4u;
-                meta[s].row_len[r] = d[j].y;
+                const uint32_t r = (uint32_t)kP * (lane + 32 * j) + p;
+                if (r < kSketchMaxRows) {
+                    meta[s].row_off[r] = d[j].z * 4u;
+                    meta[s].row_len[r] = d[j].y;
+                }
             }
-            if (half == 0 && lane == 0) meta[s].item = w;
+            if (p == 0 && lane == 0) meta[s].item = w;
             if (a.debug & 8u) mine = 0;
             __syncwarp();
             if (lane == 0) mbar_expect_tx(&full[s], mine * 16u); // expect_tx precedes my copies (release)
@@ -748,7 +751,7 @@ search_sketch_kernel(BatchArgs a) {
             }
             if (rtid == 0) st.nset = st.ovf = 0;
             if (rwarp == 0) // the stage goes back to the producers
-                asm volatile("bar.arrive %0, %1;" ::"r"(kBarStage + s), "r"(32 * (kSkProducerWarps / kSkStages) + 32) : "memory");
+                asm volatile("bar.arrive %0, %1;" ::"r"(kBarStage + s), "r"(32 * kSkProducerWarps + 32) : "memory");
             if (rwarp == 0) {
                 if (redo) {
                     // too many candidates for this path: the exact count-table kernels take the query
@@ -826,7 +829,8 @@ search_sketch_kernel(BatchArgs a) {
                 if ((t[0] | t[1] | t[2] | t[3]) & 0x80008000u) { // some counter in one of the four words is hot
                     // The true match lands here once per matching row.  After its first record its docid is
                     // "known": neutralise it and re-test, so the repeats leave after a dozen instructions
-                    // (a stale s_known only costs a repeated record).
+                    // (a stale s_known only costs a repeated record).  (Reading it together with the granule instead
+                    // was measured slower.)
                     const uint32_t known = s_known[b];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) t[e] = dd[e] == known ? 0u : t[e];
@@ -1664,6 +1668,8 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_sketch_kernel<16, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(search_sketch_kernel<12, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_sketch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kS2SmemBytes);
     return e;
 }
@@ -1695,7 +1701,13 @@ void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms) {
     }
     // 16 counter + 2 x 4 resolver + 8 producer warps.  (16 + 3 x 4 + 4 was measured slower: one producer warp per
     // stage needs 7.6 K cycles to issue a query's 100 bulk copies and becomes the bottleneck.)
-    search_sketch_kernel<16, 2, 8><<<n_sms, 1024, kSkSmemBytes, st>>>(a);
+    // 12 counter + 3 x 4 resolver + 8 producer warps.  Measured on C3 (tools/sweep.py): 16 + 2 x 4 + 8 is 2 % slower
+    // (FPX_DEBUG_ABLATE bit 14), 16 + 3 x 4 + 4 is 9 % slower (four warps cannot issue the copies fast enough).
+    if (a.debug & 0x4000u) {
+        search_sketch_kernel<16, 2, 8><<<n_sms, 1024, kSkSmemBytes, st>>>(a);
+        return;
+    }
+    search_sketch_kernel<12, 3, 8><<<n_sms, 1024, kSkSmemBytes, st>>>(a);
 }
 
 void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms) {
