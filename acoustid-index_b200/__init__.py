@@ -7,7 +7,8 @@ The directory name has a hyphen (it mirrors the reference repo name); import it 
 """
 from . import _ffi, index, synth  # noqa: F401  (multi_gpu is imported on demand: it needs torch.distributed)
 from ._ffi import FpxError, build as build_library, lib  # noqa: F401
-from .index import (Batcher, Context, FileSegment, IndexReader, MemorySegment, SearchOptions, SearchRequest,  # noqa: F401
+from .index import (WIRE_JSON, WIRE_MSGPACK, Batcher, Context, FileSegment, decode_search_request,
+                    encode_search_response, legacy_format_results, legacy_parse_fingerprint, IndexReader, MemorySegment, SearchOptions, SearchRequest,  # noqa: F401
                     SearchResult, Snapshot, SnapshotBuilder, merge_shard_results, multi_index_search,
                     open_index_dir, pack_results_device, parse_manifest, segment_file_bytes, segment_file_name,
                     SegmentFile, swap_snapshot, unpack_results)

@@ -58,6 +58,11 @@ class MemorySegmentDesc(C.Structure):
                 ("n_docs", C.c_uint64)]
 
 
+class WireSearchRequest(C.Structure):
+    _fields_ = [("query", u32p), ("n_terms", C.c_uint64), ("timeout", C.c_uint32), ("limit", C.c_uint32),
+                ("has_min_score", C.c_uint32), ("min_score", C.c_uint32), ("score_pct", C.c_uint32)]
+
+
 class BatcherConfig(C.Structure):
     _fields_ = [("max_batch", C.c_uint32), ("max_wait_us", C.c_uint32)]
 
@@ -107,6 +112,8 @@ EXPORTS = [
     "fpx_segment_write", "fpx_segment_buf_blocks", "fpx_segment_buf_block_index",
     "fpx_segment_buf_num_blocks", "fpx_segment_buf_num_items", "fpx_segment_buf_block_size",
     "fpx_segment_buf_free", "fpx_block_decode",
+    "fpx_wire_decode_search_request", "fpx_wire_encode_search_response", "fpx_legacy_parse_fingerprint",
+    "fpx_legacy_format_results", "fpx_wire_free",
     "fpx_batcher_create", "fpx_batcher_set_snapshot", "fpx_batcher_search", "fpx_batcher_get_stats",
     "fpx_batcher_destroy",
     "fpx_segment_file_parse", "fpx_segment_file_read", "fpx_segment_file_view", "fpx_segment_file_num_items",
@@ -167,6 +174,12 @@ def lib():
     L.fpx_set_chunk_queries.argtypes = [vp, C.c_uint32]
     L.fpx_set_profile.argtypes = [vp, C.c_int]
     L.fpx_pack_results_device.argtypes = [C.c_uint64, C.c_uint32, vp, vp, vp, vp, C.c_uint32, vp]
+    L.fpx_wire_decode_search_request.argtypes = [C.c_uint32, C.c_char_p, C.c_uint64, C.POINTER(WireSearchRequest)]
+    L.fpx_wire_encode_search_response.argtypes = [C.c_uint32, vp, vp, C.c_uint32, C.POINTER(vp), u64p]
+    L.fpx_legacy_parse_fingerprint.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(u32p), u64p]
+    L.fpx_legacy_format_results.argtypes = [vp, vp, C.c_uint32, C.POINTER(vp), u64p]
+    L.fpx_wire_free.argtypes = [vp]
+    L.fpx_wire_free.restype = None
     L.fpx_batcher_create.argtypes = [vp, C.POINTER(BatcherConfig), C.POINTER(vp)]
     L.fpx_batcher_set_snapshot.argtypes = [vp, vp]
     L.fpx_batcher_search.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32, vp, vp, C.c_uint32, u32p]

@@ -387,6 +387,56 @@ class IndexReader:
                                             d_counts, stream))
 
 
+WIRE_JSON, WIRE_MSGPACK = 0, 1
+
+
+def decode_search_request(data: bytes, fmt=WIRE_JSON) -> SearchRequest:
+    """server.handleSearch's decode + sanitize (server.zig:189-194) -> SearchRequest."""
+    r = _ffi.WireSearchRequest()
+    check(lib().fpx_wire_decode_search_request(fmt, data, len(data), C.byref(r)))
+    try:
+        q = [int(r.query[i]) for i in range(r.n_terms)]
+    finally:
+        lib().fpx_wire_free(C.cast(r.query, C.c_void_p))
+    return SearchRequest(q, timeout=r.timeout, limit=r.limit, min_score=r.min_score if r.has_min_score else None,
+                         score_pct=r.score_pct)
+
+
+def encode_search_response(results, fmt=WIRE_JSON) -> bytes:
+    ids = _u32([r[0] for r in results])
+    sc = _u32([r[1] for r in results])
+    out, n = C.c_void_p(), C.c_uint64()
+    check(lib().fpx_wire_encode_search_response(fmt, ids.ctypes.data if len(ids) else None,
+                                                sc.ctypes.data if len(sc) else None, len(ids), C.byref(out), C.byref(n)))
+    try:
+        return C.string_at(out, n.value)
+    finally:
+        lib().fpx_wire_free(out)
+
+
+def legacy_parse_fingerprint(text: str):
+    """legacy.zig:286-296: comma-separated signed decimals -> u32 hashes."""
+    b = text.encode()
+    out, n = _ffi.u32p(), C.c_uint64()
+    check(lib().fpx_legacy_parse_fingerprint(b, len(b), C.byref(out), C.byref(n)))
+    try:
+        return [int(out[i]) for i in range(n.value)]
+    finally:
+        lib().fpx_wire_free(C.cast(out, C.c_void_p))
+
+
+def legacy_format_results(results) -> str:
+    ids = _u32([r[0] for r in results])
+    sc = _u32([r[1] for r in results])
+    out, n = C.c_void_p(), C.c_uint64()
+    check(lib().fpx_legacy_format_results(ids.ctypes.data if len(ids) else None, sc.ctypes.data if len(sc) else None,
+                                          len(ids), C.byref(out), C.byref(n)))
+    try:
+        return C.string_at(out, n.value).decode()
+    finally:
+        lib().fpx_wire_free(out)
+
+
 class Batcher:
     """Request micro-batcher: what a host would put behind MultiIndex.search (MultiIndex.zig:287-330).  search() is
     thread-safe and blocking; concurrent callers are answered by shared GPU batches."""

@@ -231,6 +231,30 @@ fpx_status fpx_batcher_get_stats(fpx_batcher *b, fpx_batcher_stats *out);
 /* Answers what is still queued, then stops the worker.  No fpx_batcher_search may be running or start. */
 void fpx_batcher_destroy(fpx_batcher *b);
 
+/* ---- wire codecs of the search call (for a search-only endpoint without the Zig host) ----
+ * api.SearchRequest / api.SearchResponse (api.zig:14-27, 56-72) as the HTTP server decodes and encodes them
+ * (server.zig:84-142, 189-196: msgpack with one-letter keys, JSON with field names; limit clamped to [1, 100],
+ * timeout to <= 10000) and the legacy line protocol's fingerprint / result formats (legacy.zig:185-210, 286-296).
+ * Malformed input -> FPX_INVALID_ARGUMENT (error.BadRequest).  Buffers handed out are freed with fpx_wire_free. */
+#define FPX_WIRE_JSON 0u
+#define FPX_WIRE_MSGPACK 1u
+typedef struct fpx_wire_search_request {
+    uint32_t *query;       /* n_terms raw terms (fpx_wire_free) */
+    uint64_t n_terms;
+    uint32_t timeout;      /* ms, 0 = none; default 500 */
+    uint32_t limit;        /* default 40 */
+    uint32_t has_min_score, min_score; /* null -> fpx_default_min_score(n_terms) */
+    uint32_t score_pct;    /* default 10 */
+} fpx_wire_search_request;
+fpx_status fpx_wire_decode_search_request(uint32_t format, const uint8_t *data, uint64_t size,
+                                          fpx_wire_search_request *out);
+fpx_status fpx_wire_encode_search_response(uint32_t format, const uint32_t *ids, const uint32_t *scores, uint32_t n,
+                                           uint8_t **out, uint64_t *out_size);
+fpx_status fpx_legacy_parse_fingerprint(const char *text, uint64_t len, uint32_t **out_terms, uint64_t *out_n);
+fpx_status fpx_legacy_format_results(const uint32_t *ids, const uint32_t *scores, uint32_t n, uint8_t **out,
+                                     uint64_t *out_size);
+void fpx_wire_free(void *p);
+
 /* Queries per pipelined H2D / compute / D2H chunk of fpx_search_batch (same as fpx_config.chunk_queries);
  * takes effect for calls that start afterwards. */
 fpx_status fpx_set_chunk_queries(fpx_ctx *ctx, uint32_t chunk_queries);
