@@ -1670,6 +1670,8 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_sketch_kernel<12, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(search_sketch_kernel<14, 3, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_sketch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kS2SmemBytes);
     return e;
 }
@@ -1701,13 +1703,17 @@ void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms) {
     }
     // 16 counter + 2 x 4 resolver + 8 producer warps.  (16 + 3 x 4 + 4 was measured slower: one producer warp per
     // stage needs 7.6 K cycles to issue a query's 100 bulk copies and becomes the bottleneck.)
-    // 12 counter + 3 x 4 resolver + 8 producer warps.  Measured on C3 (tools/sweep.py): 16 + 2 x 4 + 8 is 2 % slower
-    // (FPX_DEBUG_ABLATE bit 14), 16 + 3 x 4 + 4 is 9 % slower (four warps cannot issue the copies fast enough).
+    // 14 counter + 3 x 4 resolver + 6 producer warps.  Measured on C3 (tools/sweep.py, sketch kernel per 100 K queries):
+    // 14/3x4/6 1.284 ms, 12/3x4/8 1.302 ms, 15/3x4/5 1.313 ms, 16/2x4/8 1.329 ms, 16/3x4/4 1.43 ms.
     if (a.debug & 0x4000u) {
         search_sketch_kernel<16, 2, 8><<<n_sms, 1024, kSkSmemBytes, st>>>(a);
         return;
     }
-    search_sketch_kernel<12, 3, 8><<<n_sms, 1024, kSkSmemBytes, st>>>(a);
+    if (a.debug & 0x8000u) {
+        search_sketch_kernel<12, 3, 8><<<n_sms, 1024, kSkSmemBytes, st>>>(a);
+        return;
+    }
+    search_sketch_kernel<14, 3, 6><<<n_sms, 1024, kSkSmemBytes, st>>>(a);
 }
 
 void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms) {

@@ -27,7 +27,7 @@ for w in want:
         i = h.index(w); vals[w] = (v[i], u[i]); lines.append("%-72s %s %s" % (w, v[i], u[i]))
 open(R + "/ncu_sketch_kernel_final_summary.txt", "w").write(
     "ncu --set full --clock-control none --import-source on -k regex:search_sketch_kernel -s 3 -c 1 ; bench.py --workload c3 --steps 1 (10 M x 120, 100 K queries x 100 terms)\n"
-    "kernel: search_sketch_kernel<16,2,8>  grid 148 x 1024 threads, 196 KB dynamic smem, 1 CTA/SM (the default hot kernel at round end)\n\n" + "\n".join(lines) + "\n")
+    "kernel: search_sketch_kernel<14,3,6>  grid 148 x 1024 threads, 196 KB dynamic smem, 1 CTA/SM (the default hot kernel at round end)\n\n" + "\n".join(lines) + "\n")
 mul = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1}
 tr = float(vals['dram__bytes_read.sum'][0]) * mul[vals['dram__bytes_read.sum'][1]] + float(vals['dram__bytes_write.sum'][0]) * mul[vals['dram__bytes_write.sum'][1]]
 json.dump({"kernel": "search_sketch_kernel", "workload": "c3", "dram_bytes_per_launch": tr,
