@@ -94,6 +94,8 @@ struct Workspace {
     } slot[kSlots];
     DevBuf<unsigned long long> wide_tables; // only the (in-order) tail stream touches them
     cudaStream_t tail_stream = nullptr;
+    cudaStream_t d2h_stream = nullptr; // result DMA of chunk c must not hold up the trailing kernels of chunk c+1
+    cudaEvent_t tail_done = nullptr;
     // staging for host batches
     DevBuf<uint32_t> d_terms;
     DevBuf<uint64_t> d_offsets;
@@ -156,6 +158,8 @@ struct Workspace {
         d_offsets.release();
         d_opts.release();
         if (tail_stream) cudaStreamDestroy(tail_stream);
+        if (d2h_stream) cudaStreamDestroy(d2h_stream);
+        if (tail_done) cudaEventDestroy(tail_done);
         if (h_error) cudaFreeHost(h_error);
         if (h_counts) cudaFreeHost(h_counts);
         if (h_pairs) cudaFreeHost(h_pairs);
@@ -229,6 +233,8 @@ fpx_status acquire_workspace(fpx_ctx *ctx, Workspace **out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->copy_fence, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->tail_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->d2h_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->tail_done, cudaEventDisableTiming);
     for (Workspace::Slot &sl : w->slot) {
         if (e == cudaSuccess) e = cudaMalloc(&sl.counters, sizeof(BatchCounters));
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.front_done, cudaEventDisableTiming);
@@ -773,7 +779,7 @@ fpx_status fpx_search_batch(fpx_snapshot *s, uint64_t n_queries, const uint32_t 
     fpx_ctx *ctx = s->ctx;
     FPX_CUDA(cudaSetDevice(ctx->device));
 
-    // Three in-order streams.  The copy stream moves the queries to the device chunk by chunk; the compute stream
+    // In-order streams.  The copy stream moves the queries to the device chunk by chunk; the compute stream
     // runs the big kernels back to back (prepare -> persistent sketch kernel, chunk after chunk); the tail stream
     // runs each chunk's small trailing kernels (exact count-table kernels, result packing) in the gaps.  Chunks
     // alternate between two workspace slots.  The packed results ({count per query, (id, score) pairs back to
@@ -882,21 +888,27 @@ fpx_status fpx_search_batch(fpx_snapshot *s, uint64_t n_queries, const uint32_t 
         rc = enqueue_batch(s, w, sl, st, ts, nq, nt, w->d_terms.p + (t0 - t_first), d_off, t0, w->d_opts.p + q0, k_stride,
                            sl.d_ids.p, sl.d_scores.p, sl.d_counts.p, tracing ? &tr[c].ev[2] : nullptr, (uint32_t)c, no_long_queries);
         if (rc != FPX_OK) break;
+        cudaStream_t rs = ts; // stream the results leave on
+        if (dma_out) {        // DMA on its own stream: the next chunk's trailing kernels need not wait for it
+            rs = w->d2h_stream;
+            cudaEventRecord(w->tail_done, ts);
+            cudaStreamWaitEvent(rs, w->tail_done, 0);
+        }
         {
-            Timed t(ctx, ts, KK_D2H);
+            Timed t(ctx, rs, KK_D2H);
             if (dma_out) {
                 if (k_stride) {
-                    cudaMemcpyAsync(out_ids + q0 * k_stride, sl.d_ids.p, nq * (uint64_t)k_stride * 4, cudaMemcpyDeviceToHost, ts);
-                    cudaMemcpyAsync(out_scores + q0 * k_stride, sl.d_scores.p, nq * (uint64_t)k_stride * 4, cudaMemcpyDeviceToHost, ts);
+                    cudaMemcpyAsync(out_ids + q0 * k_stride, sl.d_ids.p, nq * (uint64_t)k_stride * 4, cudaMemcpyDeviceToHost, rs);
+                    cudaMemcpyAsync(out_scores + q0 * k_stride, sl.d_scores.p, nq * (uint64_t)k_stride * 4, cudaMemcpyDeviceToHost, rs);
                 }
-                cudaMemcpyAsync(out_counts + q0, sl.d_counts.p, nq * 4, cudaMemcpyDeviceToHost, ts);
+                cudaMemcpyAsync(out_counts + q0, sl.d_counts.p, nq * 4, cudaMemcpyDeviceToHost, rs);
             } else {
                 launch_result_pack(sl.d_ids.p, sl.d_scores.p, sl.d_counts.p, sl.d_pack_offsets.p, (uint32_t)nq, k_stride,
-                                   w->h_counts + q0, w->h_pairs + pair_base[c], ts);
+                                   w->h_counts + q0, w->h_pairs + pair_base[c], rs);
             }
         }
-        if (tracing) cudaEventRecord(tr[c].ev[5], ts);
-        cudaEventRecord(w->chunk_done[c], ts);
+        if (tracing) cudaEventRecord(tr[c].ev[5], rs);
+        cudaEventRecord(w->chunk_done[c], rs);
         if (ctx->flags & FPX_FLAG_PROFILE) {
             std::lock_guard<std::mutex> lk(ctx->mu);
             ctx->prof.h2d_bytes += nt * 4 + (nq + 1) * 8 + nq * sizeof(SearchOpts);
@@ -998,6 +1010,7 @@ fpx_status fpx_search_batch(fpx_snapshot *s, uint64_t n_queries, const uint32_t 
         ctx->prof.d2h_bytes += d2h_bytes;
     }
     e = cudaStreamSynchronize(ts);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(w->d2h_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess && rc == FPX_OK) rc = cuda_fail(e, "search batch");
     if (tracing) {
