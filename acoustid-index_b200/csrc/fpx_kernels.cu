@@ -716,27 +716,28 @@ search_sketch_kernel(BatchArgs a) {
                     // four candidates at a time: the same halving steps for all (they depend on the row length only),
                     // so the four chains of dependent loads overlap
                     for (uint32_t c = 0; c < nc; c += 4) {
+                        const uint32_t nj = min(4u, nc - c); // the same for every thread: no divergence, no idle loads
                         uint32_t d[4], lo[4], m[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            d[j] = st.c_ids[min(c + j, nc - 1)];
+                            d[j] = (uint32_t)j < nj ? st.c_ids[c + j] : 0u;
                             lo[j] = 0; // lower bound by halving steps: lo = #elements < d
+                            m[j] = 0;
                         }
                         for (uint32_t step = top; step; step >>= 1) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const uint32_t probe = lo[j] + step;
-                                if (probe <= len && row[probe - 1] < d[j]) lo[j] = probe;
+                                if ((uint32_t)j < nj && probe <= len && row[probe - 1] < d[j]) lo[j] = probe;
                             }
                         }
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            m[j] = 0;
-                            while (lo[j] + m[j] < len && row[lo[j] + m[j]] == d[j]) ++m[j]; // repeated (hash, id) pairs all count
-                        }
+                        for (int j = 0; j < 4; ++j)
+                            if ((uint32_t)j < nj)
+                                while (lo[j] + m[j] < len && row[lo[j] + m[j]] == d[j]) ++m[j]; // repeated (hash, id) pairs all count
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            if (m[j] && c + j < nc) atomicAdd(&st.c_cnts[c + j], m[j]);
+                            if (m[j]) atomicAdd(&st.c_cnts[c + j], m[j]);
                     }
                 }
                 R.sync();
