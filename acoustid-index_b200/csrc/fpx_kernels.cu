@@ -222,36 +222,58 @@ __global__ void __launch_bounds__(kThreads, 5) prepare_kernel(BatchArgs a) {
             e[j] = make_uint4(0, 0, 0, 0);
             if (live[j]) e[j] = __ldg(reinterpret_cast<const uint4 *>(a.snap.table + h[j]));
         }
-        uint32_t n_unique = 0, n_rows = 0, off4_base = 0;
-        unsigned long long postings = 0, total4 = 0;
+        // Linear probing, an empty slot ends the search.  A lane that misses its first slot reads the next
+        // three together: the warp waits for its slowest lane (max displacement over 32 lanes ~ 5 at load 0.5),
+        // so a window of three turns ~5 dependent round trips into ~2.
+        uint32_t cnt = 0, live_n = 0;
+        unsigned long long sz = 0, postings = 0;
+        bool found[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            while (e[j].w != 0u && e[j].x != t[j]) { // linear probing; an empty slot ends the search
-                h[j] = (h[j] + 1) & a.snap.table_mask;
-                e[j] = __ldg(reinterpret_cast<const uint4 *>(a.snap.table + h[j]));
+            while (e[j].w != 0u && e[j].x != t[j]) {
+                const uint4 e1 = __ldg(reinterpret_cast<const uint4 *>(a.snap.table + ((h[j] + 1) & a.snap.table_mask)));
+                const uint4 e2 = __ldg(reinterpret_cast<const uint4 *>(a.snap.table + ((h[j] + 2) & a.snap.table_mask)));
+                const uint4 e3 = __ldg(reinterpret_cast<const uint4 *>(a.snap.table + ((h[j] + 3) & a.snap.table_mask)));
+                h[j] = (h[j] + 3) & a.snap.table_mask;
+                e[j] = (e1.w == 0u || e1.x == t[j]) ? e1 : (e2.w == 0u || e2.x == t[j]) ? e2 : e3;
             }
-            const bool found = live[j] && e[j].w != 0u;
-            const uint32_t um = __ballot_sync(0xFFFFFFFFu, live[j]);
-            const uint32_t fm = __ballot_sync(0xFFFFFFFFu, found);
-            n_unique += __popc(um);
-            // exclusive prefix of the padded row sizes in compaction order = the row's place in a stage
-            const uint32_t my4 = found ? (e[j].y + 3) >> 2 : 0u;
-            uint32_t incl = my4;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= (uint32_t)o) incl += y;
-            }
-            if (found) {
-                a.rows[o0 + n_rows + __popc(fm & lt_mask)] = make_uint4(e[j].z, e[j].y, off4_base + incl - my4, 0u);
+            found[j] = live[j] && e[j].w != 0u;
+            live_n += live[j] ? 1u : 0u;
+            if (found[j]) {
+                cnt += 1;
+                sz += (e[j].y + 3) >> 2;
                 postings += e[j].y;
             }
-            off4_base += __shfl_sync(0xFFFFFFFFu, incl, 31);
-            n_rows += __popc(fm);
         }
+        // One warp scan for both prefixes: rows are laid out lane-major (lane 0's terms, then lane 1's, ...);
+        // a row's place in a stage is the exclusive prefix of the padded row sizes in that order.
+        unsigned long long incl = ((unsigned long long)cnt << 56) | sz; // <= 128 rows; sz < 2^34
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) postings += __shfl_xor_sync(0xFFFFFFFFu, postings, off);
-        total4 = off4_base;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += y;
+        }
+        const unsigned long long tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const uint32_t n_rows = (uint32_t)(tot >> 56);
+        const unsigned long long total4 = tot & 0x00FFFFFFFFFFFFFFull;
+        {
+            unsigned long long excl = incl - (((unsigned long long)cnt << 56) | sz);
+            uint32_t r = (uint32_t)(excl >> 56);
+            unsigned long long off4 = excl & 0x00FFFFFFFFFFFFFFull;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (found[j]) {
+                    a.rows[o0 + r] = make_uint4(e[j].z, e[j].y, (uint32_t)off4, 0u);
+                    r += 1;
+                    off4 += (e[j].y + 3) >> 2;
+                }
+        }
+        const uint32_t n_unique = __reduce_add_sync(0xFFFFFFFFu, live_n);
+        {   // 64-bit sum in two 32-bit warp reductions (per-lane postings < 2^34)
+            const uint32_t lo = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)(postings & 0xFFFFFFull));
+            const uint32_t hi = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)(postings >> 24));
+            postings = ((unsigned long long)hi << 24) + lo;
+        }
         // every lane computes the (identical) work item; lane n_parked keeps it
         WorkItem w;
         const uint32_t cls = make_item(a, q, (uint32_t)o0, n_rows, postings, total4, w);
