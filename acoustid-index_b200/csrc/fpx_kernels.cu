@@ -88,8 +88,8 @@ __device__ uint32_t make_item(const BatchArgs &a, uint32_t q, uint32_t rows_off,
     // The sketch path needs min_score >= 2 (it only recounts docids whose sketch counter reaches
     // min_score) and the query must fit one 32 KB stage.  With a low floor and many postings nearly every
     // counter is "hot" and the recount list would overflow, so those go to the exact count-table path.
-    bool sketch_ok = a.use_sketch && o.min_score >= 2 && total4 <= kStageU4 && k_eff <= kFastKbuf &&
-                     n_rows <= kSketchMaxRows;
+    bool sketch_ok = a.use_sketch && o.min_score >= 2 && o.min_score <= 128 && total4 <= kStageU4 &&
+                     k_eff <= kFastKbuf && n_rows <= kSketchMaxRows;
     // expected records = postings that find their counter already at min_score-1 (Poisson, 16384 counters)
     if (o.min_score == 2 && postings > 1500) sketch_ok = false;
     if (o.min_score == 3 && postings > 4500) sketch_ok = false;
@@ -824,32 +824,33 @@ search_sketch_kernel(BatchArgs a) {
         const uint4 *st = stage + (size_t)s * kStageU4;
         unsigned char *sketch_b = sketch_base + (size_t)b * kSketchWords * 4;
         uint32_t *rec = rec_base + b * kRecCap;
-        // "either 16-bit half >= thr_m1" in two ALU ops: add (0x8000 - thr_m1) to both halves, test bit 15
-        // of each (counts stay below 8192, so nothing carries across).  A min_score above 32768 can never be
-        // reached by <= 8192 postings: bias 0 then never fires.
-        const uint32_t bias = thr_m1 < 0x8000u ? (0x8000u - thr_m1) * 0x10001u : 0u;
+        // "some byte >= thr_m1" in two ALU ops: add (0x80 - thr_m1) to all four bytes, test bit 7 of each.
+        // Nothing carries across bytes while every counter of the word is <= 128; the first add that finds a
+        // counter at 128 necessarily takes the hot branch below and hands the query to the exact path.
+        const uint32_t bias = (0x80u - thr_m1) * 0x01010101u; // 2 <= min_score <= 128 in this class
 
-        // count sketch, two 16-bit counters per word: hash bits 30..18 pick the word, the sign bit the half.
-        // All four adds of a 16-byte granule are issued before any result is used.  Row padding is made of
-        // unused docids spread over many values, so it needs no test here: it is counted like anything else,
-        // can only make a counter too high, and an exact recount gives it score 0.
+        // count sketch, four 8-bit counters per word (32768 counters): hash bits 29..17 pick the word, bits
+        // 31..30 the byte.  All four adds of a 16-byte granule are issued before any result is used.  Row padding
+        // is made of unused docids spread over many values, so it needs no test here: it is counted like
+        // anything else, can only make a counter too high, and an exact recount gives it score 0.
         if (!(a.debug & 1u)) {
 #pragma unroll 2
             for (uint32_t i = tid; i < total4; i += kSkCounters) {
                 const uint4 v = st[i];
                 const uint32_t dd[4] = {v.x, v.y, v.z, v.w};
-                uint32_t oo[4];
-                int hv[4];
+                uint32_t oo[4], sh[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    hv[e] = (int)(dd[e] * kMult);
-                    oo[e] = atomicAdd(reinterpret_cast<uint32_t *>(sketch_b + (((uint32_t)hv[e] >> 16) & 0x7FFCu)),
-                                      hv[e] < 0 ? 0x10000u : 1u);
+                    const uint32_t hv = dd[e] * kMult;
+                    sh[e] = (hv >> 27) & 0x18u;
+                    oo[e] = atomicAdd(reinterpret_cast<uint32_t *>(sketch_b + ((hv >> 15) & 0x7FFCu)), 1u << sh[e]);
                 }
                 uint32_t t[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) t[e] = oo[e] + bias;
-                if ((t[0] | t[1] | t[2] | t[3]) & 0x80008000u) { // some counter in one of the four words is hot
+                if ((t[0] | t[1] | t[2] | t[3]) & 0x80808080u) { // some counter in one of the four words is hot
+                    // a counter at 128: past this the byte tests can carry and the counter itself can wrap
+                    if ((oo[0] | oo[1] | oo[2] | oo[3]) & 0x80808080u) atomicAdd(&s_nrec[b], kRecCap + 1u);
                     // The true match lands here once per matching row.  After its first record its docid is
                     // "known": neutralise it and re-test, so the repeats leave after a dozen instructions
                     // (a stale s_known only costs a repeated record).  (Reading it together with the granule instead
@@ -857,10 +858,10 @@ search_sketch_kernel(BatchArgs a) {
                     const uint32_t known = s_known[b];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) t[e] = dd[e] == known ? 0u : t[e];
-                    if ((t[0] | t[1] | t[2] | t[3]) & 0x80008000u) {
+                    if ((t[0] | t[1] | t[2] | t[3]) & 0x80808080u) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
-                            if (t[e] & (hv[e] < 0 ? 0x80000000u : 0x8000u)) { // this posting's own counter
+                            if (t[e] & (0x80u << sh[e])) { // this posting's own counter
                                 const uint32_t p = atomicAdd(&s_nrec[b], 1u);
                                 if (p < kRecCap) rec[p] = dd[e];
                                 s_known[b] = dd[e];

@@ -172,6 +172,29 @@ def test_count_overflow_and_duplicates_fall_back_exactly(ctx):
         snap.release()
 
 
+def test_sketch_counter_saturation_hands_over_exactly(ctx):
+    """The sketch kernel counts in 8-bit counters.  A docid that arrives more than 128 times (here: every hash
+    stored twice, 100 query terms -> 200 arrivals; and three docs of 60 arrivals that may share nothing) must
+    send the query to the exact path, with the reference's scores; min_score 128 / 129 sit on the class limit."""
+    ix = OracleIndex()
+    hs = list(range(5000, 5100))
+    ch = [("insert", 1, hs + hs), ("insert", 2, hs[:60]), ("insert", 3, hs[40:]), ("insert", 4, hs[::2] + hs[::2])]
+    ch += [("insert", 100 + i, [hs[i % 100], 9000 + i]) for i in range(400)]
+    ix.update(ch)
+    ix.checkpoint()
+    snap = _snapshot_of(ctx, ix)
+    reader = pkg.IndexReader(snap)
+    queries = [hs, hs[:70], hs[30:], hs + [9000 + i for i in range(20)]]
+    terms, offs = flat_queries(queries)
+    ctx.profile_reset()
+    for opt in ((40, 5, 10), (40, 2, 0), (40, 100, 0), (40, 128, 0), (40, 129, 0), (40, 200, 0), (40, 201, 0)):
+        opts = np.tile(np.array(opt, dtype=np.uint32), (len(queries), 1))
+        _compare_batch(reader, ix, terms, offs, opts, 40)
+    prof = ctx.profile()
+    assert prof["overflow_requeues"] >= 1, prof
+    snap.release()
+
+
 def test_long_queries(ctx):
     rng = np.random.default_rng(3)
     ix, _ = _random_index(rng, rounds=6, vocab=20000, hot=(7,))
