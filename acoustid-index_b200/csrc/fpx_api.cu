@@ -372,6 +372,8 @@ fpx_status commit_gpu_built(fpx_snapshot_builder *b, fpx_snapshot **out) {
         launch_build_table(s->d_table, log2cap, csr.d_terms, csr.d_row_len, csr.d_row_start4, nt, nullptr);
         e = cudaDeviceSynchronize();
     }
+    if (e == cudaSuccess && nt)
+        e = reorder_rows_by_key(&csr.d_docids, csr.total4 * 4, csr.d_row_len, csr.d_row_start4, csr.h_row_start4.data(), nt);
     if (csr.d_terms) cudaFree(csr.d_terms);
     if (csr.d_row_len) cudaFree(csr.d_row_len);
     if (csr.d_row_start4) cudaFree(csr.d_row_start4);
@@ -612,6 +614,8 @@ fpx_status fpx_snapshot_commit(fpx_snapshot_builder *b, fpx_snapshot **out) {
             launch_build_table(s->d_table, log2cap, d_t, d_l, d_s4, nt, nullptr);
             e = cudaDeviceSynchronize();
         }
+        if (e == cudaSuccess)
+            e = reorder_rows_by_key(&s->d_docids, c->docids.size(), d_l, d_s4, c->row_start4.data(), nt);
     }
     if (d_t) cudaFree(d_t);
     if (d_l) cudaFree(d_l);
@@ -696,6 +700,8 @@ fpx_status fpx_snapshot_read_row(const fpx_snapshot *s, uint32_t term, uint32_t 
     if (len > capacity || (len && !out_docids)) return set_error(FPX_INVALID_ARGUMENT, "row does not fit the buffer");
     FPX_CUDA(cudaSetDevice(s->ctx->device));
     FPX_CUDA(cudaMemcpy(out_docids, s->d_docids + (size_t)s->h_row_start4[g] * 4, len * 4, cudaMemcpyDeviceToHost));
+    // in HBM the row is ordered by row_key (fpx_kernels.cuh); callers get it ascending, as the reference keeps it
+    std::sort(out_docids, out_docids + len);
     return FPX_OK;
 }
 

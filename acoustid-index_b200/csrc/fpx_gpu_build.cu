@@ -16,6 +16,7 @@
 // CUB is library code used for the non-hot build path only.  The result is identical to the host compiler's
 // (tests/test_gpu_parity.py compares rows and runs the whole parity suite on GPU-built snapshots).
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
 
 #include <algorithm>
@@ -25,6 +26,7 @@
 
 #include "fpx_codec.h"
 #include "fpx_gpu_build.h"
+#include "fpx_kernels.cuh"
 
 namespace fpx {
 
@@ -688,6 +690,94 @@ bool GpuSnapshotBuilder::build(GpuCsr &out) {
         GB_CUDA(cudaMemcpy(out.h_row_start4.data(), out.d_row_start4, n_rows * 4, cudaMemcpyDeviceToHost));
     }
     return true;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// rows in row_key order (fpx_kernels.cuh): docid -> key in place, segmented sort, key -> docid
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+template <bool INVERSE> __global__ void row_key_kernel(uint32_t *v, unsigned long long n) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        v[i] = INVERSE ? row_key_inv(v[i]) : row_key(v[i]);
+}
+
+struct RowBegin {
+    const uint32_t *start4;
+    unsigned long long base_word;
+    __host__ __device__ int operator()(unsigned long long r) const { return (int)((unsigned long long)start4[r] * 4ull - base_word); }
+};
+struct RowEnd {
+    const uint32_t *start4, *len;
+    unsigned long long base_word;
+    __host__ __device__ int operator()(unsigned long long r) const {
+        return (int)((unsigned long long)start4[r] * 4ull - base_word + len[r]);
+    }
+};
+
+} // namespace
+
+cudaError_t reorder_rows_by_key(uint32_t **d_docids, uint64_t n_words, const uint32_t *d_row_len,
+                                const uint32_t *d_row_start4, const uint32_t *h_row_start4, uint64_t n_rows) {
+    if (n_rows == 0 || n_words == 0) return cudaSuccess;
+    uint32_t *in = *d_docids, *out = nullptr;
+    cudaError_t e = cudaMalloc(&out, n_words * sizeof(uint32_t));
+    if (e != cudaSuccess) return e;
+    row_key_kernel<false><<<148 * 8, 256>>>(in, n_words);
+    // the sort writes the segments only: padding (and anything between rows) is carried over by a plain copy
+    e = cudaMemcpy(out, in, n_words * sizeof(uint32_t), cudaMemcpyDeviceToDevice);
+    void *tmp = nullptr;
+    size_t tmp_cap = 0;
+    constexpr uint64_t kMaxPiece = 1ull << 30; // words per cub call (its item count is an int)
+    uint64_t r0 = 0;
+    while (e == cudaSuccess && r0 < n_rows) {
+        const uint64_t base_word = (uint64_t)h_row_start4[r0] * 4;
+        // last row r1-1 such that the piece [base_word, start of row r1) stays below kMaxPiece; a single longer row
+        // (more than 2^30 postings) cannot be sorted in one call
+        uint64_t lo = r0 + 1, hi = n_rows;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi + 1) / 2;
+            if ((uint64_t)h_row_start4[mid - 1] * 4 - base_word < kMaxPiece) lo = mid; else hi = mid - 1;
+        }
+        const uint64_t r1 = lo;
+        const uint64_t end_word = r1 < n_rows ? (uint64_t)h_row_start4[r1] * 4 : n_words;
+        if (end_word - base_word >= (1ull << 31)) {
+            e = cudaErrorInvalidValue;
+            break;
+        }
+        auto begins = thrust::make_transform_iterator(thrust::counting_iterator<unsigned long long>(r0),
+                                                      RowBegin{d_row_start4, base_word});
+        auto ends = thrust::make_transform_iterator(thrust::counting_iterator<unsigned long long>(r0),
+                                                    RowEnd{d_row_start4, d_row_len, base_word});
+        size_t need = 0;
+        e = cub::DeviceSegmentedSort::SortKeys(nullptr, need, in + base_word, out + base_word, (int)(end_word - base_word),
+                                               (int)(r1 - r0), begins, ends);
+        if (e != cudaSuccess) break;
+        if (need > tmp_cap) {
+            if (tmp) cudaFree(tmp);
+            tmp = nullptr;
+            e = cudaMalloc(&tmp, need);
+            if (e != cudaSuccess) break;
+            tmp_cap = need;
+        }
+        e = cub::DeviceSegmentedSort::SortKeys(tmp, need, in + base_word, out + base_word, (int)(end_word - base_word),
+                                               (int)(r1 - r0), begins, ends);
+        r0 = r1;
+    }
+    if (e == cudaSuccess) {
+        row_key_kernel<true><<<148 * 8, 256>>>(out, n_words);
+        e = cudaDeviceSynchronize();
+    }
+    if (tmp) cudaFree(tmp);
+    if (e != cudaSuccess) {
+        cudaFree(out);
+        return e;
+    }
+    cudaFree(in);
+    *d_docids = out;
+    return cudaSuccess;
 }
 
 } // namespace fpx

@@ -18,6 +18,13 @@ struct GpuCsr { // what fpx_snapshot_commit needs to finish a snapshot
     std::vector<uint32_t> h_terms, h_row_len, h_row_start4; // host copy of the directory (ascending terms)
 };
 
+// Last step of every snapshot build (device-built or uploaded from the host compiler): re-order each row of the
+// padded CSR ascending by row_key(docid) (fpx_kernels.cuh).  *d_docids is replaced by a new allocation of n_words
+// uint32 (the old one is freed).  h_row_start4 is the host copy of d_row_start4 (used to cut the work into pieces
+// of < 2^31 words).  Padding keeps its place at the end of each row.
+cudaError_t reorder_rows_by_key(uint32_t **d_docids, uint64_t n_words, const uint32_t *d_row_len,
+                                const uint32_t *d_row_start4, const uint32_t *h_row_start4, uint64_t n_rows);
+
 class GpuSnapshotBuilder {
   public:
     GpuSnapshotBuilder();

@@ -35,6 +35,7 @@ constexpr uint32_t inv32(uint32_t a) {
 }
 constexpr uint32_t kMultInv = inv32(kMult);
 static_assert(kMult * kMultInv == 1u, "modular inverse");
+static_assert(kMult == kRowMult, "rows are ordered by the hash the sketch counts with");
 
 constexpr uint32_t FPX_UNSUPPORTED_CODE = 7;
 constexpr int kThreads = 256;
@@ -502,7 +503,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 //                         docid as a candidate.  A warp that finishes its slice arrives on `counted` and
 //                         moves straight on to the next query.
 //   resolvers (2 x 4 warps, alternating queries)  clear the sketch, de-duplicate the few candidates, count
-//                         each exactly by binary search in the staged rows (sorted by docid), rank, apply the
+//                         each exactly by binary search in the staged rows (sorted by row_key(docid)), rank, apply the
 //                         reference's cutoffs, write the results, hand the stage back.
 // Why this is exact: a counter holds the sum of the true counts of all docids hashing to it and only grows
 // by one per posting.  If doc d has c >= min_score postings in the query, at most min_score-1 of them can
@@ -739,18 +740,19 @@ search_sketch_kernel(BatchArgs a) {
                     // so the four chains of dependent loads overlap
                     for (uint32_t c = 0; c < nc; c += 4) {
                         const uint32_t nj = min(4u, nc - c); // the same for every thread: no divergence, no idle loads
-                        uint32_t d[4], lo[4], m[4];
+                        uint32_t d[4], dk[4], lo[4], m[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             d[j] = (uint32_t)j < nj ? st.c_ids[c + j] : 0u;
-                            lo[j] = 0; // lower bound by halving steps: lo = #elements < d
+                            dk[j] = row_key(d[j]); // rows are ascending by row_key (fpx_kernels.cuh)
+                            lo[j] = 0; // lower bound by halving steps: lo = #elements before d
                             m[j] = 0;
                         }
                         for (uint32_t step = top; step; step >>= 1) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const uint32_t probe = lo[j] + step;
-                                if ((uint32_t)j < nj && probe <= len && row[probe - 1] < d[j]) lo[j] = probe;
+                                if ((uint32_t)j < nj && probe <= len && row_key(row[probe - 1]) < dk[j]) lo[j] = probe;
                             }
                         }
 #pragma unroll

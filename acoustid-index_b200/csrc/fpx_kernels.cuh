@@ -23,6 +23,25 @@ struct SnapshotDev {
     uint32_t pad_spread; // 1: pad_id and all row padding are larger than every live docid
 };
 
+// Order of the docids inside a row in HBM: ascending row_key.  d -> d * kRowMult is the hash the sketch kernel
+// counts with (word = bits 29..17, so the shared-memory bank is bits 21..17); the rotation puts the bank bits on
+// top.  A warp of counter threads takes 32 consecutive 16-byte granules, i.e. every fourth posting of ~1.8 rows:
+// in this order their banks sweep 0..31 once per row instead of being random, which cuts the bank conflicts of
+// the shared atomics from ~3.5 to ~2.6 wavefronts per instruction.  It is a bijection, so equal docids stay
+// adjacent and a row can still be searched (compare keys instead of docids).
+constexpr uint32_t kRowMult = 0x9E3779B1u;
+constexpr uint32_t row_inv32(uint32_t a) {
+    uint32_t x = a;
+    for (int i = 0; i < 5; ++i) x *= 2u - a * x;
+    return x;
+}
+constexpr uint32_t kRowMultInv = row_inv32(kRowMult);
+__host__ __device__ __forceinline__ uint32_t row_key(uint32_t d) {
+    const uint32_t h = d * kRowMult;
+    return (h << 10) | (h >> 22);
+}
+__host__ __device__ __forceinline__ uint32_t row_key_inv(uint32_t k) { return ((k >> 10) | (k << 22)) * kRowMultInv; }
+
 struct SearchOpts { // == fpx_search_opts
     uint32_t max_results, min_score, min_score_pct;
 };
