@@ -730,11 +730,14 @@ search_sketch_kernel(BatchArgs a) {
                 if (gidx == 0 && rtid == 0) tick(11, tr0);
                 redo = st.ovf != 0u;
                 const uint32_t nc = st.c_n;
-                if (!redo && rtid < w.n_rows) {
+                if (!redo && nc != 0u) {
                     // exact recount: every (candidate, row) pair is an equal-range search in a sorted row;
-                    // thread rtid owns row rtid (a query has at most 128 rows here)
-                    const uint32_t *row = reinterpret_cast<const uint32_t *>(stage + (size_t)s * kStageU4) + meta[s].row_off[rtid];
-                    const uint32_t len = meta[s].row_len[rtid];
+                    // thread rtid owns row rtid (a query has at most 128 rows here; a thread without a row searches
+                    // an empty one, so that whole warps reach the reductions below)
+                    const bool has_row = rtid < w.n_rows;
+                    const uint32_t *row = reinterpret_cast<const uint32_t *>(stage + (size_t)s * kStageU4) +
+                                          (has_row ? meta[s].row_off[rtid] : 0u);
+                    const uint32_t len = has_row ? meta[s].row_len[rtid] : 0u;
                     const uint32_t top = 1u << (31 - __clz(len | 1u));
                     // four candidates at a time: the same halving steps for all (they depend on the row length only),
                     // so the four chains of dependent loads overlap
@@ -759,9 +762,14 @@ search_sketch_kernel(BatchArgs a) {
                         for (int j = 0; j < 4; ++j)
                             if ((uint32_t)j < nj)
                                 while (lo[j] + m[j] < len && row[lo[j] + m[j]] == d[j]) ++m[j]; // repeated (hash, id) pairs all count
+                        // the true match is found in most rows: one add per warp, not one per row (adds to one
+                        // address are served one after the other)
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            if (m[j]) atomicAdd(&st.c_cnts[c + j], m[j]);
+                            if ((uint32_t)j < nj) {
+                                const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, m[j]);
+                                if (lane == 0 && tot) atomicAdd(&st.c_cnts[c + j], tot);
+                            }
                     }
                 }
                 R.sync();
