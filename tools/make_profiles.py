@@ -33,7 +33,28 @@ tr = float(vals['dram__bytes_read.sum'][0]) * mul[vals['dram__bytes_read.sum'][1
 json.dump({"kernel": "search_sketch_kernel", "workload": "c3", "dram_bytes_per_launch": tr,
            "source": "profiles/r01/ncu_sketch_kernel_final_summary.txt (ncu --set full, 100 K-query launch)"}, open("profiles/traffic_c3.json", "w"))
 top = subprocess.run([sys.executable, "tools/ncu_lines.py", "gpurun_out/prof_final.ncu-rep", "30"], capture_output=True, text=True).stdout
-open(R + "/ncu_sketch_kernel_final_top_lines.txt", "w").write(top)
+# per-role budget: the line ranges are located in the source, so they follow the code
+src = open("acoustid-index_b200/csrc/fpx_kernels.cu").read().split("\n")
+def line_of(needle, start=0):
+    for i in range(start, len(src)):
+        if needle in src[i]:
+            return i + 1
+    raise SystemExit("marker not found: " + needle)
+k0 = line_of("search_sketch_kernel(BatchArgs a) {")
+lp, lr = line_of("if (warp >= kSkFirstProducer) {", k0), line_of("if (warp >= kSkFirstResolver) {", k0)
+lc, ll, le = line_of("// ===== counters", k0), line_of("if (!(a.debug & 1u)) {", k0), line_of("struct S2Shared", k0)
+lh, lm = line_of("// ranking helpers"), line_of("// mbarrier / TMA bulk-copy primitives")
+regions = ["init:%d-%d" % (k0, lp - 1), "producer:%d-%d" % (lp, lr - 1), "resolver:%d-%d" % (lr, lc - 1),
+           "counter_wait:%d-%d" % (lc, ll - 1), "counter_loop:%d-%d" % (ll, le - 1), "helpers_rank:%d-%d" % (lh, lm - 1),
+           "mbar_fns:%d-%d" % (lm, k0 - 1)]
+reg = subprocess.run([sys.executable, "tools/ncu_regions.py", "gpurun_out/prof_final.ncu-rep"] + regions, capture_output=True, text=True).stdout
+smem = subprocess.run([sys.executable, "tools/ncu_smem_lines.py", "gpurun_out/prof_final.ncu-rep", "12"], capture_output=True, text=True).stdout
+open(R + "/ncu_sketch_kernel_final_top_lines.txt", "w").write(
+    top + "\nper role (source line ranges " + " ".join(regions) + "):\n" + reg +
+    "\nshared-memory wavefronts per source line (source-page attribution; inlined atomics appear on two lines):\n" + smem)
+for n in (2, 4, 8):
+    if os.path.exists("gpurun_out/bench_%dgpu.json" % n):
+        shutil.copy("gpurun_out/bench_%dgpu.json" % n, R + "/bench_c3_%dgpu.json" % n)
 for a, b in (("bench_c3.json", "bench_c3_final.json"), ("bench_c3_reference.json", "bench_c3_reference_arm.json"), ("bench_c2.json", "bench_c2_final.json"),
              ("bench_c5.json", "bench_c5_final.json"), ("gpu.txt", "gpu_box.txt"), ("pytest_gpu.log", "pytest_gpu.log")):
     shutil.copy("gpurun_out/" + a, R + "/" + b)
