@@ -342,7 +342,7 @@ def main():
     path_bytes = 20.0 * rows + 4.0 * postings + 8.0 * results          # SURVEY.md §8d per-query formula
     sketch_share = prof["sketch_queries"] / max(1, prof["queries"])
     if sketch_share >= 0.5:   # the TMA/sketch kernel answers (nearly) all queries of this workload
-        kernel_name = "search_sketch_kernel (TMA gather + u16 count sketch + exact recount + top-k)"
+        kernel_name = "search_sketch_kernel (TMA gather + u8 count sketch + exact recount + top-k)"
         search_ms = prof["sketch_ms"] / steps
         search_bytes *= sketch_share
     else:
