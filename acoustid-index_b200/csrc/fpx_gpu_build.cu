@@ -135,8 +135,11 @@ decode_blocks_kernel(const uint8_t *blocks, uint32_t block_size, unsigned long l
         bool ok = n > 0 && n <= max_items && kBlockHeaderBytes + doff <= block_size;
         if (ok) ok = decode_column<false>(blk, kBlockHeaderBytes, n, block_size, hs, lane);
         if (ok) ok = decode_column<true>(blk, kBlockHeaderBytes + doff, n, block_size, ds, lane);
-        if (!ok) {
-            if (lane == 0) ctr->error = 1;
+        if (!ok) { // reported by the host after the pass; the kernels that follow see an empty block
+            if (lane == 0) {
+                ctr->error = 1;
+                meta[b] = BlockMeta{};
+            }
             __syncwarp();
             continue;
         }
@@ -499,6 +502,7 @@ bool GpuSnapshotBuilder::build(GpuCsr &out) {
             GB_CUDA(counts.alloc(nb));
             GB_CUDA(blk_off.alloc(nb + 1));
             GB_CUDA(meta.alloc(nb));
+            GB_CUDA(cudaMemset(meta.p, 0, std::max<uint64_t>(nb, 1) * sizeof(BlockMeta)));
             GB_CUDA(st.alloc(nb));
             if (nb) {
                 block_counts_kernel<<<(unsigned)((nb + 255) / 256), 256>>>(s.d_blocks, s.block_size, nb, counts.p, ctr.p);
