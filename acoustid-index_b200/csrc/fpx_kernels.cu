@@ -364,13 +364,22 @@ __device__ __forceinline__ unsigned long long rank_key(uint32_t score, uint32_t 
     return ((unsigned long long)(0xFFFFFFFFu - score) << 32) | id;
 }
 
+// Named barriers (bar.sync / bar.arrive are the .aligned forms: every thread of the warp has to execute them
+// together, so re-converge first; compute-sanitizer's synccheck checks exactly this).
+__device__ __forceinline__ void named_sync(uint32_t id, uint32_t n_threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+__device__ __forceinline__ void named_arrive(uint32_t id, uint32_t n_threads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+
 struct Group {
     uint32_t tid, size, bar; // thread index in the group, group size (multiple of 32), named barrier id
     __device__ __forceinline__ void sync() const {
         if (size == 32u)
             __syncwarp(); // a single warp needs no barrier resource
         else
-            asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(size) : "memory");
+            named_sync(bar, size);
     }
 };
 
@@ -614,7 +623,7 @@ search_sketch_kernel(BatchArgs a) {
             if (have1) rows_of(w1, d1);
             const long long tp0 = clock64();
             if (it >= kSkStages) // wait until the resolvers released the previous tenant of this stage: us + their warp 0
-                asm volatile("bar.sync %0, %1;" ::"r"(kBarStage + s), "r"(32 * kP + 32) : "memory");
+                named_sync(kBarStage + s, 32 * kP + 32);
             if (p == 0 && lane == 0) tick(0, tp0);
             // the row's place in the stage (d.z) was computed by prepare_kernel
             uint32_t mine = 0;
@@ -668,7 +677,7 @@ search_sketch_kernel(BatchArgs a) {
             const uint32_t *rec = rec_base + b * kRecCap;
             const long long tr0 = clock64();
             // all counter warps are done with query it (they arrive, this group waits)
-            asm volatile("bar.sync %0, %1;" ::"r"(kBarCounted + gidx), "r"(kSkCounters + kSkResolvers) : "memory");
+            named_sync(kBarCounted + gidx, kSkCounters + kSkResolvers);
             if (gidx == 0 && rtid == 0) tick(3, tr0);
             const WorkItem w = meta[s].item;
             const uint32_t nrec = (a.debug & 2u) ? 0u : s_nrec[b];
@@ -705,7 +714,7 @@ search_sketch_kernel(BatchArgs a) {
                 s_known[b] = pad;
                 if (gidx == 0) tick(4, tr0);
             }
-            if (rwarp == 0) asm volatile("bar.arrive %0, %1;" ::"r"(kBarSkFree + b), "r"(kSkCounters + 32) : "memory");
+            if (rwarp == 0) named_arrive(kBarSkFree + b, kSkCounters + 32);
             uint32_t n = 0;
             bool redo = false;
             if (nrec != 0u) {
@@ -784,7 +793,7 @@ search_sketch_kernel(BatchArgs a) {
             }
             if (rtid == 0) st.nset = st.ovf = 0;
             if (rwarp == 0) // the stage goes back to the producers
-                asm volatile("bar.arrive %0, %1;" ::"r"(kBarStage + s), "r"(32 * kSkProducerWarps + 32) : "memory");
+                named_arrive(kBarStage + s, 32 * kSkProducerWarps + 32);
             if (rwarp == 0) {
                 if (redo) {
                     // too many candidates for this path: the exact count-table kernels take the query
@@ -820,7 +829,7 @@ search_sketch_kernel(BatchArgs a) {
         // loops do, and the kernel is issue bound.  Only the TMA completion needs an mbarrier: one counter warp
         // polls it, the other fifteen wait on a named barrier.
         if (it >= 2) // sketch b cleared, records consumed by the resolvers of query it-2
-            asm volatile("bar.sync %0, %1;" ::"r"(kBarSkFree + b), "r"(kSkCounters + 32) : "memory");
+            named_sync(kBarSkFree + b, kSkCounters + 32);
         if (warp == 0) {
             if (lane == 0) {
                 mbar_wait(&full[s], (it / kSkStages) & 1, wm);
@@ -828,7 +837,7 @@ search_sketch_kernel(BatchArgs a) {
             }
             __syncwarp();
         }
-        asm volatile("bar.sync %0, %1;" ::"r"(kBarCounters), "r"(kSkCounters) : "memory");
+        named_sync(kBarCounters, kSkCounters);
         const uint32_t total4 = meta[s].item.total4;
         const uint32_t thr_m1 = meta[s].item.min_score - 1u; // min_score >= 2 in this class
         const uint4 *st = stage + (size_t)s * kStageU4;
@@ -882,7 +891,7 @@ search_sketch_kernel(BatchArgs a) {
         }
         __syncwarp();
         // my slice of query it is in the sketch
-        asm volatile("bar.arrive %0, %1;" ::"r"(kBarCounted + it % kSkResolverGroups), "r"(kSkCounters + kSkResolvers) : "memory");
+        named_arrive(kBarCounted + it % kSkResolverGroups, kSkCounters + kSkResolvers);
         if (warp == 0 && lane == 0) {
             tick(9, tc0);
             if (timed) atomicAdd(&a.stats->dbg[10], 1ull);
@@ -1150,6 +1159,7 @@ __global__ void __launch_bounds__(kS2Threads, 2) search_sketch2_kernel(BatchArgs
                 }
             }
             // heavy counters are read: my_total as an operand makes the arrive wait for the load's result
+            __syncwarp();
             asm volatile("bar.arrive 2, %0;" ::"r"(kS2Workers), "r"(my_total) : "memory");
         }
         // distinct candidates, computed by every warp for itself (registers + votes): lane c keeps candidate c
@@ -1190,6 +1200,7 @@ __global__ void __launch_bounds__(kS2Threads, 2) search_sketch2_kernel(BatchArgs
             }
         }
         // the sketch is no longer needed: clear my slice for the next query
+        __syncwarp();
         if (warp != 0) asm volatile("bar.sync 2, %0;" ::"r"(kS2Workers) : "memory"); // warp 0 has read the heavy counters
         if (!(a.debug & 16u))
             for (uint32_t i = tid; i < kSketchWords / 4; i += kS2Workers) sk4[i] = make_uint4(0, 0, 0, 0);
@@ -1471,6 +1482,7 @@ __global__ void __launch_bounds__(THREADS, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))
                     }
                     __syncthreads();
                     const uint32_t n = s_ncand;
+                    __syncthreads(); // everyone has read n before the next round appends (or the branch could differ)
                     if (n + kThreads > kKbufCap) shrink(n);
                 }
             }
@@ -1599,8 +1611,9 @@ __global__ void __launch_bounds__(kThreads) search_wide_kernel(BatchArgs a) {
                         }
                     }
                     __syncthreads();
-                    if (s_kn > kWideKbuf - 4 * kThreads) {
-                        const uint32_t n = s_kn;
+                    const uint32_t n = s_kn;
+                    __syncthreads(); // everyone has read n before the next round appends (or the branch could differ)
+                    if (n > kWideKbuf - 4 * kThreads) {
                         group_sort_keys(g, kbuf, n, kWideKbuf);
                         __syncthreads();
                         if (tid == 0) {
