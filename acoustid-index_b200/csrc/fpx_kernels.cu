@@ -8,10 +8,10 @@
 //   search_sketch_kernel the hot path (min_score >= 2, i.e. every HTTP-default query of >= 21 terms):
 //                        warp-specialised persistent CTAs.  Producer warps gather the query's posting rows
 //                        into a shared-memory stage with TMA bulk copies (cp.async.bulk + mbarrier
-//                        complete_tx); consumer warps (1) scatter-add every docid into a per-query u16
-//                        count sketch with fire-and-forget shared atomics, (2) re-read the staged postings
-//                        and send only docids whose sketch counter reaches min_score to a small exact
-//                        table, (3) rank the survivors.  The sketch never under-counts, so this is exact.
+//                        complete_tx); counter warps add every docid to a per-query sketch of 8-bit
+//                        counters with shared atomics and record the docids whose counter reaches
+//                        min_score; resolver warps count those few exactly in the staged rows and rank
+//                        them.  The sketch never under-counts, so this is exact.
 //   search_smem_kernel   persistent CTAs, one query at a time: stream the rows with 128-bit loads,
 //                        count docids in a shared-memory open-addressing table (one packed 32-bit word
 //                        per doc: quotient tag | probe number | count), then scan the table, rank the
@@ -91,7 +91,8 @@ __device__ uint32_t make_item(const BatchArgs &a, uint32_t q, uint32_t rows_off,
     // counter is "hot" and the recount list would overflow, so those go to the exact count-table path.
     bool sketch_ok = a.use_sketch && o.min_score >= 2 && o.min_score <= 128 && total4 <= kStageU4 &&
                      k_eff <= kFastKbuf && n_rows <= kSketchMaxRows;
-    // expected records = postings that find their counter already at min_score-1 (Poisson, 16384 counters)
+    // expected records = postings that find their counter already at min_score-1 (Poisson; limits chosen for the
+    // 16384-counter sketch of search_sketch2_kernel, conservative for the 32768 counters of the default kernel)
     if (o.min_score == 2 && postings > 1500) sketch_ok = false;
     if (o.min_score == 3 && postings > 4500) sketch_ok = false;
     if ((a.debug & 1024u) && (!a.snap.pad_spread || o.min_score > 0x2000u)) sketch_ok = false; // search_sketch2_kernel
@@ -506,24 +507,26 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 //                         resource (~10 SASS instructions per copy through uniform registers), so the warps
 //                         split every query row-wise; row descriptors (with the row's place in the stage,
 //                         precomputed by prepare_kernel) sit in registers, loaded one query ahead.
-//   counters  (16 warps)  scatter-add every staged docid into a 16384 x u16 count sketch (two sketches,
+//   counters  (14 warps)  scatter-add every staged docid into a 32768 x u8 count sketch (two sketches,
 //                         alternating queries) with shared atomics.  The add returns the counter's previous
 //                         value; a posting that finds its counter already at min_score-1 or more records its
 //                         docid as a candidate.  A warp that finishes its slice arrives on `counted` and
 //                         moves straight on to the next query.
-//   resolvers (2 x 4 warps, alternating queries)  clear the sketch, de-duplicate the few candidates, count
+//   resolvers (3 x 4 warps, taking queries in turn)  clear the sketch, de-duplicate the few candidates, count
 //                         each exactly by binary search in the staged rows (sorted by row_key(docid)), rank, apply the
 //                         reference's cutoffs, write the results, hand the stage back.
 // Why this is exact: a counter holds the sum of the true counts of all docids hashing to it and only grows
 // by one per posting.  If doc d has c >= min_score postings in the query, at most min_score-1 of them can
 // be among the first min_score-1 arrivals at its counter, so at least one posting of d arrives when the
 // counter is already >= min_score-1 and d is recorded.  Its exact count is then taken from the rows.
-// The kernel is bound by integer-ALU issue, not by memory, so everything per posting is kept minimal.
+// What bounds it: the request rate of the ~100 bulk copies per query and the counters'
+// shared atomics, about equally; not HBM bandwidth.
 // ------------------------------------------------------------------------------------------------
 constexpr int kSkResolverWarps = 4; // per group
 constexpr int kSkStages = 4;
 constexpr int kSkResolvers = kSkResolverWarps * 32;
-constexpr uint32_t kSketchLog = 14;       // 16384 u16 counters, two per 32-bit word = 32 KB
+constexpr uint32_t kSketchLog = 14;       // 8192 words = 32 KB per sketch (search_sketch_kernel: 32768 u8 counters;
+                                          // search_sketch2_kernel: 16384 u16 counters)
 constexpr uint32_t kSketchWords = (1u << kSketchLog) / 2;
 constexpr uint32_t kRecCap = 512;         // candidate records per query (with repeats)
 constexpr uint32_t kSetSlots = 64;        // distinct-candidate hash set
