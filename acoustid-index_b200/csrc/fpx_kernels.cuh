@@ -27,7 +27,7 @@ struct SnapshotDev {
 // counts with (word = bits 29..17, so the shared-memory bank is bits 21..17); the rotation puts the bank bits on
 // top.  A warp of counter threads takes 32 consecutive 16-byte granules, i.e. every fourth posting of ~1.8 rows:
 // in this order their banks sweep 0..31 once per row instead of being random, which cuts the bank conflicts of
-// the shared atomics from ~3.5 to ~2.6 wavefronts per instruction.  It is a bijection, so equal docids stay
+// the shared atomics from ~3.5 to ~2.9 wavefronts per instruction (measured).  It is a bijection, so equal docids stay
 // adjacent and a row can still be searched (compare keys instead of docids).
 constexpr uint32_t kRowMult = 0x9E3779B1u;
 constexpr uint32_t row_inv32(uint32_t a) {
