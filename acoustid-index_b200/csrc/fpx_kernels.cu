@@ -86,17 +86,23 @@ __device__ uint32_t make_item(const BatchArgs &a, uint32_t q, uint32_t rows_off,
     w.min_score = o.min_score;
     w.min_score_pct = o.min_score_pct;
     if (n_rows == 0 || k_eff == 0) return kNumClasses;
-    // The sketch path needs min_score >= 2 (it only recounts docids whose sketch counter reaches
-    // min_score) and the query must fit one 32 KB stage.  With a low floor and many postings nearly every
-    // counter is "hot" and the recount list would overflow, so those go to the exact count-table path.
-    bool sketch_ok = a.use_sketch && o.min_score >= 2 && o.min_score <= 128 && total4 <= kStageU4 &&
+    // The sketch path needs 2 <= min_score <= 128 (bias of its 8-bit counters) and the query's padded rows must
+    // fit one stage.  With a low floor and many postings too many counters reach it by chance: the expected
+    // number of such counters is 32768 * P(Poisson(postings / 32768) >= min_score); the limits keep it <= 4
+    // (kHotCap is 32; beyond it the query is re-queued, so this is a matter of speed only).
+    bool sketch_ok = a.use_sketch && o.min_score >= 2 && o.min_score <= 128 && total4 <= kStageLargeU4 &&
                      k_eff <= kFastKbuf && n_rows <= kSketchMaxRows;
-    // expected records = postings that find their counter already at min_score-1 (Poisson; limits chosen for the
-    // 16384-counter sketch of search_sketch2_kernel, conservative for the 32768 counters of the default kernel)
-    if (o.min_score == 2 && postings > 1500) sketch_ok = false;
-    if (o.min_score == 3 && postings > 4500) sketch_ok = false;
-    if ((a.debug & 1024u) && (!a.snap.pad_spread || o.min_score > 0x2000u)) sketch_ok = false; // search_sketch2_kernel
-    return sketch_ok ? (uint32_t)kSketchClass : exact_class_for(postings, k_eff);
+    if (a.debug & 0x2000u) { // round-1 kernel (A/B): records candidates while counting, 16384-counter limits
+        if (total4 > kStageU4) sketch_ok = false;
+        if (o.min_score == 2 && postings > 1500) sketch_ok = false;
+        if (o.min_score == 3 && postings > 4500) sketch_ok = false;
+    } else {
+        if (o.min_score == 2 && postings > 512) sketch_ok = false;
+        if (o.min_score == 3 && postings > 2900) sketch_ok = false;
+        if (o.min_score == 4 && postings > 7600) sketch_ok = false;
+    }
+    if (!sketch_ok) return exact_class_for(postings, k_eff);
+    return total4 <= kStageU4 ? (uint32_t)kSketchClass : (uint32_t)kSketchLargeClass;
 }
 
 // Bin a prepared query (called by one thread).
@@ -903,158 +909,109 @@ search_sketch_kernel(BatchArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// sketch path, second generation (FPX variant bit 1024): roles merged, the query held in registers, and a
-// *windowed* sketch.  Two CTAs per SM, each an independent query pipeline of 8 worker warps + 4 producer
-// warps; the hardware interleaves the two pipelines.
-//   producers (4 warps)  all four issue a quarter of every query's row copies (TMA bulk, as above) into one of
-//                        two 32 KB stages
-//   workers   (8 warps)  each thread loads its <= 8 granules (32 docids) of the staged query into registers and
-//                        keeps them: count (16 atomics in flight per thread before any result is looked at) ->
-//                        barrier A, the only rendezvous; the stage goes back to the producers -> every warp
-//                        de-duplicates the few candidate records for itself (warp votes), clears its slice of
-//                        the sketch, compares its register-resident granules with each candidate (exact
-//                        recount) and adds its share to the candidates' counts -> warps 1..7 go straight on to
-//                        the next query; warp 0 waits for the eight shares (mbarrier), checks the heavy
-//                        counters, ranks and writes the results (registers + shuffles).
-//
-// Windowed sketch.  16384 counters of 16 bits (two per word).  The atomic add returns the counter's previous
-// value `old`; with t = min_score-1 a posting is an *event* iff t <= old < t+W (W = 4): two biased adds and one
-// logic op per posting, accumulated per granule.  An event records its docid as a candidate; the event that sees
-// old == t+W-1 also lists the counter as heavy.  Later arrivals at that counter are silent.  Without the
-// window the ~75 postings of a true match would all be events, and since an event costs its whole warp a
-// divergent detour the kernel would spend a third of its time there.
-// Why this is exact: (a) a counter that never left the window recorded every posting that arrived at
-// position >= t, and a doc with >= min_score = t+1 postings in it has such a posting; (b) for a heavy counter
-// the total number of arrivals is its final value, the recorded candidates that hash to it get exact counts
-// from the recount, and what is left over ("hidden") bounds the count of every unrecorded doc in that
-// counter: hidden < min_score means no unrecorded doc can be a result; otherwise the query is re-queued to the
-// exact count-table kernels.  Candidate scores never come from the sketch.
-// The kernel is bound by instruction issue, so the common path is branch-free.
-// Needs row padding above every live docid (SnapshotDev::pad_spread) and min_score-1 < 0x2000.
+// sketch path, "count, then find" (the hot kernel; classes kSketchClass and kSketchLargeClass).
+// One persistent CTA per SM, warps in three roles, hand-overs by named barriers (arrive / sync pairs; the TMA
+// completion is the only mbarrier), several queries in flight per SM:
+//   producers  TMA bulk copies (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) of the query's posting rows
+//              into a ring of shared-memory stages; all producer warps fill one stage at a time.
+//   counters   add every staged docid to a sketch of 32768 8-bit counters (four per 32-bit word) with shared
+//              atomics whose results are never looked at (SASS: ATOMS without a destination): the loop is a
+//              128-bit load, one hash multiply and five integer ops per posting, no branch, no dependence on the
+//              shared-memory round trip.  h = docid * kRowMult; word = h[29:17], byte = h[16:15].
+//   resolvers  (groups of four warps, taking queries in turn) read the sketch back once — the pass that clears it
+//              for the query after next — and list the counters that reached min_score ("hot").  The sketch is
+//              cleared to the bias 128 - min_score of its next query, so "hot" is bit 7 of a byte and the test of
+//              sixteen counters is two logic ops.  Rows are sorted by row_key(docid), whose top 15 bits are the
+//              counter index, so the postings of a hot counter are one contiguous range in every staged row:
+//              a binary search per (hot counter, row) finds them, a small table counts them per docid — exactly —
+//              and the survivors are ranked and cut like common.zig:140-166.
+// Exactness: a counter receives every posting whose docid maps to it, so a docid with count >= min_score makes
+// its counter hot, and a hot counter's postings are all enumerated; scores never come from the sketch.  A byte
+// that carries into its neighbour (128 + min_score arrivals at one counter) would corrupt the picture: the
+// clearing pass also sums all bytes (IDP.4A), and the sum equals 32768 * bias + the number of staged postings
+// iff no byte carried; otherwise, and when there are more hot counters or candidates than fit, the query is
+// re-queued to the exact count-table kernels.
 // ------------------------------------------------------------------------------------------------
-constexpr int kS2WorkerWarps = 8;
-constexpr int kS2ProducerWarps = 4;
-constexpr int kS2Workers = kS2WorkerWarps * 32;
-constexpr int kS2Threads = (kS2WorkerWarps + kS2ProducerWarps) * 32;
-constexpr int kS2Stages = 2;
-constexpr uint32_t kS2RecCap = 128;   // candidate records per query (with repeats): four per lane of warp 0
-constexpr uint32_t kS2HeavyCap = 32;  // heavy counters per query: one per lane of warp 0
-constexpr uint32_t kS2Window = 4;
-constexpr size_t kS2SmemBytes = (size_t)kS2Stages * kStageU4 * 16; // the stages; the sketch is static shared memory
-static_assert(kStageU4 == 8 * kS2Workers, "a staged query is exactly eight granules per worker thread");
+constexpr uint32_t kHotCap = 32;    // hot counters per query handled here
+constexpr uint32_t kCandSlots = 64; // candidate table: docid -> exact count
+constexpr uint32_t kCandMax = 48;   // distinct candidates; more -> exact count-table path
+constexpr uint32_t kSketchBytes = kSketchWords * 4;
 
-struct S2Shared {
-    uint64_t full[kS2Stages], empty[kS2Stages];
-    WorkItem item[kS2Stages];
-    uint32_t nrec[2], nheavy[2], rec[2][kS2RecCap], heavy[2][kS2HeavyCap]; // per query parity
-    uint32_t c_cnts[2][kMaxCand]; // exact counts of the candidates, per query parity
-    uint64_t cleared, counted;    // per worker warp: my slice of the sketch is clear / my exact counts are added
+struct FindState { // private to one resolver group
+    uint32_t hot[kHotCap];
+    uint32_t cand_id[kCandSlots], cand_cnt[kCandSlots];
+    unsigned long long r_keys[kCandSlots];
+    uint32_t n_hot, n_cand, sum, ovf, r_count;
 };
-static_assert(kMaxCand == 32, "one candidate per lane of warp 0");
 
-// hash bits 31..19 pick the word, bit 18 the half
-__device__ __forceinline__ uint32_t s2_word(uint32_t hv) { return hv >> 19; }
-__device__ __forceinline__ bool s2_upper(uint32_t hv) { return (hv & 0x40000u) != 0u; }
-
-// Rare path (per thread): one of the four postings of granule `v` arrived inside the window of its counter
-// word.  o = previous values of the four words; checks each posting's own counter.
-__device__ __forceinline__ void s2_event(uint4 v, uint4 o, uint32_t thr_m1, uint32_t *nrec, uint32_t *rec,
-                                         uint32_t *nheavy, uint32_t *heavy) {
+__device__ __forceinline__ void cand_add(FindState &st, uint32_t pad, uint32_t d, uint32_t c) {
+    uint32_t x = (d * kMult2) >> 26;
 #pragma unroll 1
-    for (int e = 0; e < 4; ++e) {
-        const uint32_t hv = v.x * kMult;
-        const uint32_t rel = (s2_upper(hv) ? o.x >> 16 : o.x & 0xFFFFu) - thr_m1; // my own counter, before my add
-        if (rel < kS2Window) {
-            const uint32_t pos = atomicAdd(nrec, 1u);
-            if (pos < kS2RecCap) rec[pos] = v.x;
-            if (rel == kS2Window - 1u) { // the window closes: the counter is heavy
-                const uint32_t hp = atomicAdd(nheavy, 1u);
-                if (hp < kS2HeavyCap) heavy[hp] = hv >> 18; // counter index: word * 2 + half
-            }
+    for (uint32_t tries = 0; tries < kCandSlots; ++tries) {
+        const uint32_t old = atomicCAS(st.cand_id + x, pad, d);
+        if (old == pad || old == d) {
+            if (old == pad && atomicAdd(&st.n_cand, 1u) >= kCandMax) st.ovf = 1u;
+            atomicAdd(st.cand_cnt + x, c);
+            return;
         }
-        v = make_uint4(v.y, v.z, v.w, v.x);
-        o = make_uint4(o.y, o.z, o.w, o.x);
+        x = (x + 1) & (kCandSlots - 1);
     }
+    st.ovf = 1u;
 }
 
-// One trip of the count: thread `tid` takes granules tid + (4T+k)*256, k = 0..3, keeps them in v[4T+k], adds
-// their sixteen docids to the sketch (all sixteen atomics issued before any result is looked at) and handles
-// events.  FULL: all four granules lie inside the query.  b_lo / b_hi: per 16-bit half, 0x8000 - t and
-// 0x8000 - t - W, so bit 15 of (old + b_lo) & ~(old + b_hi) says t <= old < t+W (counts stay below 0x2000 + t,
-// nothing carries across the halves).
-template <int T, bool FULL>
-__device__ __forceinline__ void s2_trip(uint4 (&v)[8], const uint4 *sg, uint32_t tid, uint32_t total4, uint4 pad4,
-                                        uint32_t *sk, uint32_t b_lo, uint32_t b_hi, uint32_t thr_m1, uint32_t *nrec,
-                                        uint32_t *rec, uint32_t *nheavy, uint32_t *heavy) {
-    uint32_t oo[16];
-    uint32_t lo[4], hi[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t i = tid + (4 * T + k) * kS2Workers;
-        const bool act = FULL || i < total4;
-        v[4 * T + k] = sg[i]; // inside the stage even when outside the query
-        lo[k] = act ? 1u : 0u; // adding 0 leaves the sketch alone
-        hi[k] = act ? 0x10000u : 0u;
-        if (!FULL && !act) v[4 * T + k] = pad4;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t dd[4] = {v[4 * T + k].x, v[4 * T + k].y, v[4 * T + k].z, v[4 * T + k].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const uint32_t hv = dd[e] * kMult;
-            oo[4 * k + e] = atomicAdd(sk + s2_word(hv), s2_upper(hv) ? hi[k] : lo[k]);
-        }
-    }
-    uint32_t hotg[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        uint32_t acc = 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc |= (oo[4 * k + e] + b_lo) & ~(oo[4 * k + e] + b_hi);
-        hotg[k] = acc & 0x80008000u;
-    }
-    if (hotg[0] | hotg[1] | hotg[2] | hotg[3]) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (hotg[k] && (FULL || lo[k]))
-                s2_event(v[4 * T + k], make_uint4(oo[4 * k], oo[4 * k + 1], oo[4 * k + 2], oo[4 * k + 3]), thr_m1, nrec, rec,
-                         nheavy, heavy);
-    }
+template <int STAGES, uint32_t STAGE_U4> constexpr size_t find_smem_bytes() {
+    return 2 * (size_t)kSketchBytes + (size_t)STAGES * STAGE_U4 * 16;
 }
 
-__global__ void __launch_bounds__(kS2Threads, 2) search_sketch2_kernel(BatchArgs a) {
+template <int CW, int RG, int PW, int STAGES, uint32_t STAGE_U4>
+__global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) search_find_kernel(BatchArgs a, uint32_t cls) {
+    static_assert(RG >= 2 && RG <= 3 && STAGES >= 2 && STAGES <= 4, "barrier ids");
+    constexpr int kFirstResolver = CW;
+    constexpr int kFirstProducer = CW + RG * kSkResolverWarps;
+    constexpr int kAllThreads = (kFirstProducer + PW) * 32;
+    constexpr int kCounters = CW * 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint4 *stage = reinterpret_cast<uint4 *>(smem_raw);
-    __shared__ __align__(16) uint32_t sk[kSketchWords]; // static: its address folds into the ATOMS operand
-    __shared__ S2Shared sh;
+    unsigned char *sketch_base = smem_raw; // 2 x 32 KB
+    uint4 *stage = reinterpret_cast<uint4 *>(smem_raw + 2 * (size_t)kSketchBytes);
+    __shared__ uint64_t full[STAGES]; // TMA completion; every other hand-over is a named barrier
+    __shared__ StageMeta meta[STAGES];
+    __shared__ FindState fs[RG];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t count = a.counters->qcount[kSketchClass];
-    const WorkItem *items = a.items + (size_t)kSketchClass * a.n_queries;
+    const uint32_t count = a.counters->qcount[cls];
+    const WorkItem *items = a.items + (size_t)cls * a.n_queries;
     const uint32_t pad = a.snap.pad_id;
+    const bool timed = (a.debug & 512u) && blockIdx.x == 0 && a.stats != nullptr;
+    auto tick = [&](int slot, long long t0) {
+        if (timed) atomicAdd(&a.stats->dbg[slot], (unsigned long long)(clock64() - t0));
+    };
+    if (count == 0u) return;
 
     if (tid == 0) {
-        for (int s = 0; s < kS2Stages; ++s) {
-            mbar_init(&sh.full[s], kS2ProducerWarps);
-            mbar_init(&sh.empty[s], 1);
-        }
-        mbar_init(&sh.cleared, kS2WorkerWarps);
-        mbar_init(&sh.counted, kS2WorkerWarps);
-        sh.nrec[0] = sh.nrec[1] = 0;
-        sh.nheavy[0] = sh.nheavy[1] = 0;
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], PW); // every producer warp arrives with its share of the bytes
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // the sketch, and the stages too: a partial trip reads (and ignores) granules beyond the query
-    for (uint32_t i = tid; i < kS2SmemBytes / 16; i += kS2Threads)
-        reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
-    for (uint32_t i = tid; i < kSketchWords / 4; i += kS2Threads) reinterpret_cast<uint4 *>(sk)[i] = make_uint4(0, 0, 0, 0);
-    if (tid < 2 * kMaxCand) sh.c_cnts[tid / kMaxCand][tid % kMaxCand] = 0;
+    // the two sketches start at the bias of this CTA's first two queries
+    for (uint32_t b = 0; b < 2; ++b) {
+        const unsigned long long idx = blockIdx.x + (unsigned long long)b * gridDim.x;
+        const uint32_t ms = idx < count ? items[idx].min_score : 2u;
+        const uint32_t bias = (0x80u - ms) * 0x01010101u;
+        uint4 *sk4 = reinterpret_cast<uint4 *>(sketch_base + (size_t)b * kSketchBytes);
+        for (uint32_t i = tid; i < kSketchWords / 4; i += kAllThreads) sk4[i] = make_uint4(bias, bias, bias, bias);
+    }
+    if (tid < RG * kCandSlots) {
+        fs[tid / kCandSlots].cand_id[tid % kCandSlots] = pad;
+        fs[tid / kCandSlots].cand_cnt[tid % kCandSlots] = 0u;
+    }
+    if (tid < RG) fs[tid].n_hot = fs[tid].n_cand = fs[tid].sum = fs[tid].ovf = 0u;
     __syncthreads();
 
-    if (warp >= kS2WorkerWarps) {
-        // ===== producers: warp p copies rows p, p+4, p+8, ... of every query; lane l holds row 4*l + p
-        const uint32_t p = warp - kS2WorkerWarps;
+    if (warp >= kFirstProducer) {
+        // ===== producers: all producer warps fill one stage at a time, query after query (stage = it % STAGES);
+        // warp p issues rows p, p + P, p + 2P, ... (lane l holds row P*l + p).  A bulk copy costs ~10 instructions
+        // and ~80 cycles of a warp, so a query's ~100 copies are spread over every producer warp.
+        constexpr int kP = PW, kDesc = (kSketchMaxRows + 32 * kP - 1) / (32 * kP);
+        const uint32_t p = warp - kFirstProducer;
         const uint4 *docids4 = reinterpret_cast<const uint4 *>(a.snap.docids);
         auto item_at = [&](uint32_t it, WorkItem &w) -> bool {
             const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
@@ -1062,237 +1019,262 @@ __global__ void __launch_bounds__(kS2Threads, 2) search_sketch2_kernel(BatchArgs
             w = items[idx];
             return true;
         };
-        auto row_of = [&](const WorkItem &w) -> uint4 {
-            const uint32_t r = (uint32_t)kS2ProducerWarps * lane + p;
-            return r < w.n_rows ? a.rows[w.rows_off + r] : make_uint4(0u, 0u, 0u, 0u);
+        auto rows_of = [&](const WorkItem &w, uint4 (&d)[kDesc]) {
+#pragma unroll
+            for (int j = 0; j < kDesc; ++j) {
+                const uint32_t r = (uint32_t)kP * (lane + 32 * j) + p;
+                d[j] = r < w.n_rows ? a.rows[w.rows_off + r] : make_uint4(0u, 0u, 0u, 0u);
+            }
         };
         WorkItem w{}, w1{};
-        uint4 d = make_uint4(0u, 0u, 0u, 0u), d1 = make_uint4(0u, 0u, 0u, 0u);
+        uint4 d[kDesc], d1[kDesc];
         bool have = item_at(0, w);
-        if (have) d = row_of(w);
+        if (have) rows_of(w, d);
         for (uint32_t it = 0; have; ++it) {
-            const uint32_t s = it & 1u;
-            const bool have1 = item_at(it + 1, w1); // next query's descriptors: in flight during wait + issue
-            if (have1) d1 = row_of(w1);
-            if (it >= kS2Stages) { // the workers hold the previous tenant of this stage in registers now
-                if (lane == 0) mbar_wait(&sh.empty[s], ((it >> 1) - 1) & 1);
-                __syncwarp();
-            }
-            uint32_t mine = (d.y + 3) >> 2;
+            const uint32_t s = it % STAGES;
+            uint4 *dst = stage + (size_t)s * STAGE_U4;
+            const bool have1 = item_at(it + 1, w1); // the next query: in flight during wait + issue
+            if (have1) rows_of(w1, d1);
+            const long long tp0 = clock64();
+            if (it >= (uint32_t)STAGES) // the resolvers released the previous tenant of this stage: us + their warp 0
+                named_sync(kBarStage + s, 32 * kP + 32);
+            if (p == 0 && lane == 0) tick(0, tp0);
+            uint32_t mine = 0;
+#pragma unroll
+            for (int j = 0; j < kDesc; ++j) mine += (d[j].y + 3) >> 2;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
-            if (p == 0 && lane == 0) sh.item[s] = w;
+#pragma unroll
+            for (int j = 0; j < kDesc; ++j) { // stage directory for the resolvers (d.z: the row's place, from prepare_kernel)
+                const uint32_t r = (uint32_t)kP * (lane + 32 * j) + p;
+                if (r < kSketchMaxRows) {
+                    meta[s].row_off[r] = d[j].z * 4u;
+                    meta[s].row_len[r] = d[j].y;
+                }
+            }
+            if (p == 0 && lane == 0) meta[s].item = w;
             if (a.debug & 8u) mine = 0;
             __syncwarp();
-            if (lane == 0) mbar_expect_tx(&sh.full[s], mine * 16u); // expect_tx precedes my copies (release)
+            if (lane == 0) mbar_expect_tx(&full[s], mine * 16u); // expect_tx precedes my copies (release)
             __syncwarp();
-            if (!(a.debug & 8u) && d.y)
-                bulk_g2s(stage + (size_t)s * kStageU4 + d.z, docids4 + d.x, ((d.y + 3) >> 2) * 16u, &sh.full[s]);
+            if (!(a.debug & 8u)) {
+#pragma unroll
+                for (int j = 0; j < kDesc; ++j)
+                    if (d[j].y) bulk_g2s(dst + d[j].z, docids4 + d[j].x, ((d[j].y + 3) >> 2) * 16u, &full[s]);
+            }
             have = have1;
             w = w1;
-            d = d1;
+#pragma unroll
+            for (int j = 0; j < kDesc; ++j) d[j] = d1[j];
+            if (p == 0 && lane == 0) {
+                tick(1, tp0);
+                if (timed) atomicAdd(&a.stats->dbg[2], 1ull);
+            }
         }
         return;
     }
 
-    // ===== workers
-    const Group R{tid, (uint32_t)kS2Workers, 1u};
-    uint4 *sk4 = reinterpret_cast<uint4 *>(sk);
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t n_res = 0; // queries with candidates so far: phase of `counted`
+    if (warp >= kFirstResolver) {
+        // ===== resolvers: group gidx takes every RG-th query; query `it` used sketch it & 1
+        const uint32_t gidx = (warp - kFirstResolver) / kSkResolverWarps;
+        const uint32_t rwarp = (warp - kFirstResolver) % kSkResolverWarps;
+        const uint32_t rtid = rwarp * 32 + lane;
+        const Group R{rtid, (uint32_t)kSkResolvers, kBarGroup + gidx};
+        const Group W{lane, 32u, 0u};
+        FindState &st = fs[gidx];
+        for (uint32_t it = gidx;; it += RG) {
+            const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
+            if (idx >= count) break;
+            const uint32_t s = it % STAGES, b = it & 1u;
+            uint4 *sk4 = reinterpret_cast<uint4 *>(sketch_base + (size_t)b * kSketchBytes);
+            // the sketch's next tenant is this CTA's query it + 2: clear to its bias
+            const unsigned long long idx2 = idx + 2ull * gridDim.x;
+            const uint32_t ms2 = idx2 < count ? items[idx2].min_score : 2u;
+            const long long tr0 = clock64();
+            named_sync(kBarCounted + gidx, kCounters + kSkResolvers); // all counter warps are done with query it
+            if (gidx == 0 && rtid == 0) tick(3, tr0);
+            const WorkItem w = meta[s].item;
+            // read the sketch back: hot counters (bit 7 of a byte), the byte sum, and the clear for query it + 2
+            {
+                const uint32_t b2 = (0x80u - ms2) * 0x01010101u;
+                const uint4 clear4 = make_uint4(b2, b2, b2, b2);
+                uint32_t acc = 0;
+#pragma unroll 4
+                for (uint32_t i = rtid; i < kSketchWords / 4; i += kSkResolvers) {
+                    const uint4 v = sk4[i];
+                    if (!(a.debug & 16u)) sk4[i] = clear4;
+                    acc = __dp4a(v.x, 0x01010101u, acc);
+                    acc = __dp4a(v.y, 0x01010101u, acc);
+                    acc = __dp4a(v.z, 0x01010101u, acc);
+                    acc = __dp4a(v.w, 0x01010101u, acc);
+                    if ((v.x | v.y | v.z | v.w) & 0x80808080u) {
+                        const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll 1
+                        for (uint32_t e = 0; e < 4; ++e) {
+                            uint32_t m = ws[e] & 0x80808080u;
+                            while (m) {
+                                const uint32_t bit = __ffs(m) - 1u;
+                                m &= m - 1u;
+                                const uint32_t pos = atomicAdd(&st.n_hot, 1u);
+                                if (pos < kHotCap) st.hot[pos] = ((i * 4u + e) << 2) | (bit >> 3); // word * 4 + byte
+                            }
+                        }
+                    }
+                }
+                acc = __reduce_add_sync(0xFFFFFFFFu, acc);
+                if (lane == 0) atomicAdd(&st.sum, acc);
+            }
+            R.sync();
+            if (rwarp == 0) named_arrive(kBarSkFree + b, kCounters + 32); // the counters may start query it + 2 on this sketch
+            if (gidx == 0 && rtid == 0) tick(4, tr0);
+            const uint32_t n_hot = (a.debug & 2u) ? 0u : st.n_hot;
+            // no byte carried <=> the bytes add up to the bias of every counter plus one per staged posting
+            bool redo = st.sum != 32768u * (0x80u - w.min_score) + 4u * w.total4 && !(a.debug & 3u);
+            redo = redo || n_hot > kHotCap;
+            uint32_t n = 0;
+            if (n_hot != 0u && !redo) {
+                // find the postings of the hot counters: thread rtid owns row rtid of the stage (<= 128 rows); the
+                // postings of counter c are the range of row keys with top 15 bits == c's place in the row order
+                const bool has_row = rtid < w.n_rows;
+                const uint32_t *row = reinterpret_cast<const uint32_t *>(stage + (size_t)s * STAGE_U4) +
+                                      (has_row ? meta[s].row_off[rtid] : 0u);
+                const uint32_t len = has_row ? meta[s].row_len[rtid] : 0u;
+                const uint32_t top = 1u << (31 - __clz(len | 1u));
+                for (uint32_t c = 0; c < n_hot; c += 4) {
+                    const uint32_t nj = min(4u, n_hot - c); // the same for every thread
+                    uint32_t kp[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t hc = (uint32_t)j < nj ? st.hot[c + j] : 0u;
+                        const uint32_t wd = hc >> 2;
+                        kp[j] = ((wd & 31u) << 27) | ((wd >> 5) << 19) | ((hc & 3u) << 17); // row_key of the range start
+                        lo[j] = 0;
+                    }
+                    for (uint32_t step = top; step; step >>= 1) { // lower bound by halving steps, four chains interleaved
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t probe = lo[j] + step;
+                            if ((uint32_t)j < nj && probe <= len && row_key(row[probe - 1]) < kp[j]) lo[j] = probe;
+                        }
+                    }
+#pragma unroll 1
+                    for (uint32_t j = 0; j < nj; ++j) {
+                        const uint32_t kpj = j == 0 ? kp[0] : j == 1 ? kp[1] : j == 2 ? kp[2] : kp[3];
+                        uint32_t pos = j == 0 ? lo[0] : j == 1 ? lo[1] : j == 2 ? lo[2] : lo[3];
+                        uint32_t d = pos < len ? row[pos] : 0u;
+                        const bool has = pos < len && ((row_key(d) ^ kpj) >> 17) == 0u;
+                        // a true match is found in most rows: one table update per warp and docid, not one per row
+                        uint32_t act = __ballot_sync(0xFFFFFFFFu, has);
+                        while (act) {
+                            const uint32_t leader = __ffs(act) - 1u;
+                            const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, d, leader);
+                            const uint32_t same = __ballot_sync(0xFFFFFFFFu, has && d == d0);
+                            if (lane == leader) cand_add(st, pad, d0, __popc(same));
+                            act &= ~same;
+                        }
+                        // further postings of this counter in my row: repeated (hash, id) pairs, other docids
+                        if (has) {
+                            for (++pos; pos < len; ++pos) {
+                                d = row[pos];
+                                if (((row_key(d) ^ kpj) >> 17) != 0u) break;
+                                cand_add(st, pad, d, 1u);
+                            }
+                        }
+                    }
+                }
+                R.sync();
+                redo = st.ovf != 0u;
+                if (rwarp == 0 && !redo) { // common.zig:140-145: keep score >= min_score
+                    uint32_t base = 0;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const uint32_t id = st.cand_id[lane + 32 * half], cn = st.cand_cnt[lane + 32 * half];
+                        const bool keep = id != pad && cn >= w.min_score;
+                        const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+                        if (keep) st.r_keys[base + __popc(km & ((1u << lane) - 1u))] = rank_key(cn, id);
+                        base += __popc(km);
+                    }
+                    n = base;
+                    __syncwarp();
+                }
+            }
+            if (gidx == 0 && rtid == 0) tick(11, tr0);
+            if (rwarp == 0) { // the stage goes back to the producers
+                named_arrive(kBarStage + s, 32 * PW + 32);
+                if (n_hot != 0u) { // the group's table, for its next query (this warp was its last reader)
+                    st.cand_id[lane] = st.cand_id[lane + 32] = pad;
+                    st.cand_cnt[lane] = st.cand_cnt[lane + 32] = 0u;
+                }
+                if (redo) {
+                    if (lane == 0) {
+                        enqueue(a, exact_class_for(w.postings, w.k_eff), w);
+                        if (a.stats) atomicAdd(&a.stats->overflow_requeues, 1ull);
+                    }
+                } else if (n == 0) {
+                    if (lane == 0) a.out_counts[w.q] = 0;
+                } else {
+                    group_sort_keys(W, st.r_keys, n, kCandSlots);
+                    group_emit_results(W, a, w, st.r_keys, n, &st.r_count);
+                }
+                if (lane == 0) {
+                    st.n_hot = st.n_cand = st.sum = st.ovf = 0u;
+                    if (a.stats && !redo) atomicAdd(&a.stats->sketch_queries, 1ull);
+                }
+            }
+            R.sync(); // the group's scratch is reused by its next query
+            if (gidx == 0 && rtid == 0) {
+                tick(5, tr0);
+                if (timed) atomicAdd(&a.stats->dbg[6], 1ull);
+            }
+        }
+        return;
+    }
+
+    // ===== counters: each warp streams its slice of every query and arrives on `counted`
     for (uint32_t it = 0;; ++it) {
         const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
         if (idx >= count) break;
-        const uint32_t s = it & 1u;
-        if (lane == 0) {
-            mbar_wait(&sh.full[s], (it >> 1) & 1);
-            if (it > 0) mbar_wait(&sh.cleared, (it - 1) & 1); // every warp has cleared its slice of the sketch
-        }
-        __syncwarp();
-        const WorkItem w = sh.item[s];
-        const uint32_t total4 = w.total4;
-        const uint32_t thr_m1 = w.min_score - 1u; // 1 <= min_score-1 < 0x2000 in this class
-        const uint4 *sg = stage + (size_t)s * kStageU4;
-        const uint32_t b_lo = (0x8000u - thr_m1) * 0x10001u, b_hi = b_lo - kS2Window * 0x10001u;
-        // granules beyond the query: four distinct row-padding values (no live docid, no repeated value)
-        const uint4 pad4 = make_uint4(pad, pad + 1, pad + 2, pad + 3);
-
-        // ---- count: thread t owns granules t, t+256, ... of the staged query and keeps them in registers.
-        // Row padding is made of unused docids: counted like anything else, never equal to a candidate.
-        uint4 v[8];
-#define FPX_S2_ARGS v, sg, tid, total4, pad4, sk, b_lo, b_hi, thr_m1, &sh.nrec[s], sh.rec[s], &sh.nheavy[s], sh.heavy[s]
-        if (a.debug & 1u) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = pad4;
-        } else if (total4 >= 8u * kS2Workers) {
-            s2_trip<0, true>(FPX_S2_ARGS);
-            s2_trip<1, true>(FPX_S2_ARGS);
-        } else if (total4 > 4u * kS2Workers) {
-            s2_trip<0, true>(FPX_S2_ARGS);
-            s2_trip<1, false>(FPX_S2_ARGS);
-        } else {
-            s2_trip<0, false>(FPX_S2_ARGS);
-#pragma unroll
-            for (int k = 4; k < 8; ++k) v[k] = pad4;
-        }
-#undef FPX_S2_ARGS
-        R.sync(); // A — the only rendezvous of the eight warps: sketch, registers and records are complete
-        const uint32_t nrec = (a.debug & 2u) ? 0u : sh.nrec[s];
-        const uint32_t r0 = lane < min(nrec, kS2RecCap) ? sh.rec[s][lane] : pad;
-        uint32_t my_heavy = 0, my_total = 0; // warp 0: lane j keeps heavy counter j and its final value = arrivals
-        uint32_t nheavy = 0;
-        bool ovf = nrec > kS2RecCap;
-        if (warp == 0) {
+        const uint32_t s = it % STAGES, b = it & 1u;
+        const long long tc0 = clock64();
+        if (it >= 2) // sketch b was read back and cleared by the resolvers of query it - 2
+            named_sync(kBarSkFree + b, kCounters + 32);
+        if (warp == 0) { // one warp polls the TMA completion, the others park on a named barrier
             if (lane == 0) {
-                mbar_arrive(&sh.empty[s]); // the stage goes back to the producers
-                // the other parity's words: every warp read them before barrier A of this query
-                sh.nrec[s ^ 1u] = 0;
-                sh.nheavy[s ^ 1u] = 0;
-            }
-            if (nrec != 0u) { // final values of the heavy counters, before the sketch is cleared
-                nheavy = sh.nheavy[s];
-                if (nheavy > kS2HeavyCap) {
-                    ovf = true;
-                    nheavy = kS2HeavyCap;
-                }
-                if (lane < nheavy) {
-                    my_heavy = sh.heavy[s][lane];
-                    const uint32_t wv = sk[my_heavy >> 1];
-                    my_total = (my_heavy & 1u) ? wv >> 16 : wv & 0xFFFFu;
-                }
-            }
-            // heavy counters are read: my_total as an operand makes the arrive wait for the load's result
-            __syncwarp();
-            asm volatile("bar.arrive 2, %0;" ::"r"(kS2Workers), "r"(my_total) : "memory");
-        }
-        // distinct candidates, computed by every warp for itself (registers + votes): lane c keeps candidate c
-        uint32_t my_cand = pad, nc = 0;
-        if (nrec != 0u) {
-            if (nrec <= 32u) {
-                const uint32_t same = __match_any_sync(0xFFFFFFFFu, r0);
-                const uint32_t lm = __ballot_sync(0xFFFFFFFFu, r0 != pad && (same & lt_mask) == 0u);
-                nc = __popc(lm);
-                my_cand = __shfl_sync(0xFFFFFFFFu, r0, __fns(lm, 0, lane + 1) & 31u);
-                if (lane >= nc) my_cand = pad;
-            } else {
-                uint32_t r[4];
-                r[0] = r0;
-#pragma unroll
-                for (int j = 1; j < 4; ++j) r[j] = (lane + 32 * j < min(nrec, kS2RecCap)) ? sh.rec[s][lane + 32 * j] : pad;
-                for (;;) { // repeatedly take the first record not yet covered
-                    uint32_t cand = pad;
-                    bool found = false;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, r[j] != pad);
-                        if (!found && m != 0u) {
-                            cand = __shfl_sync(0xFFFFFFFFu, r[j], __ffs(m) - 1);
-                            found = true;
-                        }
-                    }
-                    if (!found) break;
-                    if (nc == kMaxCand) {
-                        ovf = true;
-                        break;
-                    }
-                    if (lane == nc) my_cand = cand;
-                    ++nc;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) r[j] = r[j] == cand ? pad : r[j];
-                }
-            }
-        }
-        // the sketch is no longer needed: clear my slice for the next query
-        __syncwarp();
-        if (warp != 0) asm volatile("bar.sync 2, %0;" ::"r"(kS2Workers) : "memory"); // warp 0 has read the heavy counters
-        if (!(a.debug & 16u))
-            for (uint32_t i = tid; i < kSketchWords / 4; i += kS2Workers) sk4[i] = make_uint4(0, 0, 0, 0);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sh.cleared);
-        if (nrec == 0u) {
-            if (tid == 0) {
-                a.out_counts[w.q] = 0;
-                if (a.stats) atomicAdd(&a.stats->sketch_queries, 1ull);
-            }
-            continue;
-        }
-        if (!ovf) {
-            // exact recount from registers: one "granule contains d" test per granule; a thread that holds a
-            // granule with the same docid twice (a fingerprint with a repeated hash: sorted rows keep the copies
-            // adjacent) counts element by element.  Padding never equals a candidate.
-            bool dup = false;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) dup = dup || v[k].x == v[k].y || v[k].y == v[k].z || v[k].z == v[k].w;
-            for (uint32_t c = 0; c < nc; ++c) {
-                const uint32_t d = __shfl_sync(0xFFFFFFFFu, my_cand, c);
-                uint32_t m = 0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (v[k].x == d || v[k].y == d || v[k].z == d || v[k].w == d) m += 1;
-                if (dup) { // rare: exact multiplicities
-                    m = 0;
-#pragma unroll 1
-                    for (int k = 0; k < 8; ++k) {
-                        m += (v[0].x == d) + (v[0].y == d) + (v[0].z == d) + (v[0].w == d);
-                        const uint4 t0 = v[0];
-#pragma unroll
-                        for (int q = 0; q < 7; ++q) v[q] = v[q + 1];
-                        v[7] = t0;
-                    }
-                }
-                m = __reduce_add_sync(0xFFFFFFFFu, m);
-                if (lane == 0 && m) atomicAdd(&sh.c_cnts[s][c], m);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sh.counted); // my share of the exact counts is in c_cnts (release)
-        ++n_res;
-        if (warp != 0) continue; // warps 1..7 go on to the next query; warp 0 ranks and writes this one
-        if (lane == 0) mbar_wait(&sh.counted, (n_res - 1) & 1);
-        __syncwarp();
-        const uint32_t sc = sh.c_cnts[s][lane];
-        sh.c_cnts[s][lane] = 0; // for query it+2
-        bool redo = ovf;
-        if (!redo) {
-            // heavy counters: arrivals not explained by the recorded candidates bound every unrecorded doc
-            const uint32_t my_ctr = (my_cand * kMult) >> 18;
-            for (uint32_t j = 0; j < nheavy; ++j) {
-                const uint32_t hc = __shfl_sync(0xFFFFFFFFu, my_heavy, j), tot = __shfl_sync(0xFFFFFFFFu, my_total, j);
-                const uint32_t expl = __reduce_add_sync(0xFFFFFFFFu, (lane < nc && my_ctr == hc) ? sc : 0u);
-                if (tot - expl >= w.min_score) redo = true; // tot >= expl: the candidates' postings all arrived there
-            }
-        }
-        if (redo) {
-            // not decidable here (too many candidates, or a heavy counter hides enough arrivals for another
-            // result): the exact count-table kernels take the query
-            if (lane == 0) {
-                enqueue(a, exact_class_for(w.postings, w.k_eff), w);
-                if (a.stats) atomicAdd(&a.stats->overflow_requeues, 1ull);
+                mbar_wait(&full[s], (it / STAGES) & 1, 0);
+                tick(7, tc0);
             }
             __syncwarp();
-            continue;
         }
-        // rank in registers: lane c holds candidate c.  common.zig:140-171: floor, order (score desc, id asc),
-        // limit, relative cutoff anchored on the best (u32 wrapping product, truncating division; the best is
-        // emitted before the cutoff is raised).
-        const bool keep = lane < nc && sc >= w.min_score;
-        const unsigned long long key = keep ? rank_key(sc, my_cand) : ~0ull;
-        uint32_t rank = 0;
-        for (uint32_t l = 0; l < nc; ++l) rank += (__shfl_sync(0xFFFFFFFFu, key, l) < key) ? 1u : 0u;
-        const uint32_t best = __reduce_max_sync(0xFFFFFFFFu, keep ? sc : 0u);
-        const uint32_t ms = max(w.min_score, (uint32_t)(best * w.min_score_pct) / 100u);
-        const bool emit = keep && rank < w.k_eff && (rank == 0 || sc >= ms);
-        if (emit) {
-            a.out_ids[(size_t)w.q * a.k_stride + rank] = my_cand;
-            a.out_scores[(size_t)w.q * a.k_stride + rank] = sc;
-        }
-        const uint32_t n_out = __popc(__ballot_sync(0xFFFFFFFFu, emit));
-        if (lane == 0) {
-            a.out_counts[w.q] = n_out;
-            if (a.stats) {
-                atomicAdd(&a.stats->results, (unsigned long long)n_out);
-                atomicAdd(&a.stats->sketch_queries, 1ull);
+        named_sync(kBarCounters, kCounters);
+        const uint32_t total4 = meta[s].item.total4;
+        const uint4 *sg = stage + (size_t)s * STAGE_U4;
+        const uint32_t boff = b * kSketchBytes; // folded into the address by the same LOP3 that masks the word offset
+        // Row padding is made of unused docids spread over many values: counted like anything else (the byte sum
+        // expects it), never found by the resolvers (they search the true row lengths).
+        auto add4 = [&](const uint4 v) {
+            const uint32_t dd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t t = (dd[e] * kMult) >> 15; // word = h[29:17], byte = h[16:15]
+                atomicAdd(reinterpret_cast<uint32_t *>(sketch_base + ((t & 0x7FFCu) | boff)), __funnelshift_l(0u, 1u, t << 3));
             }
+        };
+        if (!(a.debug & 1u)) {
+            uint32_t i = tid;
+            for (; i + 3 * kCounters < total4; i += 4 * kCounters) { // four loads in flight, then sixteen adds
+                const uint4 v0 = sg[i], v1 = sg[i + kCounters], v2 = sg[i + 2 * kCounters], v3 = sg[i + 3 * kCounters];
+                add4(v0);
+                add4(v1);
+                add4(v2);
+                add4(v3);
+            }
+            for (; i < total4; i += kCounters) add4(sg[i]);
+        }
+        __syncwarp();
+        named_arrive(kBarCounted + it % RG, kCounters + kSkResolvers); // my slice of query it is in the sketch
+        if (warp == 0 && lane == 0) {
+            tick(9, tc0);
+            if (timed) atomicAdd(&a.stats->dbg[10], 1ull);
         }
     }
 }
@@ -1708,6 +1690,10 @@ __global__ void __launch_bounds__(256) result_pack_kernel(const uint32_t *ids, c
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+// Warp split of the hot kernel: counter / resolver-group / producer warps (FPX_DEBUG_ABLATE bits 24..27 pick another
+// one for A/B runs).
+#define FPX_FIND_CONFIGS(X) X(0, 12, 3, 8) X(1, 14, 3, 6) X(2, 10, 3, 10) X(3, 8, 3, 12) X(4, 12, 2, 12) X(5, 16, 2, 8) X(6, 8, 2, 16)
+
 cudaError_t configure_kernels() {
     cudaError_t e;
     e = cudaFuncSetAttribute(search_smem_kernel<13, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for<13, 256>());
@@ -1716,13 +1702,16 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_smem_kernel<15, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for<15, 1024>());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(search_sketch_kernel<16, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(search_sketch_kernel<12, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
-    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_sketch_kernel<14, 3, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(search_sketch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kS2SmemBytes);
+#define X(I, CW, RG, PW)                                                                                              \
+    e = cudaFuncSetAttribute(search_find_kernel<CW, RG, PW, 4, kStageU4>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)find_smem_bytes<4, kStageU4>());                                                    \
+    if (e != cudaSuccess) return e;
+    FPX_FIND_CONFIGS(X)
+#undef X
+    e = cudaFuncSetAttribute(search_find_kernel<12, 3, 8, 3, kStageLargeU4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)find_smem_bytes<3, kStageLargeU4>());
     return e;
 }
 
@@ -1747,23 +1736,20 @@ void launch_prepare_long(const BatchArgs &a, cudaStream_t st, int n_sms) {
 }
 
 void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms) {
-    if (a.debug & 1024u) {
-        search_sketch2_kernel<<<2 * n_sms, kS2Threads, kS2SmemBytes, st>>>(a);
+    if (a.debug & 0x2000u) { // round-1 kernel (A/B)
+        search_sketch_kernel<14, 3, 6><<<n_sms, 1024, kSkSmemBytes, st>>>(a);
         return;
     }
-    // 16 counter + 2 x 4 resolver + 8 producer warps.  (16 + 3 x 4 + 4 was measured slower: one producer warp per
-    // stage needs 7.6 K cycles to issue a query's 100 bulk copies and becomes the bottleneck.)
-    // 14 counter + 3 x 4 resolver + 6 producer warps.  Measured on C3 (tools/sweep.py, sketch kernel per 100 K queries):
-    // 14/3x4/6 1.284 ms, 12/3x4/8 1.302 ms, 15/3x4/5 1.313 ms, 16/2x4/8 1.329 ms, 16/3x4/4 1.43 ms.
-    if (a.debug & 0x4000u) {
-        search_sketch_kernel<16, 2, 8><<<n_sms, 1024, kSkSmemBytes, st>>>(a);
-        return;
+    switch ((a.debug >> 24) & 15u) {
+#define X(I, CW, RG, PW)                                                                                              \
+    case I:                                                                                                           \
+        search_find_kernel<CW, RG, PW, 4, kStageU4><<<n_sms, (CW + 4 * RG + PW) * 32, find_smem_bytes<4, kStageU4>(), st>>>(a, kSketchClass); \
+        break;
+        FPX_FIND_CONFIGS(X)
+#undef X
+    default: break;
     }
-    if (a.debug & 0x8000u) {
-        search_sketch_kernel<12, 3, 8><<<n_sms, 1024, kSkSmemBytes, st>>>(a);
-        return;
-    }
-    search_sketch_kernel<14, 3, 6><<<n_sms, 1024, kSkSmemBytes, st>>>(a);
+    search_find_kernel<12, 3, 8, 3, kStageLargeU4><<<n_sms, 1024, find_smem_bytes<3, kStageLargeU4>(), st>>>(a, kSketchLargeClass);
 }
 
 void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms) {

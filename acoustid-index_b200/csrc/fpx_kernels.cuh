@@ -23,12 +23,15 @@ struct SnapshotDev {
     uint32_t pad_spread; // 1: pad_id and all row padding are larger than every live docid
 };
 
-// Order of the docids inside a row in HBM: ascending row_key.  d -> d * kRowMult is the hash the sketch kernel
-// counts with (word = bits 29..17, so the shared-memory bank is bits 21..17); the rotation puts the bank bits on
-// top.  A warp of counter threads takes 32 consecutive 16-byte granules, i.e. every fourth posting of ~1.8 rows:
-// in this order their banks sweep 0..31 once per row instead of being random, which cuts the bank conflicts of
-// the shared atomics from ~3.5 to ~2.9 wavefronts per instruction (measured).  It is a bijection, so equal docids stay
-// adjacent and a row can still be searched (compare keys instead of docids).
+// Order of the docids inside a row in HBM: ascending row_key.  h = d * kRowMult is the hash the sketch kernel
+// counts with: 32768 8-bit counters, four per 32-bit word; word = h[29:17], byte = h[16:15].  row_key is a bit
+// permutation of h whose top 15 bits are the counter — first the word's shared-memory bank h[21:17], then the rest
+// of the word index h[29:22], then the byte h[16:15] — followed by the remaining bits h[31:30], h[14:0].  So
+//  * the postings of one counter are one contiguous range of every row (the resolvers of search_find_kernel
+//    binary-search it), equal docids stay adjacent, and a row is still searchable by key;
+//  * a warp of counter threads takes 32 consecutive 16-byte granules, i.e. every fourth posting of ~1.8 rows: in
+//    this order their banks sweep 0..31 once per row instead of being random, which cuts the bank conflicts of the
+//    shared atomics (~3.5 -> ~2.9 wavefronts per instruction, measured in round 1).
 constexpr uint32_t kRowMult = 0x9E3779B1u;
 constexpr uint32_t row_inv32(uint32_t a) {
     uint32_t x = a;
@@ -38,9 +41,14 @@ constexpr uint32_t row_inv32(uint32_t a) {
 constexpr uint32_t kRowMultInv = row_inv32(kRowMult);
 __host__ __device__ __forceinline__ uint32_t row_key(uint32_t d) {
     const uint32_t h = d * kRowMult;
-    return (h << 10) | (h >> 22);
+    return ((h << 10) & 0xF8000000u) | ((h >> 3) & 0x07F80000u) | ((h << 2) & 0x00060000u) | ((h >> 15) & 0x00018000u) |
+           (h & 0x00007FFFu);
 }
-__host__ __device__ __forceinline__ uint32_t row_key_inv(uint32_t k) { return ((k >> 10) | (k << 22)) * kRowMultInv; }
+__host__ __device__ __forceinline__ uint32_t row_key_inv(uint32_t k) {
+    const uint32_t h = ((k >> 10) & 0x003E0000u) | ((k << 3) & 0x3FC00000u) | ((k >> 2) & 0x00018000u) |
+                       ((k << 15) & 0xC0000000u) | (k & 0x00007FFFu);
+    return h * kRowMultInv;
+}
 
 struct SearchOpts { // == fpx_search_opts
     uint32_t max_results, min_score, min_score_pct;
@@ -59,12 +67,15 @@ struct WorkItem {
 };
 
 // Work classes.
-//   0      sketch path: TMA-staged rows, u16 count sketch + small exact table (needs min_score >= 2)
+//   0      sketch path: TMA-staged rows (<= 32 KB per query), u8 count sketch, hot counters resolved exactly
+//          in the staged rows (needs 2 <= min_score <= 128)
 //   1..3   exact shared-memory count table of 2^13 / 2^14 / 2^15 packed slots
 //   4      global-memory table: whatever the others cannot represent exactly
-constexpr int kNumClasses = 5;
+//   5      sketch path with 48 KB stages (queries of up to 12288 padded postings)
+constexpr int kNumClasses = 6;
 constexpr int kSketchClass = 0;
 constexpr int kWideClass = 4;
+constexpr int kSketchLargeClass = 5;
 
 struct BatchCounters {
     uint32_t qcount[kNumClasses];
@@ -108,14 +119,15 @@ constexpr uint32_t kFastKbuf = 512;       // candidate buffer of the shared-memo
 constexpr uint32_t kWideKbuf = 2048;      // candidate buffer of the global-memory path
 constexpr uint32_t kMaxResults = 1024;    // FPX_MAX_RESULTS
 constexpr uint32_t kRowsChunk = 256;      // row descriptors staged per round
-constexpr uint32_t kStageU4 = 2048;       // sketch path: one query's padded rows must fit 32 KB
+constexpr uint32_t kStageU4 = 2048;       // sketch path: one query's padded rows must fit 32 KB ...
+constexpr uint32_t kStageLargeU4 = 3072;  // ... or 48 KB in the large-stage class
 constexpr uint32_t kSketchMaxRows = 128;  // sketch path: row descriptors live in producer registers
 
 void launch_build_table(TermEntry *table, uint32_t log2cap, const uint32_t *terms, const uint32_t *lens,
                         const uint32_t *start4, uint64_t n_terms, cudaStream_t st);
 void launch_prepare(const BatchArgs &a, cudaStream_t st);
 void launch_prepare_long(const BatchArgs &a, cudaStream_t st, int n_sms);
-void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms);
+void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms); // both sketch classes
 void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms);
 void launch_search_wide(const BatchArgs &a, cudaStream_t st, int n_ctas);
 // pack the k_stride-wide result arrays of n queries: out_counts[q] and the (id, score) pairs back to back

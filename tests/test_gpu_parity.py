@@ -409,33 +409,66 @@ def test_pinned_dma_and_pageable_packed_paths_agree(ctx, c2):
     ctx.set_chunk_queries(32768)
 
 
-def test_second_generation_sketch_kernel(ctx, c2):
-    """search_sketch2_kernel (variant bit 1024: register-resident queries, windowed sketch with heavy-counter
-    check) against the oracle: C2 documents as queries, several option sets, and a multi-segment snapshot with
-    duplicate hashes and supersession."""
+def test_hot_kernel_variants_agree_with_the_oracle(ctx, c2):
+    """search_find_kernel under its alternative warp splits (FPX_DEBUG_ABLATE bits 24..27) and the round-1 kernel
+    (bit 0x2000, records candidates while counting) against the oracle: C2 documents as queries under several option
+    sets, and a multi-segment snapshot with duplicate hashes and supersession."""
     syn, seg, snap, ix = c2
     reader = pkg.IndexReader(snap)
     terms, _ = syn.queries(3000, 60, seed=4321)
     nq, T = terms.shape
     offs = np.arange(nq + 1, dtype=np.uint64) * T
-    ctx.debug_set(1024)
+    rng = np.random.default_rng(7)
+    ix2, _ = _random_index(rng)
+    snap2 = _snapshot_of(ctx, ix2)
+    queries = [rng.integers(0, 4000, size=int(rng.integers(0, 120))).tolist() for _ in range(500)]
+    t2, o2 = flat_queries(queries)
     try:
-        for opt in ((40, 5, 10), (40, 2, 0), (100, 3, 50), (512, 7, 10), (3, 4, 100)):
-            opts = np.tile(np.array(opt, dtype=np.uint32), (nq, 1))
-            ctx.profile_reset()
-            _compare_batch(reader, ix, terms.reshape(-1), offs, opts, min(opt[0], 64), threads=16)
-            if opt[1] >= 4:
-                assert ctx.profile()["sketch_queries"] > 0.9 * nq
-        rng = np.random.default_rng(7)
-        ix2, _ = _random_index(rng)
-        snap2 = _snapshot_of(ctx, ix2)
-        queries = [rng.integers(0, 4000, size=int(rng.integers(0, 120))).tolist() for _ in range(500)]
-        t2, o2 = flat_queries(queries)
-        for opt in ((40, 2, 10), (40, 3, 0), (64, 5, 10)):
-            _compare_batch(pkg.IndexReader(snap2), ix2, t2, o2, np.tile(np.array(opt, dtype=np.uint32), (len(queries), 1)), 64)
-        snap2.release()
+        for variant in (0x2000, 1 << 24, 3 << 24, 4 << 24, 6 << 24):
+            ctx.debug_set(variant)
+            for opt in ((40, 5, 10), (40, 2, 0), (100, 3, 50), (512, 7, 10), (3, 4, 100)):
+                opts = np.tile(np.array(opt, dtype=np.uint32), (nq, 1))
+                ctx.profile_reset()
+                _compare_batch(reader, ix, terms.reshape(-1), offs, opts, min(opt[0], 64), threads=16)
+                if opt[1] >= 5:
+                    assert ctx.profile()["sketch_queries"] > 0.9 * nq
+            for opt in ((40, 2, 10), (40, 3, 0), (64, 5, 10)):
+                _compare_batch(pkg.IndexReader(snap2), ix2, t2, o2, np.tile(np.array(opt, dtype=np.uint32), (len(queries), 1)), 64)
     finally:
         ctx.debug_set(0)
+        snap2.release()
+
+
+def test_c2_queries_stay_on_the_sketch_path(ctx, c2):
+    """100-term C2 queries (~9.6 K padded postings, more than one 32 KB stage) are answered by the large-stage
+    instance of the hot kernel, not by the exact count-table kernels."""
+    syn, seg, snap, ix = c2
+    terms, _ = syn.queries(4000, 100, seed=99)
+    nq, T = terms.shape
+    offs = np.arange(nq + 1, dtype=np.uint64) * T
+    opts = pkg.synth.http_opts(nq, T)
+    ctx.profile_reset()
+    _compare_batch(pkg.IndexReader(snap), ix, terms.reshape(-1), offs, opts, 40, threads=16)
+    prof = ctx.profile()
+    assert prof["sketch_queries"] > 0.95 * nq, prof
+
+
+def test_sketch_admission_keeps_requeues_rare(ctx, c2):
+    """The admission limits of the sketch path (csrc/fpx_kernels.cu make_item: postings <= 512 / 2900 / 7600 for
+    min_score 2 / 3 / 4) are derived for <= 4 expected chance-hot counters per query; kHotCap is 32.  Measured here:
+    queries right below each limit must be answered by the sketch kernel with (almost) no re-queues."""
+    syn, seg, snap, ix = c2
+    reader = pkg.IndexReader(snap)
+    for ms, T in ((2, 5), (3, 29), (4, 76), (5, 100)):    # ~95 postings per term
+        terms, _ = syn.queries(2000, T, seed=1000 + ms)
+        nq = terms.shape[0]
+        offs = np.arange(nq + 1, dtype=np.uint64) * T
+        opts = np.tile(np.array((40, ms, 0), dtype=np.uint32), (nq, 1))
+        ctx.profile_reset()
+        _compare_batch(reader, ix, terms.reshape(-1), offs, opts, 40, threads=16)
+        prof = ctx.profile()
+        assert prof["sketch_queries"] + prof["overflow_requeues"] > 0.8 * nq, (ms, prof)
+        assert prof["overflow_requeues"] <= 0.02 * nq, (ms, prof)
 
 
 def test_pack_results_for_exchange(ctx, c2):
@@ -560,3 +593,101 @@ def test_device_built_snapshot_equals_host_built(ctx, c2):
         pkg.swap_snapshot(ctx, [bad])
     assert e.value.status == 3
     host_ctx.close()
+
+
+@pytest.fixture(scope="module")
+def c3(ctx):
+    """C3, the metric's configuration: 10 M fingerprints x 120 hashes, vocabulary 2^24, one merged file segment."""
+    import torch
+    cfg = pkg.synth.SynthConfig(n_docs=10_000_000, hashes_per_doc=120, vocab_log2=24, seed=0xF1D00001 + 3)
+    syn = pkg.synth.Synth(cfg, device="cuda:0")
+    items, doc_ids, doc_alive = syn.corpus_items()
+    seg = pkg.FileSegment.from_items(items, doc_ids, doc_alive, commit_id=1)
+    del items
+    torch.cuda.empty_cache()
+    snap = pkg.swap_snapshot(ctx, [seg])
+    ix = OracleIndex()
+    ix.adopt_file_segment(1, 0, seg.block_size, seg.blocks, seg.num_blocks, seg.block_index, seg.doc_ids, seg.doc_alive)
+    yield syn, seg, snap, ix
+    snap.release()
+
+
+def test_c3_full_size_bit_exact(ctx, c3):
+    """The headline configuration at full size: the whole 100 K-query batch through the C ABI; ids, scores and
+    counts of a 6000-query sample against the oracle; size-independent properties on all of it."""
+    syn, seg, snap, ix = c3
+    assert snap.info()["n_postings_total"] == 1_200_000_000
+    reader = pkg.IndexReader(snap)
+    terms, src = syn.queries(100_000, 100, seed=0xF1D01001 + 3)
+    nq, T = terms.shape
+    offs = np.arange(nq + 1, dtype=np.uint64) * T
+    opts = pkg.synth.http_opts(nq, T)
+    ctx.profile_reset()
+    ids, sc, cnt = reader.search_batch(terms.reshape(-1), offs, opts, 40)
+    prof = ctx.profile()
+    assert prof["sketch_queries"] > 0.99 * nq and prof["overflow_requeues"] < 0.001 * nq, prof
+    # the oracle on a sample spread over the batch (every 17th query, about 6000): ids AND scores AND counts
+    pick = np.arange(0, nq, 17)
+    st, so = flat_queries([terms[q].tolist() for q in pick])
+    oi, os_, oc, _ = ix.search_batch(st, so, opts[pick], 40, n_threads=16)
+    assert np.array_equal(cnt[pick], oc)
+    mask = np.arange(40)[None, :] < oc[:, None]
+    assert np.array_equal(ids[pick][mask], oi[mask]) and np.array_equal(sc[pick][mask], os_[mask])
+    # properties of the whole batch: a noisy copy of doc d finds d first with ~75 of its 100 terms; lists are
+    # ordered (score desc, id asc), respect the floor 5 and the 10 % cutoff anchored on the best
+    hit = src >= 0
+    assert (cnt[hit] >= 1).all()
+    assert (ids[hit, 0] == (src[hit] + 1)).mean() > 0.999
+    assert 60 < sc[hit, 0].mean() < 90
+    valid = np.arange(40)[None, :] < cnt[:, None]
+    assert (sc[valid] >= 5).all()
+    key = (0xFFFFFFFF - sc.astype(np.int64)) * (1 << 32) + ids.astype(np.int64)
+    both = valid[:, 1:] & valid[:, :-1]
+    assert (key[:, 1:][both] > key[:, :-1][both]).all()
+    best = np.where(cnt > 0, sc[:, 0], 0).astype(np.int64)
+    assert (sc.astype(np.int64)[valid] >= np.maximum(5, best[:, None] * 10 // 100).repeat(40, axis=1)[valid]).all()
+    # idempotence, and independence of the batch split
+    ids2, sc2, cnt2 = reader.search_batch(terms[:30_000].reshape(-1), offs[:30_001], opts[:30_000], 40)
+    assert np.array_equal(cnt2, cnt[:30_000])
+    m2 = np.arange(40)[None, :] < cnt2[:, None]
+    assert np.array_equal(ids2[m2], ids[:30_000][m2]) and np.array_equal(sc2[m2], sc[:30_000][m2])
+
+
+def test_reference_50k_fingerprint_vector_through_the_gpu(ctx):
+    """The reference's largest known-answer vector, tests/test_fingerprint_api.py:67-99: 50 000 fingerprints of
+    100 CPython random.Random(i).randint(0, 2**18) hashes, inserted in batches of 1000; the query is fingerprint 100;
+    HTTP defaults -> exactly [{id: 100, score: 100}].  Through the CUDA path, on a snapshot of several file and
+    memory segments and on the fully merged one; plus 300 other fingerprints as queries against the oracle."""
+    import random
+    max_hash = 2 ** 18
+    ix = OracleIndex()
+    batch, fps = [], {}
+    for i in range(1, 50001):
+        rng = random.Random(i)
+        fp = [rng.randint(0, max_hash) for _ in range(100)]
+        if i % 167 == 0 or i == 100:
+            fps[i] = fp
+        batch.append(("insert", i, fp))
+        if len(batch) == 1000:
+            ix.update(batch)
+            batch = []
+            if ix.num_memory_segments >= 16:
+                ix.merge_memory(0, 10)
+            if (i // 1000) % 20 == 0:
+                ix.checkpoint()
+    assert ix.num_file_segments >= 1 and ix.num_memory_segments >= 1
+    query = fps[100]
+    for merged in (False, True):
+        if merged:
+            ix.checkpoint()
+            ix.merge_files(0, ix.num_file_segments)
+            assert ix.num_file_segments == 1
+        snap = _snapshot_of(ctx, ix)
+        reader = pkg.IndexReader(snap)
+        assert [tuple(r) for r in pkg.multi_index_search(reader, pkg.SearchRequest(query))] == [(100, 100)]
+        assert ix.search_http(query) == [(100, 100)]
+        qs = [fps[i] for i in sorted(fps)]
+        t, o = flat_queries(qs)
+        _compare_batch(reader, ix, t, o, pkg.synth.http_opts(len(qs), 100), 40, threads=8)
+        _compare_batch(reader, ix, t, o, np.tile(np.array((500, 1, 10), dtype=np.uint32), (len(qs), 1)), 500, threads=8)
+        snap.release()
