@@ -53,7 +53,8 @@ struct RunStateOp {
 
 struct BuildCounters {
     unsigned long long unreachable, superseded, out_of_range;
-    uint32_t error; // 1 corrupt block, 2 block_index mismatch, 3 hashes not ascending, 4 items not sorted
+    uint32_t error; // 1 corrupt block, 2 block_index mismatch, 3 hashes not ascending, 4 items not sorted,
+                    // 5 docs map holds 0xFFFFFFFF, 6 row longer than u32
     uint32_t max_row_len;
 };
 
@@ -217,10 +218,14 @@ struct NewestMap { // open addressing: id -> 1-based index of the newest segment
 };
 __device__ __forceinline__ uint32_t newest_slot(uint32_t id, uint32_t mask) { return (id * 0x9E3779B1u) & mask; }
 
-__global__ void newest_insert_kernel(NewestMap m, const uint32_t *ids, unsigned long long n, uint32_t seg1) {
+__global__ void newest_insert_kernel(NewestMap m, const uint32_t *ids, unsigned long long n, uint32_t seg1, BuildCounters *ctr) {
     const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t id = ids[i];
+    if (id == 0xFFFFFFFFu) { // the map's empty marker: the host build handles such a docs map
+        ctr->error = 5;
+        return;
+    }
     uint32_t s = newest_slot(id, m.mask);
     for (;;) {
         const uint32_t old = atomicCAS(m.keys + s, 0xFFFFFFFFu, id);
@@ -319,29 +324,98 @@ struct Quads { // 64-bit so that the scan accumulates in 64 bits
     __host__ __device__ __forceinline__ unsigned long long operator()(const uint32_t &len) const { return (len + 3) >> 2; }
 };
 
-// one warp per row: copy the docids of row g into its padded place; padding = unused docids above max_live,
-// varying from row to row (fpx_snapshot_host.h, same formula)
-__global__ void scatter_rows_kernel(const unsigned long long *keys, const unsigned long long *row_first, const uint32_t *row_len,
-                                    const uint32_t *row_start4, unsigned long long n_rows, uint32_t pad_base, uint32_t *docids,
-                                    BuildCounters *ctr) {
+struct HeadOfRun { // posting i starts a row of its segment
+    const unsigned long long *keys;
+    __host__ __device__ __forceinline__ uint8_t operator()(const unsigned long long &i) const {
+        return (i == 0 || (uint32_t)(keys[i] >> 32) != (uint32_t)(keys[i - 1] >> 32)) ? 1 : 0;
+    }
+};
+struct HeadOfTerm { // sorted entry i starts a merged row
+    const uint32_t *terms;
+    __host__ __device__ __forceinline__ uint8_t operator()(const uint32_t &i) const {
+        return (i == 0 || terms[i] != terms[i - 1]) ? 1 : 0;
+    }
+};
+struct GatherLen {
+    const uint32_t *lens;
+    __host__ __device__ __forceinline__ unsigned long long operator()(const uint32_t &entry) const { return lens[entry]; }
+};
+
+__global__ void iota_kernel(uint32_t *v, unsigned long long n) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = (uint32_t)i;
+}
+
+// row j of a segment: its term and length from the row starts
+__global__ void segment_rows_kernel(const unsigned long long *kept, unsigned long long n_kept, const unsigned long long *first,
+                                    unsigned long long nt, uint32_t *terms, uint32_t *lens, BuildCounters *ctr) {
+    const unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (j >= nt) return;
+    const unsigned long long f = first[j], e = j + 1 < nt ? first[j + 1] : n_kept;
+    terms[j] = (uint32_t)(kept[f] >> 32);
+    if (e - f > 0xFFFFFFFFull) ctr->error = 6;
+    lens[j] = (uint32_t)(e - f);
+}
+
+// merged row g = sorted entries [head_pos[g], head_pos[g+1]); E = running sum of the entries' lengths
+__global__ void merged_rows_kernel(const uint32_t *sorted_terms, const unsigned long long *E, const uint32_t *head_pos,
+                                   unsigned long long n_rows, uint32_t *terms, uint32_t *lens, BuildCounters *ctr) {
+    const unsigned long long g = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (g >= n_rows) return;
+    const uint32_t h = head_pos[g];
+    const unsigned long long len = E[head_pos[g + 1]] - E[h];
+    terms[g] = sorted_terms[h];
+    if (len > 0xFFFFFFFFull) ctr->error = 6;
+    lens[g] = (uint32_t)len;
+}
+
+// every entry of merged row g: its place in the padded array (in words), and entry -> sorted position
+__global__ void entry_places_kernel(const uint32_t *sorted_entry, const unsigned long long *E, const uint32_t *head_pos,
+                                    const unsigned long long *start4, unsigned long long n_rows, unsigned long long *dst_word,
+                                    uint32_t *inv) {
+    const unsigned long long g = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (g >= n_rows) return;
+    const uint32_t h0 = head_pos[g], h1 = head_pos[g + 1];
+    const unsigned long long base = start4[g] * 4ull, e0 = E[h0];
+    for (uint32_t i = h0; i < h1; ++i) {
+        dst_word[i] = base + (E[i] - e0);
+        inv[sorted_entry[i]] = i;
+    }
+}
+
+// one warp per row of one segment: copy its docids to their place in the merged, padded rows
+__global__ void copy_entries_kernel(const uint32_t *seg_docids, const unsigned long long *first, unsigned long long n_kept,
+                                    unsigned long long nt, const uint32_t *inv /* of this segment's entries */,
+                                    const unsigned long long *dst_word, uint32_t *docids) {
     const uint32_t lane = threadIdx.x & 31;
     const unsigned long long warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long j = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < nt; j += warps) {
+        const unsigned long long f = first[j], e = j + 1 < nt ? first[j + 1] : n_kept;
+        uint32_t *dst = docids + dst_word[inv[j]];
+        for (unsigned long long k = lane; k < e - f; k += 32) dst[k] = seg_docids[f + k];
+    }
+}
+
+// padding of every row's last 16-byte granule = unused docids above max_live, varying from row to row
+// (fpx_snapshot_host.h, same formula)
+__global__ void pad_rows_kernel(const uint32_t *row_len, const uint32_t *row_start4, unsigned long long n_rows, uint32_t pad_base,
+                                uint32_t *docids, BuildCounters *ctr) {
     uint32_t longest = 0;
-    for (unsigned long long g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_rows; g += warps) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_rows; g += stride) {
         const uint32_t len = row_len[g];
-        const unsigned long long first = row_first[g];
         uint32_t *dst = docids + (size_t)row_start4[g] * 4;
-        const uint32_t padded = (len + 3) & ~3u;
-        for (uint32_t j = lane; j < padded; j += 32)
-            dst[j] = j < len ? (uint32_t)keys[first + j] : pad_base + (uint32_t)((g * 3 + j) & 0xFFFFu);
+        for (uint32_t j = len; j < ((len + 3) & ~3u); ++j) dst[j] = pad_base + (uint32_t)((g * 3 + j) & 0xFFFFu);
         longest = max(longest, len);
     }
-    if (lane == 0 && longest) atomicMax(&ctr->max_row_len, longest);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) longest = max(longest, __shfl_xor_sync(0xFFFFFFFFu, longest, o));
+    if ((threadIdx.x & 31) == 0 && longest) atomicMax(&ctr->max_row_len, longest);
 }
 
 __global__ void narrow_kernel(const unsigned long long *in, uint32_t *out, unsigned long long n) {
-    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (uint32_t)in[i];
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (uint32_t)in[i];
 }
 
 template <class T> struct Dev {
@@ -450,6 +524,132 @@ bool GpuSnapshotBuilder::add_memory_segment(uint64_t commit_id, uint64_t merges,
     return true;
 }
 
+// One segment's kept postings as a CSR: ascending terms, row lengths, row starts, docids (ascending inside a row).
+struct GpuSnapshotBuilder::SegCsr {
+    Dev<uint32_t> terms, lens, docids;
+    Dev<unsigned long long> first; // nt entries: start of row j in docids
+    uint64_t nt = 0, kept = 0;
+};
+
+// Decode, flag and select one segment; its raw bytes are freed on the way.
+bool GpuSnapshotBuilder::build_segment(size_t si, bool multi, const void *newest_p, void *ctr_p, SegCsr &out) {
+    Segment &s = *segs_[si];
+    const NewestMap newest = *static_cast<const NewestMap *>(newest_p);
+    BuildCounters *ctr = static_cast<BuildCounters *>(ctr_p);
+    Dev<BlockMeta> meta;
+    Dev<unsigned long long> blk_off;
+    Dev<RunState> st;
+    Dev<unsigned long long> keys;
+    if (s.is_file) {
+        const uint64_t nb = s.num_blocks;
+        Dev<uint32_t> counts;
+        GB_CUDA(counts.alloc(nb));
+        GB_CUDA(blk_off.alloc(nb + 1));
+        GB_CUDA(meta.alloc(nb));
+        GB_CUDA(cudaMemset(meta.p, 0, std::max<uint64_t>(nb, 1) * sizeof(BlockMeta)));
+        GB_CUDA(st.alloc(nb));
+        if (nb) {
+            block_counts_kernel<<<(unsigned)((nb + 255) / 256), 256>>>(s.d_blocks, s.block_size, nb, counts.p, ctr);
+            size_t tmp_bytes = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.p, blk_off.p, (long long)nb);
+            Dev<uint8_t> tmp;
+            GB_CUDA(tmp.alloc(tmp_bytes));
+            GB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, counts.p, blk_off.p, (long long)nb));
+            unsigned long long last_off = 0;
+            uint32_t last_cnt = 0;
+            GB_CUDA(cudaMemcpy(&last_off, blk_off.p + (nb - 1), 8, cudaMemcpyDeviceToHost));
+            GB_CUDA(cudaMemcpy(&last_cnt, counts.p + (nb - 1), 4, cudaMemcpyDeviceToHost));
+            s.n_items = last_off + last_cnt;
+            GB_CUDA(cudaMemcpy(blk_off.p + nb, &s.n_items, 8, cudaMemcpyHostToDevice));
+        } else {
+            s.n_items = 0;
+        }
+        GB_CUDA(keys.alloc(s.n_items));
+        if (nb) {
+            // items per block: every quad costs two control-byte shares and >= 4 docid bytes (block.zig:479-485)
+            const uint32_t max_items = std::min<uint32_t>(kWriterWindow, 4 * ((s.block_size - kBlockHeaderBytes) / 6 + 1));
+            const size_t per_warp = ((size_t)s.block_size + 15) / 16 * 16 + (size_t)max_items * 8;
+            const size_t smem = per_warp * kDecodeWarps;
+            GB_CUDA(cudaFuncSetAttribute(decode_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const unsigned grid = (unsigned)std::min<uint64_t>((nb + kDecodeWarps - 1) / kDecodeWarps, 148ull * 32);
+            decode_blocks_kernel<<<grid, kDecodeWarps * 32, smem>>>(s.d_blocks, s.block_size, nb, blk_off.p, s.d_block_index,
+                                                                   s.min_doc_id, max_items, keys.p, meta.p, ctr);
+            run_state_kernel<<<(unsigned)((nb + 255) / 256), 256>>>(meta.p, blk_off.p, nb, st.p, ctr);
+            size_t tmp_bytes = 0;
+            cub::DeviceScan::InclusiveScan(nullptr, tmp_bytes, st.p, st.p, RunStateOp(), (long long)nb);
+            Dev<uint8_t> tmp;
+            GB_CUDA(tmp.alloc(tmp_bytes));
+            GB_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, tmp_bytes, st.p, st.p, RunStateOp(), (long long)nb));
+        }
+    } else {
+        keys.p = s.d_items; // (hash << 32) | id already
+        s.d_items = nullptr;
+        if (!keys.p) GB_CUDA(keys.alloc(1));
+    }
+    Dev<uint8_t> flags;
+    GB_CUDA(flags.alloc(s.n_items));
+    if (s.n_items)
+        keep_flags_kernel<<<148 * 8, 256>>>(keys.p, s.n_items, s.is_file ? meta.p : nullptr, blk_off.p, st.p, s.num_blocks, newest,
+                                            (uint32_t)si + 1, multi ? 1u : 0u, lo_, hi_, flags.p, ctr);
+    GB_CUDA(cudaDeviceSynchronize());
+    if (s.d_blocks) cudaFree(s.d_blocks); // the raw blocks are not needed any more
+    s.d_blocks = nullptr;
+    if (s.d_block_index) cudaFree(s.d_block_index);
+    s.d_block_index = nullptr;
+    meta.free();
+    blk_off.free();
+    st.free();
+    if (s.n_items == 0) return true;
+
+    // kept postings, still (hash << 32 | docid) ascending
+    Dev<unsigned long long> kept, d_num;
+    GB_CUDA(kept.alloc(s.n_items));
+    GB_CUDA(d_num.alloc(1));
+    {
+        size_t tmp_bytes = 0;
+        cub::DeviceSelect::Flagged(nullptr, tmp_bytes, keys.p, flags.p, kept.p, d_num.p, (long long)s.n_items);
+        Dev<uint8_t> tmp;
+        GB_CUDA(tmp.alloc(tmp_bytes));
+        GB_CUDA(cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, keys.p, flags.p, kept.p, d_num.p, (long long)s.n_items));
+        unsigned long long got = 0;
+        GB_CUDA(cudaMemcpy(&got, d_num.p, 8, cudaMemcpyDeviceToHost));
+        out.kept = got;
+    }
+    keys.free();
+    flags.free();
+    if (out.kept == 0) return true;
+    // rows: positions where the hash changes
+    GB_CUDA(out.first.alloc(out.kept)); // at most one row per posting; trimmed below
+    {
+        auto pos = thrust::counting_iterator<unsigned long long>(0);
+        auto heads = thrust::make_transform_iterator(pos, HeadOfRun{kept.p});
+        size_t tmp_bytes = 0;
+        cub::DeviceSelect::Flagged(nullptr, tmp_bytes, pos, heads, out.first.p, d_num.p, (long long)out.kept);
+        Dev<uint8_t> tmp;
+        GB_CUDA(tmp.alloc(tmp_bytes));
+        GB_CUDA(cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, pos, heads, out.first.p, d_num.p, (long long)out.kept));
+        unsigned long long got = 0;
+        GB_CUDA(cudaMemcpy(&got, d_num.p, 8, cudaMemcpyDeviceToHost));
+        out.nt = got;
+    }
+    if (out.nt >= 0xFFFFFFFFull) return fail_unsupported("too many distinct terms in one segment");
+    {   // trim the row starts to nt entries (the scratch above was sized for the worst case)
+        Dev<unsigned long long> first;
+        GB_CUDA(first.alloc(out.nt));
+        GB_CUDA(cudaMemcpy(first.p, out.first.p, out.nt * 8, cudaMemcpyDeviceToDevice));
+        out.first.free();
+        out.first.p = first.p;
+        first.p = nullptr;
+    }
+    GB_CUDA(out.terms.alloc(out.nt));
+    GB_CUDA(out.lens.alloc(out.nt));
+    GB_CUDA(out.docids.alloc(out.kept));
+    segment_rows_kernel<<<(unsigned)((out.nt + 255) / 256), 256>>>(kept.p, out.kept, out.first.p, out.nt, out.terms.p, out.lens.p, ctr);
+    narrow_kernel<<<148 * 16, 256>>>(kept.p, out.docids.p, out.kept);
+    GB_CUDA(cudaDeviceSynchronize());
+    return true;
+}
+
 bool GpuSnapshotBuilder::build(GpuCsr &out) {
     const size_t ns = segs_.size();
     const bool multi = ns > 1;
@@ -465,7 +665,7 @@ bool GpuSnapshotBuilder::build(GpuCsr &out) {
         for (Segment *s : segs_) total_docs += s->n_docs;
         uint64_t cap = 16;
         while (cap < 2 * total_docs + 2) cap <<= 1;
-        if (cap > 0x80000000ull) return fail("too many docs for the device liveness map");
+        if (cap > 0x80000000ull) return fail_unsupported("too many docs for the device liveness map");
         GB_CUDA(nk.alloc(cap));
         GB_CUDA(nv.alloc(cap));
         GB_CUDA(cudaMemset(nk.p, 0xFF, cap * 4));
@@ -474,86 +674,22 @@ bool GpuSnapshotBuilder::build(GpuCsr &out) {
         for (size_t si = 0; si < ns; ++si)
             if (segs_[si]->n_docs)
                 newest_insert_kernel<<<(unsigned)((segs_[si]->n_docs + 255) / 256), 256>>>(newest, segs_[si]->d_doc_ids,
-                                                                                          segs_[si]->n_docs, (uint32_t)si + 1);
+                                                                                          segs_[si]->n_docs, (uint32_t)si + 1, ctr.p);
     }
 
-    // ---- per segment: decode, flag, count
-    std::vector<unsigned long long *> seg_keys(ns, nullptr);
-    std::vector<uint8_t *> seg_flags(ns, nullptr);
-    struct Cleanup {
-        std::vector<unsigned long long *> &k;
-        std::vector<uint8_t *> &f;
-        ~Cleanup() {
-            for (auto p : k)
-                if (p) cudaFree(p);
-            for (auto p : f)
-                if (p) cudaFree(p);
-        }
-    } cleanup{seg_keys, seg_flags};
-    uint64_t n_total = 0;
+    // ---- per segment: decode, flag, select -> the segment's own CSR (one segment's intermediates at a time, so the
+    // peak is the raw blocks + one decoded segment + the CSRs built so far; no 2^31 limit on the whole snapshot)
+    std::vector<std::unique_ptr<SegCsr>> csr(ns);
+    uint64_t n_total = 0, n_kept = 0, n_entries = 0;
     for (size_t si = 0; si < ns; ++si) {
-        Segment &s = *segs_[si];
-        Dev<BlockMeta> meta;
-        Dev<unsigned long long> blk_off;
-        Dev<RunState> st;
-        if (s.is_file) {
-            const uint64_t nb = s.num_blocks;
-            Dev<uint32_t> counts;
-            GB_CUDA(counts.alloc(nb));
-            GB_CUDA(blk_off.alloc(nb + 1));
-            GB_CUDA(meta.alloc(nb));
-            GB_CUDA(cudaMemset(meta.p, 0, std::max<uint64_t>(nb, 1) * sizeof(BlockMeta)));
-            GB_CUDA(st.alloc(nb));
-            if (nb) {
-                block_counts_kernel<<<(unsigned)((nb + 255) / 256), 256>>>(s.d_blocks, s.block_size, nb, counts.p, ctr.p);
-                size_t tmp_bytes = 0;
-                cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.p, blk_off.p, (int)nb);
-                Dev<uint8_t> tmp;
-                GB_CUDA(tmp.alloc(tmp_bytes));
-                GB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, counts.p, blk_off.p, (int)nb));
-                unsigned long long last_off = 0;
-                uint32_t last_cnt = 0;
-                GB_CUDA(cudaMemcpy(&last_off, blk_off.p + (nb - 1), 8, cudaMemcpyDeviceToHost));
-                GB_CUDA(cudaMemcpy(&last_cnt, counts.p + (nb - 1), 4, cudaMemcpyDeviceToHost));
-                s.n_items = last_off + last_cnt;
-                GB_CUDA(cudaMemcpy(blk_off.p + nb, &s.n_items, 8, cudaMemcpyHostToDevice));
-            } else {
-                s.n_items = 0;
-            }
-            GB_CUDA(cudaMalloc(&seg_keys[si], std::max<uint64_t>(s.n_items, 1) * 8));
-            if (nb) {
-                // items per block: every quad costs two control-byte shares and >= 4 docid bytes (block.zig:479-485)
-                const uint32_t max_items = std::min<uint32_t>(kWriterWindow, 4 * ((s.block_size - kBlockHeaderBytes) / 6 + 1));
-                const size_t per_warp = ((size_t)s.block_size + 15) / 16 * 16 + (size_t)max_items * 8;
-                const size_t smem = per_warp * kDecodeWarps;
-                GB_CUDA(cudaFuncSetAttribute(decode_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                const unsigned grid = (unsigned)std::min<uint64_t>((nb + kDecodeWarps - 1) / kDecodeWarps, 148ull * 32);
-                decode_blocks_kernel<<<grid, kDecodeWarps * 32, smem>>>(s.d_blocks, s.block_size, nb, blk_off.p, s.d_block_index,
-                                                                       s.min_doc_id, max_items, seg_keys[si], meta.p, ctr.p);
-                run_state_kernel<<<(unsigned)((nb + 255) / 256), 256>>>(meta.p, blk_off.p, nb, st.p, ctr.p);
-                size_t tmp_bytes = 0;
-                cub::DeviceScan::InclusiveScan(nullptr, tmp_bytes, st.p, st.p, RunStateOp(), (int)nb);
-                Dev<uint8_t> tmp;
-                GB_CUDA(tmp.alloc(tmp_bytes));
-                GB_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, tmp_bytes, st.p, st.p, RunStateOp(), (int)nb));
-            }
-            // the raw blocks are not needed any more
-            cudaFree(s.d_blocks);
-            s.d_blocks = nullptr;
-        } else {
-            seg_keys[si] = s.d_items; // (hash << 32) | id already
-            s.d_items = nullptr;
-            if (!seg_keys[si]) GB_CUDA(cudaMalloc(&seg_keys[si], 8));
-        }
-        GB_CUDA(cudaMalloc(&seg_flags[si], std::max<uint64_t>(s.n_items, 1)));
-        if (s.n_items) {
-            const unsigned grid = 148 * 8;
-            keep_flags_kernel<<<grid, 256>>>(seg_keys[si], s.n_items, s.is_file ? meta.p : nullptr, blk_off.p, st.p, s.num_blocks,
-                                             newest, (uint32_t)si + 1, multi ? 1u : 0u, lo_, hi_, seg_flags[si], ctr.p);
-        }
-        GB_CUDA(cudaDeviceSynchronize());
-        n_total += s.n_items;
+        csr[si].reset(new SegCsr());
+        if (!build_segment(si, multi, &newest, ctr.p, *csr[si])) return false;
+        n_total += segs_[si]->n_items;
+        n_kept += csr[si]->kept;
+        n_entries += csr[si]->nt;
     }
+    nk.free();
+    nv.free();
     BuildCounters hc{};
     GB_CUDA(cudaMemcpy(&hc, ctr.p, sizeof hc, cudaMemcpyDeviceToHost));
     switch (hc.error) {
@@ -561,100 +697,118 @@ bool GpuSnapshotBuilder::build(GpuCsr &out) {
     case 1: return fail("corrupt block (stream overruns the block)");
     case 2: return fail("block_index does not match the blocks");
     case 3: return fail("hashes not ascending");
+    case 5: return fail_unsupported("docs map holds the id 0xFFFFFFFF (the device liveness map's empty marker)");
+    case 6: return fail_unsupported("a row of more than 2^32 - 1 postings");
     default: return fail("memory segment items not sorted");
     }
-    if (n_total >= 0x7FFFFFFFull) return fail_unsupported("too many postings for the device build");
+    if (n_kept != n_total - hc.unreachable - hc.superseded - hc.out_of_range) return fail("internal: kept-posting count mismatch");
+    if (n_entries >= 0xFFFFFFFFull) return fail_unsupported("too many (segment, term) rows for the device build");
 
-    // ---- kept postings of all segments, back to back
-    const uint64_t n_kept_max = n_total - hc.unreachable - hc.superseded - hc.out_of_range;
-    Dev<unsigned long long> all;
-    GB_CUDA(all.alloc(n_kept_max + 1));
-    uint64_t n_kept = 0;
-    {
-        Dev<unsigned long long> d_num;
-        GB_CUDA(d_num.alloc(1));
-        for (size_t si = 0; si < ns; ++si) {
-            const uint64_t n = segs_[si]->n_items;
-            if (n == 0) continue;
-            size_t tmp_bytes = 0;
-            cub::DeviceSelect::Flagged(nullptr, tmp_bytes, seg_keys[si], seg_flags[si], all.p + n_kept, d_num.p, (int)n);
-            Dev<uint8_t> tmp;
-            GB_CUDA(tmp.alloc(tmp_bytes));
-            GB_CUDA(cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, seg_keys[si], seg_flags[si], all.p + n_kept, d_num.p, (int)n));
-            unsigned long long got = 0;
-            GB_CUDA(cudaMemcpy(&got, d_num.p, 8, cudaMemcpyDeviceToHost));
-            n_kept += got;
-            cudaFree(seg_keys[si]);
-            seg_keys[si] = nullptr;
-            cudaFree(seg_flags[si]);
-            seg_flags[si] = nullptr;
-        }
-    }
-    if (n_kept != n_kept_max) return fail("internal: kept-posting count mismatch");
-    unsigned long long *sorted = all.p;
-    Dev<unsigned long long> alt;
-    if (multi && n_kept) { // rows fed by several segments: one global order by (hash, docid)
-        GB_CUDA(alt.alloc(n_kept));
-        cub::DoubleBuffer<unsigned long long> db(all.p, alt.p);
-        size_t tmp_bytes = 0;
-        cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, db, (int)n_kept);
-        Dev<uint8_t> tmp;
-        GB_CUDA(tmp.alloc(tmp_bytes));
-        GB_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, db, (int)n_kept));
-        sorted = db.Current();
-    }
-
-    // ---- rows: terms, lengths, padded starts
-    Dev<uint32_t> terms, lens, start4;
-    Dev<unsigned long long> row_first;
+    // ---- merge the segments' rows: sort all (term, entry) pairs by term (stable: a term's entries stay in segment order,
+    // i.e. ascending docids for non-overlapping segments; the row order is re-done by reorder_rows_by_key anyway)
+    const uint64_t N = n_entries;
+    Dev<uint32_t> terms, lens, start4; // the merged row directory
     uint64_t n_rows = 0, total4 = 0;
     uint32_t max_live = 0;
-    if (n_kept) {
-        GB_CUDA(terms.alloc(n_kept));
-        GB_CUDA(lens.alloc(n_kept));
-        Dev<unsigned long long> d_runs;
-        GB_CUDA(d_runs.alloc(1));
-        auto hashes = thrust::make_transform_iterator(static_cast<const unsigned long long *>(sorted), HashOf());
-        size_t tmp_bytes = 0;
-        cub::DeviceRunLengthEncode::Encode(nullptr, tmp_bytes, hashes, terms.p, lens.p, d_runs.p, (int)n_kept);
-        {
+    Dev<unsigned long long> dst_word; // per sorted entry: where its postings go in the padded array
+    Dev<uint32_t> inv;                // entry -> sorted position
+    std::vector<uint64_t> seg_base(ns + 1, 0);
+    for (size_t si = 0; si < ns; ++si) seg_base[si + 1] = seg_base[si] + csr[si]->nt;
+    if (N) {
+        Dev<uint32_t> t_a, t_b, i_a, i_b, all_lens;
+        GB_CUDA(t_a.alloc(N));
+        GB_CUDA(t_b.alloc(N));
+        GB_CUDA(i_a.alloc(N));
+        GB_CUDA(i_b.alloc(N));
+        GB_CUDA(all_lens.alloc(N));
+        for (size_t si = 0; si < ns; ++si) {
+            const uint64_t nt = csr[si]->nt;
+            if (!nt) continue;
+            GB_CUDA(cudaMemcpy(t_a.p + seg_base[si], csr[si]->terms.p, nt * 4, cudaMemcpyDeviceToDevice));
+            GB_CUDA(cudaMemcpy(all_lens.p + seg_base[si], csr[si]->lens.p, nt * 4, cudaMemcpyDeviceToDevice));
+            csr[si]->terms.free();
+            csr[si]->lens.free();
+            // largest live docid
+            Dev<uint32_t> d_max;
+            GB_CUDA(d_max.alloc(1));
+            size_t tmp_bytes = 0;
+            cub::DeviceReduce::Max(nullptr, tmp_bytes, csr[si]->docids.p, d_max.p, (long long)csr[si]->kept);
             Dev<uint8_t> tmp;
             GB_CUDA(tmp.alloc(tmp_bytes));
-            GB_CUDA(cub::DeviceRunLengthEncode::Encode(tmp.p, tmp_bytes, hashes, terms.p, lens.p, d_runs.p, (int)n_kept));
+            GB_CUDA(cub::DeviceReduce::Max(tmp.p, tmp_bytes, csr[si]->docids.p, d_max.p, (long long)csr[si]->kept));
+            uint32_t m = 0;
+            GB_CUDA(cudaMemcpy(&m, d_max.p, 4, cudaMemcpyDeviceToHost));
+            max_live = std::max(max_live, m);
         }
-        unsigned long long runs = 0;
-        GB_CUDA(cudaMemcpy(&runs, d_runs.p, 8, cudaMemcpyDeviceToHost));
-        n_rows = runs;
+        iota_kernel<<<148 * 8, 256>>>(i_a.p, N);
+        cub::DoubleBuffer<uint32_t> dk(t_a.p, t_b.p), dv(i_a.p, i_b.p);
+        {
+            size_t tmp_bytes = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (long long)N);
+            Dev<uint8_t> tmp;
+            GB_CUDA(tmp.alloc(tmp_bytes));
+            GB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, dk, dv, (long long)N));
+        }
+        const uint32_t *st = dk.Current(), *sidx = dv.Current();
+        // lengths in sorted order and their running sum
+        Dev<unsigned long long> E;
+        GB_CUDA(E.alloc(N + 1));
+        {
+            auto ls = thrust::make_transform_iterator(sidx, GatherLen{all_lens.p});
+            size_t tmp_bytes = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ls, E.p, (long long)N);
+            Dev<uint8_t> tmp;
+            GB_CUDA(tmp.alloc(tmp_bytes));
+            GB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, ls, E.p, (long long)N));
+            GB_CUDA(cudaMemcpy(E.p + N, &n_kept, 8, cudaMemcpyHostToDevice));
+        }
+        // merged rows: positions where the sorted term changes
+        Dev<uint32_t> head_pos;
+        Dev<unsigned long long> d_num;
+        GB_CUDA(head_pos.alloc(N + 1));
+        GB_CUDA(d_num.alloc(1));
+        {
+            auto pos = thrust::counting_iterator<uint32_t>(0);
+            auto heads = thrust::make_transform_iterator(pos, HeadOfTerm{st});
+            size_t tmp_bytes = 0;
+            cub::DeviceSelect::Flagged(nullptr, tmp_bytes, pos, heads, head_pos.p, d_num.p, (long long)N);
+            Dev<uint8_t> tmp;
+            GB_CUDA(tmp.alloc(tmp_bytes));
+            GB_CUDA(cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, pos, heads, head_pos.p, d_num.p, (long long)N));
+            unsigned long long got = 0;
+            GB_CUDA(cudaMemcpy(&got, d_num.p, 8, cudaMemcpyDeviceToHost));
+            n_rows = got;
+            const uint32_t n32 = (uint32_t)N;
+            GB_CUDA(cudaMemcpy(head_pos.p + n_rows, &n32, 4, cudaMemcpyHostToDevice));
+        }
+        GB_CUDA(terms.alloc(n_rows));
+        GB_CUDA(lens.alloc(n_rows));
         GB_CUDA(start4.alloc(n_rows + 1));
-        GB_CUDA(row_first.alloc(n_rows + 1));
-        auto q4 = thrust::make_transform_iterator(static_cast<const uint32_t *>(lens.p), Quads());
+        merged_rows_kernel<<<(unsigned)((n_rows + 255) / 256), 256>>>(st, E.p, head_pos.p, n_rows, terms.p, lens.p, ctr.p);
         Dev<unsigned long long> start4_64;
         GB_CUDA(start4_64.alloc(n_rows + 1));
-        tmp_bytes = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, q4, start4_64.p, (int)n_rows);
         {
+            auto q4 = thrust::make_transform_iterator(static_cast<const uint32_t *>(lens.p), Quads());
+            size_t tmp_bytes = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, q4, start4_64.p, (long long)n_rows);
             Dev<uint8_t> tmp;
             GB_CUDA(tmp.alloc(tmp_bytes));
-            GB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, q4, start4_64.p, (int)n_rows));
-            GB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, lens.p, row_first.p, (int)n_rows));
+            GB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, q4, start4_64.p, (long long)n_rows));
         }
         unsigned long long last4 = 0;
         uint32_t last_len = 0;
         GB_CUDA(cudaMemcpy(&last4, start4_64.p + (n_rows - 1), 8, cudaMemcpyDeviceToHost));
         GB_CUDA(cudaMemcpy(&last_len, lens.p + (n_rows - 1), 4, cudaMemcpyDeviceToHost));
+        GB_CUDA(cudaMemcpy(&hc, ctr.p, sizeof hc, cudaMemcpyDeviceToHost));
+        if (hc.error == 6) return fail_unsupported("a row of more than 2^32 - 1 postings");
         total4 = last4 + ((last_len + 3) >> 2);
         if (total4 > 0xFFFFFFFFull) return fail_unsupported("snapshot exceeds 2^32 16-byte granules");
         narrow_kernel<<<(unsigned)((n_rows + 255) / 256), 256>>>(start4_64.p, start4.p, n_rows);
-        // largest live docid
-        Dev<uint32_t> d_max;
-        GB_CUDA(d_max.alloc(1));
-        auto ids = thrust::make_transform_iterator(static_cast<const unsigned long long *>(sorted), DocOf());
-        tmp_bytes = 0;
-        cub::DeviceReduce::Max(nullptr, tmp_bytes, ids, d_max.p, (int)n_kept);
-        Dev<uint8_t> tmp;
-        GB_CUDA(tmp.alloc(tmp_bytes));
-        GB_CUDA(cub::DeviceReduce::Max(tmp.p, tmp_bytes, ids, d_max.p, (int)n_kept));
-        GB_CUDA(cudaMemcpy(&max_live, d_max.p, 4, cudaMemcpyDeviceToHost));
+        // where every (segment, term) entry goes, and the inverse of the sort
+        GB_CUDA(dst_word.alloc(N));
+        GB_CUDA(inv.alloc(N));
+        entry_places_kernel<<<(unsigned)((n_rows + 255) / 256), 256>>>(sidx, E.p, head_pos.p, start4_64.p, n_rows, dst_word.p, inv.p);
+        GB_CUDA(cudaDeviceSynchronize());
     }
     if (max_live >= 0xFFFE0000u) return fail_unsupported("docids reach the top of the u32 range (host build picks the padding)");
 
@@ -670,7 +824,14 @@ bool GpuSnapshotBuilder::build(GpuCsr &out) {
     out.n_out_of_range = hc.out_of_range;
     GB_CUDA(cudaMalloc(&out.d_docids, std::max<uint64_t>(total4 * 4, 4) * 4));
     if (n_rows) {
-        scatter_rows_kernel<<<148 * 8, 256>>>(sorted, row_first.p, lens.p, start4.p, n_rows, max_live + 2, out.d_docids, ctr.p);
+        for (size_t si = 0; si < ns; ++si) {
+            if (!csr[si]->nt) continue;
+            copy_entries_kernel<<<148 * 8, 256>>>(csr[si]->docids.p, csr[si]->first.p, csr[si]->kept, csr[si]->nt, inv.p + seg_base[si],
+                                                  dst_word.p, out.d_docids);
+            GB_CUDA(cudaDeviceSynchronize());
+            csr[si].reset();
+        }
+        pad_rows_kernel<<<148 * 8, 256>>>(lens.p, start4.p, n_rows, max_live + 2, out.d_docids, ctr.p);
         GB_CUDA(cudaDeviceSynchronize());
         GB_CUDA(cudaMemcpy(&hc, ctr.p, sizeof hc, cudaMemcpyDeviceToHost));
     }
