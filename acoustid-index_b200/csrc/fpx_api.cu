@@ -491,12 +491,15 @@ void fpx_shutdown(fpx_ctx *ctx) {
 
 fpx_status fpx_snapshot_begin(fpx_ctx *ctx, fpx_snapshot_builder **out) {
     if (!ctx || !out) return set_error(FPX_INVALID_ARGUMENT, "null argument");
-    *out = new (std::nothrow) fpx_snapshot_builder(ctx);
-    if (!*out) return set_error(FPX_OUT_OF_MEMORY, "builder");
+    *out = nullptr;
+    std::unique_ptr<fpx_snapshot_builder> b(new (std::nothrow) fpx_snapshot_builder(ctx));
+    if (!b) return set_error(FPX_OUT_OF_MEMORY, "builder");
     if (!ctx->host_only && !(ctx->flags & FPX_FLAG_HOST_BUILD)) {
-        FPX_CUDA(cudaSetDevice(ctx->device));
-        (*out)->gpu.reset(new (std::nothrow) GpuSnapshotBuilder());
+        FPX_CUDA(cudaSetDevice(ctx->device)); // b is freed on this early return
+        b->gpu.reset(new (std::nothrow) GpuSnapshotBuilder());
+        if (!b->gpu) return set_error(FPX_OUT_OF_MEMORY, "device builder");
     }
+    *out = b.release();
     return FPX_OK;
 }
 
@@ -507,7 +510,8 @@ fpx_status fpx_snapshot_add_file_segment(fpx_snapshot_builder *b, const fpx_file
         cudaSetDevice(b->ctx->device);
         if (!b->gpu->add_file_segment(seg->commit_id, seg->merges, seg->min_doc_id, seg->block_size, seg->blocks, seg->num_blocks,
                                       seg->block_index, seg->doc_ids, seg->n_docs))
-            return set_error(b->gpu->oom ? FPX_OUT_OF_MEMORY : FPX_INVALID_SEGMENT, b->gpu->error);
+            return set_error(b->gpu->oom ? FPX_OUT_OF_MEMORY : b->gpu->unsupported ? FPX_UNSUPPORTED : FPX_INVALID_SEGMENT,
+                             b->gpu->error + (b->gpu->unsupported ? " (use FPX_FLAG_HOST_BUILD)" : ""));
         return FPX_OK;
     }
     try {

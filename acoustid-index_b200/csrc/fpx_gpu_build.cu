@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -477,12 +478,14 @@ bool GpuSnapshotBuilder::check_order(uint64_t commit_id, bool is_file) {
 bool GpuSnapshotBuilder::add_file_segment(uint64_t commit_id, uint64_t merges, uint32_t min_doc_id, uint32_t block_size,
                                           const uint8_t *blocks, uint64_t num_blocks, const uint32_t *block_index,
                                           const uint32_t *doc_ids, uint64_t n_docs) {
+    if (poisoned_) return fail("an earlier segment failed to upload; abort this builder");
     if (!check_order(commit_id, true)) return false;
-    if (block_size < kMinBlockSize || block_size > kMaxBlockSize || block_size % 16) return fail("block_size out of range");
+    if (block_size < kMinBlockSize || block_size > kMaxBlockSize) return fail("block_size out of range");
+    // filefmt.zig:237 accepts any size in 64..4096; the device decoder reads blocks as 16-byte pieces
+    if (block_size % 16) return fail_unsupported("block_size is not a multiple of 16");
     if (num_blocks && (!blocks || !block_index)) return fail("null blocks / block_index");
     if (num_blocks > 0xFFFFFFF0ull) return fail("too many blocks");
-    Segment *s = new Segment();
-    segs_.push_back(s);
+    std::unique_ptr<Segment> s(new Segment());
     s->is_file = true;
     s->commit_id = commit_id;
     s->merges = merges;
@@ -490,6 +493,7 @@ bool GpuSnapshotBuilder::add_file_segment(uint64_t commit_id, uint64_t merges, u
     s->block_size = block_size;
     s->num_blocks = num_blocks;
     s->n_docs = n_docs;
+    poisoned_ = true; // until the uploads below have succeeded
     if (num_blocks) {
         GB_CUDA(cudaMalloc(&s->d_blocks, num_blocks * block_size));
         GB_CUDA(cudaMalloc(&s->d_block_index, num_blocks * 4));
@@ -500,19 +504,22 @@ bool GpuSnapshotBuilder::add_file_segment(uint64_t commit_id, uint64_t merges, u
         GB_CUDA(cudaMalloc(&s->d_doc_ids, n_docs * 4));
         GB_CUDA(cudaMemcpy(s->d_doc_ids, doc_ids, n_docs * 4, cudaMemcpyHostToDevice));
     }
+    segs_.push_back(s.release());
+    poisoned_ = false;
     return true;
 }
 
 bool GpuSnapshotBuilder::add_memory_segment(uint64_t commit_id, uint64_t merges, const uint64_t *items, uint64_t n_items,
                                             const uint32_t *doc_ids, uint64_t n_docs) {
+    if (poisoned_) return fail("an earlier segment failed to upload; abort this builder");
     if (!check_order(commit_id, false)) return false;
     if (n_items && !items) return fail("null items");
-    Segment *s = new Segment();
-    segs_.push_back(s);
+    std::unique_ptr<Segment> s(new Segment());
     s->commit_id = commit_id;
     s->merges = merges;
     s->n_items = n_items;
     s->n_docs = n_docs;
+    poisoned_ = true;
     if (n_items) {
         GB_CUDA(cudaMalloc(&s->d_items, n_items * 8));
         GB_CUDA(cudaMemcpy(s->d_items, items, n_items * 8, cudaMemcpyHostToDevice));
@@ -521,6 +528,8 @@ bool GpuSnapshotBuilder::add_memory_segment(uint64_t commit_id, uint64_t merges,
         GB_CUDA(cudaMalloc(&s->d_doc_ids, n_docs * 4));
         GB_CUDA(cudaMemcpy(s->d_doc_ids, doc_ids, n_docs * 4, cudaMemcpyHostToDevice));
     }
+    segs_.push_back(s.release());
+    poisoned_ = false;
     return true;
 }
 
@@ -651,6 +660,7 @@ bool GpuSnapshotBuilder::build_segment(size_t si, bool multi, const void *newest
 }
 
 bool GpuSnapshotBuilder::build(GpuCsr &out) {
+    if (poisoned_) return fail("a segment failed to upload; abort this builder");
     const size_t ns = segs_.size();
     const bool multi = ns > 1;
     Dev<BuildCounters> ctr;

@@ -51,6 +51,9 @@ class GpuSnapshotBuilder {
 
   private:
     struct Segment;
+    struct SegCsr;
+    // decode, flag and select segment si; its raw bytes are freed on the way (newest: the liveness map, ctr: BuildCounters)
+    bool build_segment(size_t si, bool multi, const void *newest, void *ctr, SegCsr &out);
     bool fail(const char *m) {
         error = m;
         return false;
@@ -64,6 +67,7 @@ class GpuSnapshotBuilder {
     bool check_order(uint64_t commit_id, bool is_file);
     std::vector<Segment *> segs_;
     uint32_t lo_ = 0, hi_ = 0;
+    bool poisoned_ = false; // an add_*_segment call failed half way: commit must fail
 };
 
 } // namespace fpx

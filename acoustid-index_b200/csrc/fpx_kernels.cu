@@ -937,11 +937,18 @@ constexpr uint32_t kCandSlots = 64; // candidate table: docid -> exact count
 constexpr uint32_t kCandMax = 48;   // distinct candidates; more -> exact count-table path
 constexpr uint32_t kSketchBytes = kSketchWords * 4;
 
+struct FindMeta { // one per stage: what travels with the staged query
+    WorkItem item;
+    uint32_t row_off[kSketchMaxRows]; // first docid of row r inside the stage
+    uint32_t row_len[kSketchMaxRows]; // postings in row r (without padding)
+    uint32_t hot[kHotCap];            // counters that reached min_score: word * 4 + byte
+    uint32_t n_hot, sum;              // sum: all bytes of the sketch after counting
+};
+
 struct FindState { // private to one resolver group
-    uint32_t hot[kHotCap];
     uint32_t cand_id[kCandSlots], cand_cnt[kCandSlots];
     unsigned long long r_keys[kCandSlots];
-    uint32_t n_hot, n_cand, sum, ovf, r_count;
+    uint32_t n_cand, ovf, r_count;
 };
 
 __device__ __forceinline__ void cand_add(FindState &st, uint32_t pad, uint32_t d, uint32_t c) {
@@ -959,13 +966,19 @@ __device__ __forceinline__ void cand_add(FindState &st, uint32_t pad, uint32_t d
     st.ovf = 1u;
 }
 
+// top 15 bits of row_key(d): the sketch counter of d in row order (bank, rest of the word index, byte)
+__device__ __forceinline__ uint32_t row_counter(uint32_t d) {
+    const uint32_t h = d * kRowMult;
+    return ((h >> 7) & 0x7C00u) | ((h >> 20) & 0x03FCu) | ((h >> 15) & 3u);
+}
+
 template <int STAGES, uint32_t STAGE_U4> constexpr size_t find_smem_bytes() {
     return 2 * (size_t)kSketchBytes + (size_t)STAGES * STAGE_U4 * 16;
 }
 
 template <int CW, int RG, int PW, int STAGES, uint32_t STAGE_U4>
 __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) search_find_kernel(BatchArgs a, uint32_t cls) {
-    static_assert(RG >= 2 && RG <= 3 && STAGES >= 2 && STAGES <= 4, "barrier ids");
+    static_assert(RG >= 1 && RG <= 3 && STAGES >= 2 && STAGES <= 4, "barrier ids");
     constexpr int kFirstResolver = CW;
     constexpr int kFirstProducer = CW + RG * kSkResolverWarps;
     constexpr int kAllThreads = (kFirstProducer + PW) * 32;
@@ -974,7 +987,7 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
     unsigned char *sketch_base = smem_raw; // 2 x 32 KB
     uint4 *stage = reinterpret_cast<uint4 *>(smem_raw + 2 * (size_t)kSketchBytes);
     __shared__ uint64_t full[STAGES]; // TMA completion; every other hand-over is a named barrier
-    __shared__ StageMeta meta[STAGES];
+    __shared__ FindMeta meta[STAGES];
     __shared__ FindState fs[RG];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1003,7 +1016,8 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
         fs[tid / kCandSlots].cand_id[tid % kCandSlots] = pad;
         fs[tid / kCandSlots].cand_cnt[tid % kCandSlots] = 0u;
     }
-    if (tid < RG) fs[tid].n_hot = fs[tid].n_cand = fs[tid].sum = fs[tid].ovf = 0u;
+    if (tid < RG) fs[tid].n_cand = fs[tid].ovf = 0u;
+    if (tid < STAGES) meta[tid].n_hot = meta[tid].sum = 0u;
     __syncthreads();
 
     if (warp >= kFirstProducer) {
@@ -1075,7 +1089,7 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
     }
 
     if (warp >= kFirstResolver) {
-        // ===== resolvers: group gidx takes every RG-th query; query `it` used sketch it & 1
+        // ===== resolvers: group gidx takes every RG-th query
         const uint32_t gidx = (warp - kFirstResolver) / kSkResolverWarps;
         const uint32_t rwarp = (warp - kFirstResolver) % kSkResolverWarps;
         const uint32_t rtid = rwarp * 32 + lane;
@@ -1085,110 +1099,85 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
         for (uint32_t it = gidx;; it += RG) {
             const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
             if (idx >= count) break;
-            const uint32_t s = it % STAGES, b = it & 1u;
-            uint4 *sk4 = reinterpret_cast<uint4 *>(sketch_base + (size_t)b * kSketchBytes);
-            // the sketch's next tenant is this CTA's query it + 2: clear to its bias
-            const unsigned long long idx2 = idx + 2ull * gridDim.x;
-            const uint32_t ms2 = idx2 < count ? items[idx2].min_score : 2u;
+            const uint32_t s = it % STAGES;
+            FindMeta &m = meta[s];
             const long long tr0 = clock64();
-            named_sync(kBarCounted + gidx, kCounters + kSkResolvers); // all counter warps are done with query it
+            named_sync(kBarCounted + gidx, kCounters + kSkResolvers); // the counters counted query it and read the sketch back
             if (gidx == 0 && rtid == 0) tick(3, tr0);
-            const WorkItem w = meta[s].item;
-            // read the sketch back: hot counters (bit 7 of a byte), the byte sum, and the clear for query it + 2
-            {
-                const uint32_t b2 = (0x80u - ms2) * 0x01010101u;
-                const uint4 clear4 = make_uint4(b2, b2, b2, b2);
-                uint32_t acc = 0;
-#pragma unroll 4
-                for (uint32_t i = rtid; i < kSketchWords / 4; i += kSkResolvers) {
-                    const uint4 v = sk4[i];
-                    if (!(a.debug & 16u)) sk4[i] = clear4;
-                    acc = __dp4a(v.x, 0x01010101u, acc);
-                    acc = __dp4a(v.y, 0x01010101u, acc);
-                    acc = __dp4a(v.z, 0x01010101u, acc);
-                    acc = __dp4a(v.w, 0x01010101u, acc);
-                    if ((v.x | v.y | v.z | v.w) & 0x80808080u) {
-                        const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll 1
-                        for (uint32_t e = 0; e < 4; ++e) {
-                            uint32_t m = ws[e] & 0x80808080u;
-                            while (m) {
-                                const uint32_t bit = __ffs(m) - 1u;
-                                m &= m - 1u;
-                                const uint32_t pos = atomicAdd(&st.n_hot, 1u);
-                                if (pos < kHotCap) st.hot[pos] = ((i * 4u + e) << 2) | (bit >> 3); // word * 4 + byte
-                            }
-                        }
-                    }
-                }
-                acc = __reduce_add_sync(0xFFFFFFFFu, acc);
-                if (lane == 0) atomicAdd(&st.sum, acc);
-            }
-            R.sync();
-            if (rwarp == 0) named_arrive(kBarSkFree + b, kCounters + 32); // the counters may start query it + 2 on this sketch
-            if (gidx == 0 && rtid == 0) tick(4, tr0);
-            const uint32_t n_hot = (a.debug & 2u) ? 0u : st.n_hot;
+            const WorkItem w = m.item;
+            const uint32_t n_hot = (a.debug & 2u) ? 0u : m.n_hot;
             // no byte carried <=> the bytes add up to the bias of every counter plus one per staged posting
-            bool redo = st.sum != 32768u * (0x80u - w.min_score) + 4u * w.total4 && !(a.debug & 3u);
+            bool redo = m.sum != 32768u * (0x80u - w.min_score) + 4u * w.total4 && !(a.debug & 3u);
             redo = redo || n_hot > kHotCap;
             uint32_t n = 0;
             if (n_hot != 0u && !redo) {
                 // find the postings of the hot counters: thread rtid owns row rtid of the stage (<= 128 rows); the
-                // postings of counter c are the range of row keys with top 15 bits == c's place in the row order
+                // postings of counter c are the range of the row whose keys start with c's place in the row order.
+                // Shared memory answers slowly under the counters' atomics (several hundred cycles), so the lower
+                // bound is a 9-ary search: eight independent probes per round, two rounds for a row of <= 80.
                 const bool has_row = rtid < w.n_rows;
                 const uint32_t *row = reinterpret_cast<const uint32_t *>(stage + (size_t)s * STAGE_U4) +
-                                      (has_row ? meta[s].row_off[rtid] : 0u);
-                const uint32_t len = has_row ? meta[s].row_len[rtid] : 0u;
-                const uint32_t top = 1u << (31 - __clz(len | 1u));
-                for (uint32_t c = 0; c < n_hot; c += 4) {
-                    const uint32_t nj = min(4u, n_hot - c); // the same for every thread
-                    uint32_t kp[4], lo[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t hc = (uint32_t)j < nj ? st.hot[c + j] : 0u;
-                        const uint32_t wd = hc >> 2;
-                        kp[j] = ((wd & 31u) << 27) | ((wd >> 5) << 19) | ((hc & 3u) << 17); // row_key of the range start
-                        lo[j] = 0;
-                    }
-                    for (uint32_t step = top; step; step >>= 1) { // lower bound by halving steps, four chains interleaved
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t probe = lo[j] + step;
-                            if ((uint32_t)j < nj && probe <= len && row_key(row[probe - 1]) < kp[j]) lo[j] = probe;
-                        }
-                    }
+                                      (has_row ? m.row_off[rtid] : 0u);
+                const uint32_t len = has_row ? m.row_len[rtid] : 0u;
 #pragma unroll 1
-                    for (uint32_t j = 0; j < nj; ++j) {
-                        const uint32_t kpj = j == 0 ? kp[0] : j == 1 ? kp[1] : j == 2 ? kp[2] : kp[3];
-                        uint32_t pos = j == 0 ? lo[0] : j == 1 ? lo[1] : j == 2 ? lo[2] : lo[3];
-                        uint32_t d = pos < len ? row[pos] : 0u;
-                        const bool has = pos < len && ((row_key(d) ^ kpj) >> 17) == 0u;
-                        // a true match is found in most rows: one table update per warp and docid, not one per row
-                        uint32_t act = __ballot_sync(0xFFFFFFFFu, has);
-                        while (act) {
-                            const uint32_t leader = __ffs(act) - 1u;
-                            const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, d, leader);
-                            const uint32_t same = __ballot_sync(0xFFFFFFFFu, has && d == d0);
-                            if (lane == leader) cand_add(st, pad, d0, __popc(same));
-                            act &= ~same;
+                for (uint32_t c = 0; c < n_hot; ++c) {
+                    const uint32_t hc = m.hot[c];
+                    const uint32_t ctr = (((hc >> 2) & 31u) << 10) | ((hc >> 7) << 2) | (hc & 3u); // counter in row order
+                    uint32_t lo = 0, hi = len; // everything before lo is below ctr, everything from hi on is not
+                    while (hi - lo > 8u) {
+                        const uint32_t step = (hi - lo) / 9u + 1u;
+                        uint32_t below = 0;
+#pragma unroll
+                        for (uint32_t j = 1; j <= 8; ++j) {
+                            const uint32_t pj = lo + j * step - 1u;
+                            if (pj < hi && row_counter(row[pj]) < ctr) ++below; // pivots below ctr form a prefix
                         }
-                        // further postings of this counter in my row: repeated (hash, id) pairs, other docids
-                        if (has) {
-                            for (++pos; pos < len; ++pos) {
-                                d = row[pos];
-                                if (((row_key(d) ^ kpj) >> 17) != 0u) break;
-                                cand_add(st, pad, d, 1u);
-                            }
+                        const uint32_t nxt = lo + (below + 1u) * step - 1u; // first pivot not below ctr, if it exists
+                        if (below < 8u && nxt < hi) hi = nxt;
+                        lo += below * step;
+                    }
+                    {
+                        uint32_t below = 0;
+#pragma unroll
+                        for (uint32_t j = 0; j < 8; ++j)
+                            if (lo + j < hi && row_counter(row[lo + j]) < ctr) ++below;
+                        lo += below;
+                    }
+                    uint32_t pos = lo;
+                    uint32_t d = pos < len ? row[pos] : 0u;
+                    const bool has = pos < len && row_counter(d) == ctr;
+                    // a true match is found in most rows: one table update per warp and docid, not one per row
+                    uint32_t act = __ballot_sync(0xFFFFFFFFu, has);
+                    while (act) {
+                        const uint32_t leader = __ffs(act) - 1u;
+                        const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, d, leader);
+                        const uint32_t same = __ballot_sync(0xFFFFFFFFu, has && d == d0);
+                        if (lane == leader) cand_add(st, pad, d0, __popc(same));
+                        act &= ~same;
+                    }
+                    // further postings of this counter in my row: repeated (hash, id) pairs, other docids
+                    if (has) {
+                        for (++pos; pos < len; ++pos) {
+                            d = row[pos];
+                            if (row_counter(d) != ctr) break;
+                            cand_add(st, pad, d, 1u);
                         }
                     }
                 }
-                R.sync();
-                redo = st.ovf != 0u;
-                if (rwarp == 0 && !redo) { // common.zig:140-145: keep score >= min_score
+            }
+            R.sync(); // everyone has read the stage and its meta
+            if (gidx == 0 && rtid == 0) tick(11, tr0);
+            if (rwarp == 0) { // the stage goes back to the producers
+                if (lane == 0) m.n_hot = m.sum = 0u;
+                named_arrive(kBarStage + s, 32 * PW + 32);
+                redo = redo || st.ovf != 0u;
+                if (n_hot != 0u) { // common.zig:140-145: keep score >= min_score; the table is left empty for the next query
                     uint32_t base = 0;
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         const uint32_t id = st.cand_id[lane + 32 * half], cn = st.cand_cnt[lane + 32 * half];
+                        st.cand_id[lane + 32 * half] = pad;
+                        st.cand_cnt[lane + 32 * half] = 0u;
                         const bool keep = id != pad && cn >= w.min_score;
                         const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
                         if (keep) st.r_keys[base + __popc(km & ((1u << lane) - 1u))] = rank_key(cn, id);
@@ -1196,14 +1185,6 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
                     }
                     n = base;
                     __syncwarp();
-                }
-            }
-            if (gidx == 0 && rtid == 0) tick(11, tr0);
-            if (rwarp == 0) { // the stage goes back to the producers
-                named_arrive(kBarStage + s, 32 * PW + 32);
-                if (n_hot != 0u) { // the group's table, for its next query (this warp was its last reader)
-                    st.cand_id[lane] = st.cand_id[lane + 32] = pad;
-                    st.cand_cnt[lane] = st.cand_cnt[lane + 32] = 0u;
                 }
                 if (redo) {
                     if (lane == 0) {
@@ -1217,11 +1198,11 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
                     group_emit_results(W, a, w, st.r_keys, n, &st.r_count);
                 }
                 if (lane == 0) {
-                    st.n_hot = st.n_cand = st.sum = st.ovf = 0u;
+                    st.n_cand = st.ovf = 0u;
                     if (a.stats && !redo) atomicAdd(&a.stats->sketch_queries, 1ull);
                 }
             }
-            R.sync(); // the group's scratch is reused by its next query
+            R.sync(); // the group's table is reused by its next query
             if (gidx == 0 && rtid == 0) {
                 tick(5, tr0);
                 if (timed) atomicAdd(&a.stats->dbg[6], 1ull);
@@ -1230,14 +1211,16 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
         return;
     }
 
-    // ===== counters: each warp streams its slice of every query and arrives on `counted`
+    // ===== counters: count query it into sketch it & 1, then (all of them together) read that sketch back: byte sum,
+    // hot counters, and the clear to the bias of its next tenant, this CTA's query it + 2
+    constexpr int kScan = (int)((kSketchWords / 4 + kCounters - 1) / kCounters); // 16-byte pieces of the sketch per thread
     for (uint32_t it = 0;; ++it) {
         const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
         if (idx >= count) break;
         const uint32_t s = it % STAGES, b = it & 1u;
+        const unsigned long long idx2 = idx + 2ull * gridDim.x;
+        const uint32_t ms2 = idx2 < count ? items[idx2].min_score : 2u;
         const long long tc0 = clock64();
-        if (it >= 2) // sketch b was read back and cleared by the resolvers of query it - 2
-            named_sync(kBarSkFree + b, kCounters + 32);
         if (warp == 0) { // one warp polls the TMA completion, the others park on a named barrier
             if (lane == 0) {
                 mbar_wait(&full[s], (it / STAGES) & 1, 0);
@@ -1246,7 +1229,8 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
             __syncwarp();
         }
         named_sync(kBarCounters, kCounters);
-        const uint32_t total4 = meta[s].item.total4;
+        FindMeta &m = meta[s];
+        const uint32_t total4 = m.item.total4;
         const uint4 *sg = stage + (size_t)s * STAGE_U4;
         const uint32_t boff = b * kSketchBytes; // folded into the address by the same LOP3 that masks the word offset
         // Row padding is made of unused docids spread over many values: counted like anything else (the byte sum
@@ -1270,8 +1254,45 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
             }
             for (; i < total4; i += kCounters) add4(sg[i]);
         }
+        if (warp == 0 && lane == 0) tick(8, tc0);
+        named_sync(kBarCounters, kCounters); // every counter warp is done with query it
+        {
+            uint4 *sk4 = reinterpret_cast<uint4 *>(sketch_base + boff);
+            const uint32_t b2 = (0x80u - ms2) * 0x01010101u;
+            const uint4 clear4 = make_uint4(b2, b2, b2, b2);
+            uint4 v[kScan];
+#pragma unroll
+            for (int k = 0; k < kScan; ++k) { // all loads first: shared memory answers slowly under the atomics
+                const uint32_t i = tid + (uint32_t)k * kCounters;
+                v[k] = i < kSketchWords / 4 ? sk4[i] : make_uint4(0u, 0u, 0u, 0u);
+            }
+            uint32_t acc = 0;
+#pragma unroll
+            for (int k = 0; k < kScan; ++k) {
+                const uint32_t i = tid + (uint32_t)k * kCounters;
+                if (i < kSketchWords / 4 && !(a.debug & 16u)) sk4[i] = clear4;
+                acc = __dp4a(v[k].x, 0x01010101u, acc);
+                acc = __dp4a(v[k].y, 0x01010101u, acc);
+                acc = __dp4a(v[k].z, 0x01010101u, acc);
+                acc = __dp4a(v[k].w, 0x01010101u, acc);
+                if ((v[k].x | v[k].y | v[k].z | v[k].w) & 0x80808080u) { // rare: a counter at bias + min_score or more
+#pragma unroll 1
+                    for (uint32_t e = 0; e < 4; ++e) {
+                        uint32_t hm = (e == 0 ? v[k].x : e == 1 ? v[k].y : e == 2 ? v[k].z : v[k].w) & 0x80808080u;
+                        while (hm) {
+                            const uint32_t bit = __ffs(hm) - 1u;
+                            hm &= hm - 1u;
+                            const uint32_t pos = atomicAdd(&m.n_hot, 1u);
+                            if (pos < kHotCap) m.hot[pos] = ((i * 4u + e) << 2) | (bit >> 3); // word * 4 + byte
+                        }
+                    }
+                }
+            }
+            acc = __reduce_add_sync(0xFFFFFFFFu, acc);
+            if (lane == 0) atomicAdd(&m.sum, acc);
+        }
         __syncwarp();
-        named_arrive(kBarCounted + it % RG, kCounters + kSkResolvers); // my slice of query it is in the sketch
+        named_arrive(kBarCounted + it % RG, kCounters + kSkResolvers); // query it is counted and read back
         if (warp == 0 && lane == 0) {
             tick(9, tc0);
             if (timed) atomicAdd(&a.stats->dbg[10], 1ull);
@@ -1692,7 +1713,7 @@ __global__ void __launch_bounds__(256) result_pack_kernel(const uint32_t *ids, c
 // ------------------------------------------------------------------------------------------------
 // Warp split of the hot kernel: counter / resolver-group / producer warps (FPX_DEBUG_ABLATE bits 24..27 pick another
 // one for A/B runs).
-#define FPX_FIND_CONFIGS(X) X(0, 12, 3, 8) X(1, 14, 3, 6) X(2, 10, 3, 10) X(3, 8, 3, 12) X(4, 12, 2, 12) X(5, 16, 2, 8) X(6, 8, 2, 16)
+#define FPX_FIND_CONFIGS(X) X(0, 12, 3, 8) X(1, 14, 2, 10) X(2, 10, 3, 10) X(3, 16, 2, 8) X(4, 12, 2, 12) X(5, 14, 3, 6) X(6, 10, 2, 14) X(7, 18, 1, 10)
 
 cudaError_t configure_kernels() {
     cudaError_t e;

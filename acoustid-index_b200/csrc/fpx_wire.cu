@@ -267,17 +267,21 @@ fpx_status fpx_legacy_parse_fingerprint(const char *text, uint64_t len, uint32_t
 // legacy.zig:203-208: "id:score id:score ..."
 fpx_status fpx_legacy_format_results(const uint32_t *ids, const uint32_t *scores, uint32_t n, uint8_t **out, uint64_t *out_size) {
     if (!out || !out_size || (n && (!ids || !scores))) return bad("null argument");
-    std::string s;
-    char tmp[32];
-    for (uint32_t i = 0; i < n; ++i) {
-        std::snprintf(tmp, sizeof tmp, "%s%u:%u", i ? " " : "", ids[i], scores[i]);
-        s += tmp;
+    try { // no exception may cross the C boundary
+        std::string s;
+        char tmp[32];
+        for (uint32_t i = 0; i < n; ++i) {
+            std::snprintf(tmp, sizeof tmp, "%s%u:%u", i ? " " : "", ids[i], scores[i]);
+            s += tmp;
+        }
+        uint8_t *mem = static_cast<uint8_t *>(std::malloc(std::max<size_t>(s.size(), 1)));
+        if (!mem) return FPX_OUT_OF_MEMORY;
+        std::memcpy(mem, s.data(), s.size());
+        *out = mem;
+        *out_size = s.size();
+    } catch (const std::bad_alloc &) {
+        return FPX_OUT_OF_MEMORY;
     }
-    uint8_t *mem = static_cast<uint8_t *>(std::malloc(std::max<size_t>(s.size(), 1)));
-    if (!mem) return FPX_OUT_OF_MEMORY;
-    std::memcpy(mem, s.data(), s.size());
-    *out = mem;
-    *out_size = s.size();
     return FPX_OK;
 }
 
