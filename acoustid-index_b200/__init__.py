@@ -9,6 +9,6 @@ from . import _ffi, index, synth  # noqa: F401  (multi_gpu is imported on demand
 from ._ffi import FpxError, build as build_library, lib  # noqa: F401
 from .index import (WIRE_JSON, WIRE_MSGPACK, Batcher, Context, FileSegment, decode_search_request,
                     encode_search_response, legacy_format_results, legacy_parse_fingerprint, IndexReader, MemorySegment, SearchOptions, SearchRequest,  # noqa: F401
-                    SearchResult, Snapshot, SnapshotBuilder, merge_shard_results, multi_index_search,
+                    SearchResult, Snapshot, SnapshotBuilder, merge_packed_shards_device, merge_shard_results, multi_index_search,
                     open_index_dir, pack_results_device, parse_manifest, segment_file_bytes, segment_file_name,
                     SegmentFile, swap_snapshot, unpack_results)

@@ -108,7 +108,8 @@ EXPORTS = [
     "fpx_snapshot_set_doc_range", "fpx_snapshot_compile", "fpx_snapshot_csr", "fpx_snapshot_commit",
     "fpx_snapshot_abort", "fpx_snapshot_acquire", "fpx_snapshot_release", "fpx_snapshot_get_info",
     "fpx_snapshot_row_lengths", "fpx_snapshot_read_row", "fpx_default_min_score", "fpx_search", "fpx_search_batch",
-    "fpx_search_batch_device", "fpx_merge_shard_results", "fpx_profile_reset", "fpx_profile_read", "fpx_debug_set", "fpx_set_chunk_queries", "fpx_set_profile", "fpx_pack_results_device",
+    "fpx_search_batch_packed",
+    "fpx_search_batch_device", "fpx_merge_shard_results", "fpx_profile_reset", "fpx_profile_read", "fpx_debug_set", "fpx_set_chunk_queries", "fpx_set_profile", "fpx_pack_results_device", "fpx_merge_packed_shards_device",
     "fpx_segment_write", "fpx_segment_buf_blocks", "fpx_segment_buf_block_index",
     "fpx_segment_buf_num_blocks", "fpx_segment_buf_num_items", "fpx_segment_buf_block_size",
     "fpx_segment_buf_free", "fpx_block_decode",
@@ -173,7 +174,9 @@ def lib():
     L.fpx_debug_set.argtypes = [vp, C.c_uint32]
     L.fpx_set_chunk_queries.argtypes = [vp, C.c_uint32]
     L.fpx_set_profile.argtypes = [vp, C.c_int]
+    L.fpx_search_batch_packed.argtypes = [vp, C.c_uint64, vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, vp]
     L.fpx_pack_results_device.argtypes = [C.c_uint64, C.c_uint32, vp, vp, vp, vp, C.c_uint32, vp]
+    L.fpx_merge_packed_shards_device.argtypes = [C.c_uint32, C.c_uint64, vp, C.c_uint64, vp, C.c_uint32, vp, vp, vp, vp]
     L.fpx_wire_decode_search_request.argtypes = [C.c_uint32, C.c_char_p, C.c_uint64, C.POINTER(WireSearchRequest)]
     L.fpx_wire_encode_search_response.argtypes = [C.c_uint32, vp, vp, C.c_uint32, C.POINTER(vp), u64p]
     L.fpx_legacy_parse_fingerprint.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(u32p), u64p]

@@ -545,7 +545,7 @@ fpx_status fpx_snapshot_add_memory_segment(fpx_snapshot_builder *b, const fpx_me
 
 fpx_status fpx_snapshot_set_doc_range(fpx_snapshot_builder *b, uint32_t lo, uint32_t hi) {
     if (!b) return set_error(FPX_INVALID_ARGUMENT, "null argument");
-    if (hi < lo) return set_error(FPX_INVALID_ARGUMENT, "hi < lo");
+    if (hi != 0 && hi < lo) return set_error(FPX_INVALID_ARGUMENT, "hi < lo");
     b->compiler.set_doc_range(lo, hi);
     if (b->gpu) b->gpu->set_doc_range(lo, hi);
     return FPX_OK;
@@ -767,12 +767,22 @@ fpx_status fpx_search_batch_device(fpx_snapshot *s, uint64_t n_queries, const ui
     return rc;
 }
 
-fpx_status fpx_search_batch(fpx_snapshot *s, uint64_t n_queries, const uint32_t *terms, const uint64_t *term_offsets,
-                            const fpx_search_opts *opts, uint32_t k_stride, uint32_t *out_ids, uint32_t *out_scores,
-                            uint32_t *out_counts) {
+} // extern "C"
+
+namespace {
+
+struct PackedOut { // results as {count per query, (id, score) pairs back to back} instead of k_stride-wide arrays
+    uint32_t *pairs;
+    uint64_t capacity; // in pairs
+    uint64_t n_pairs;  // needed
+};
+
+fpx_status search_batch_host(fpx_snapshot *s, uint64_t n_queries, const uint32_t *terms, const uint64_t *term_offsets,
+                             const fpx_search_opts *opts, uint32_t k_stride, uint32_t *out_ids, uint32_t *out_scores,
+                             uint32_t *out_counts, PackedOut *packed) {
     if (!s) return set_error(FPX_INVALID_ARGUMENT, "null snapshot");
     if (n_queries == 0) return FPX_OK;
-    if (!term_offsets || !opts || !out_counts || (k_stride && (!out_ids || !out_scores)))
+    if (!term_offsets || !opts || !out_counts || (!packed && k_stride && (!out_ids || !out_scores)))
         return set_error(FPX_INVALID_ARGUMENT, "null buffer");
     if (k_stride > FPX_MAX_RESULTS) return set_error(FPX_UNSUPPORTED, "k_stride exceeds FPX_MAX_RESULTS");
     if (n_queries > 0x7FFFFFFFull) return set_error(FPX_INVALID_ARGUMENT, "batch too large (split it)");
@@ -822,8 +832,8 @@ fpx_status fpx_search_batch(fpx_snapshot *s, uint64_t n_queries, const uint32_t 
     // chunk by chunk (the copy engine is otherwise idle and the calling thread has nothing to do).  Otherwise
     // (pageable memory) the GPU packs them to {count, (id, score) pairs} in the library's own pinned memory and
     // the calling thread scatters them.
-    bool dma_out = true;
-    {
+    bool dma_out = packed == nullptr;
+    if (dma_out) {
         const void *outs[3] = {out_counts, k_stride ? out_ids : out_counts, k_stride ? out_scores : out_counts};
         for (const void *p : outs) {
             cudaPointerAttributes at{};
@@ -947,7 +957,7 @@ fpx_status fpx_search_batch(fpx_snapshot *s, uint64_t n_queries, const uint32_t 
             hp += n;
         }
     };
-    const unsigned n_helpers = (!dma_out && n_queries >= 16384) ? std::min(3u, ctx->host_threads > 1 ? ctx->host_threads - 1 : 0u) : 0u;
+    const unsigned n_helpers = (!dma_out && !packed && n_queries >= 16384) ? std::min(3u, ctx->host_threads > 1 ? ctx->host_threads - 1 : 0u) : 0u;
     std::mutex jm;
     std::condition_variable jcv;
     std::deque<Job> jobs;
@@ -984,6 +994,17 @@ fpx_status fpx_search_batch(fpx_snapshot *s, uint64_t n_queries, const uint32_t 
             continue;
         }
         const uint2 *hp = w->h_pairs + pair_base[c];
+        if (packed) { // the chunk's counts and pairs as they are: two contiguous copies
+            uint64_t o = 0;
+            for (uint64_t q = q0; q < q1; ++q) o += w->h_counts[q];
+            std::memcpy(out_counts + q0, w->h_counts + q0, nq * sizeof(uint32_t));
+            const uint64_t room = packed->n_pairs < packed->capacity ? packed->capacity - packed->n_pairs : 0;
+            if (std::min(o, room)) std::memcpy(packed->pairs + 2 * packed->n_pairs, hp, std::min(o, room) * sizeof(uint2));
+            packed->n_pairs += o;
+            d2h_bytes += nq * 4 + o * 8;
+            if (tracing) tr[c].host_col1 = host_ms();
+            continue;
+        }
         const unsigned parts = (n_helpers && nq >= 4096) ? n_helpers + 1 : 1;
         Job mine{q0, q1, hp};
         if (parts > 1) {
@@ -1041,6 +1062,29 @@ fpx_status fpx_search_batch(fpx_snapshot *s, uint64_t n_queries, const uint32_t 
     return rc;
 }
 
+} // namespace
+
+extern "C" {
+
+fpx_status fpx_search_batch(fpx_snapshot *s, uint64_t n_queries, const uint32_t *terms, const uint64_t *term_offsets,
+                            const fpx_search_opts *opts, uint32_t k_stride, uint32_t *out_ids, uint32_t *out_scores,
+                            uint32_t *out_counts) {
+    return search_batch_host(s, n_queries, terms, term_offsets, opts, k_stride, out_ids, out_scores, out_counts, nullptr);
+}
+
+fpx_status fpx_search_batch_packed(fpx_snapshot *s, uint64_t n_queries, const uint32_t *terms, const uint64_t *term_offsets,
+                                   const fpx_search_opts *opts, uint32_t k_stride, uint32_t *out_counts, uint32_t *out_pairs,
+                                   uint64_t capacity_pairs, uint64_t *out_n_pairs) {
+    if (!out_n_pairs || (capacity_pairs && !out_pairs)) return set_error(FPX_INVALID_ARGUMENT, "null buffer");
+    PackedOut po{out_pairs, capacity_pairs, 0};
+    *out_n_pairs = 0;
+    const fpx_status rc = search_batch_host(s, n_queries, terms, term_offsets, opts, k_stride, nullptr, nullptr, out_counts, &po);
+    *out_n_pairs = po.n_pairs;
+    if (rc == FPX_OK && po.n_pairs > capacity_pairs)
+        return set_error(FPX_INVALID_ARGUMENT, "out_pairs too small: *out_n_pairs pairs are needed (counts are complete)");
+    return rc;
+}
+
 fpx_status fpx_search(fpx_snapshot *s, const uint32_t *terms, uint64_t n_terms, const fpx_search_opts *opts,
                       uint32_t *out_ids, uint32_t *out_scores, uint32_t capacity, uint32_t *out_count) {
     if (!opts || !out_count) return set_error(FPX_INVALID_ARGUMENT, "null argument");
@@ -1063,6 +1107,22 @@ fpx_status fpx_pack_results_device(uint64_t n_queries, uint32_t k_stride, const 
     launch_result_pack(d_ids, d_scores, d_counts, d_packed + n, n, k_stride, d_packed,
                        reinterpret_cast<uint2 *>(d_packed + 2 * (size_t)n + 2), static_cast<cudaStream_t>(cuda_stream),
                        capacity_pairs);
+    FPX_CUDA(cudaGetLastError());
+    return FPX_OK;
+}
+
+fpx_status fpx_merge_packed_shards_device(uint32_t n_shards, uint64_t n_queries, const uint32_t *d_packed,
+                                          uint64_t shard_stride_words, const fpx_search_opts *d_opts, uint32_t k_stride,
+                                          uint32_t *d_out_ids, uint32_t *d_out_scores, uint32_t *d_out_counts, void *cuda_stream) {
+    if (n_queries == 0) return FPX_OK;
+    if (n_shards == 0 || n_shards > 32) return set_error(FPX_INVALID_ARGUMENT, "1..32 shards");
+    if (n_queries > 0x7FFFFFFFull) return set_error(FPX_INVALID_ARGUMENT, "batch too large (split it)");
+    if (!d_packed || !d_opts || !d_out_counts || (k_stride && (!d_out_ids || !d_out_scores)))
+        return set_error(FPX_INVALID_ARGUMENT, "null buffer");
+    if (shard_stride_words < 2 * n_queries + 2) return set_error(FPX_INVALID_ARGUMENT, "shard stride shorter than a packed header");
+    launch_merge_packed_shards(d_packed, shard_stride_words, n_shards, (uint32_t)n_queries,
+                               reinterpret_cast<const SearchOpts *>(d_opts), k_stride, d_out_ids, d_out_scores, d_out_counts,
+                               static_cast<cudaStream_t>(cuda_stream));
     FPX_CUDA(cudaGetLastError());
     return FPX_OK;
 }

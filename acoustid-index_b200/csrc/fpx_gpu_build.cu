@@ -265,7 +265,7 @@ __global__ void keep_flags_kernel(const unsigned long long *keys, unsigned long 
             ++sup;
             return 0;
         }
-        if (ranged && !(id >= lo && id < hi)) {
+        if (ranged && !(id >= lo && (hi == 0u || id < hi))) { // hi == 0 with lo > 0: open-ended
             ++oor;
             return 0;
         }

@@ -554,7 +554,7 @@ struct ResolverState { // private to one resolver group
 
 // named barrier ids (0 is __syncthreads): resolver groups 1..3, counters 4, stage release 5..8, "counted" 9..11 (one
 // per resolver group: two groups must never wait on the same id), "sketch free" 12..13 (one per sketch)
-constexpr uint32_t kBarGroup = 1, kBarCounters = 4, kBarStage = 5, kBarCounted = 9, kBarSkFree = 12;
+constexpr uint32_t kBarGroup = 1, kBarCounters = 4, kBarStage = 5, kBarCounted = 9, kBarSkFree = 12, kBarTaken = 12;
 
 template <int kSkCounterWarps, int kSkResolverGroups, int kSkProducerWarps>
 __global__ void __launch_bounds__((kSkCounterWarps + kSkResolverGroups * kSkResolverWarps + kSkProducerWarps) * 32, 1)
@@ -1103,6 +1103,9 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
             FindMeta &m = meta[s];
             const long long tr0 = clock64();
             named_sync(kBarCounted + gidx, kCounters + kSkResolvers); // the counters counted query it and read the sketch back
+            // `counted` is free for the group's next query: nothing else keeps the counters from running RG queries
+            // ahead and arriving on it a second time before this sync
+            if (rwarp == 0) named_arrive(kBarTaken + gidx, kCounters + 32);
             if (gidx == 0 && rtid == 0) tick(3, tr0);
             const WorkItem w = m.item;
             const uint32_t n_hot = (a.debug & 2u) ? 0u : m.n_hot;
@@ -1292,6 +1295,7 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
             if (lane == 0) atomicAdd(&m.sum, acc);
         }
         __syncwarp();
+        if (it >= (uint32_t)RG) named_sync(kBarTaken + it % RG, kCounters + 32); // the group has taken query it - RG
         named_arrive(kBarCounted + it % RG, kCounters + kSkResolvers); // query it is counted and read back
         if (warp == 0 && lane == 0) {
             tick(9, tc0);
@@ -1657,53 +1661,130 @@ __global__ void __launch_bounds__(kThreads) search_wide_kernel(BatchArgs a) {
 // arrays are packed to {count per query, (id, score) pairs back to back} and written straight into mapped
 // pinned host memory — the device-to-host traffic is the results, not the padding.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) result_offsets_kernel(const uint32_t *counts, uint32_t n, uint32_t k_stride,
-                                                               uint32_t *offsets /* n+1 */) {
-    __shared__ uint32_t warp_sum[32];
-    __shared__ uint32_t carry;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry = 0;
+// exclusive scan of the per-query result counts in three small steps (any batch size, all SMs):
+//   1. every block of 1024 queries leaves its total in offsets[first query of the block]
+//   2. one block scans those totals in place (they become the blocks' bases) and writes offsets[n] = number of pairs
+//   3. the pack kernel scans inside its block on top of the base
+constexpr uint32_t kPackBlock = 1024;
+
+__device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t *warp_sum /* 32 */, uint32_t &total) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (uint32_t)o) incl += y;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
     __syncthreads();
-    for (uint32_t base = 0; base < n; base += 1024) {
-        const uint32_t q = base + tid;
-        const uint32_t c = q < n ? min(counts[q], k_stride) : 0u;
-        uint32_t incl = c;
+    if (warp == 0) {
+        const uint32_t ws = warp_sum[lane];
+        uint32_t wi = ws;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= (uint32_t)o) incl += y;
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+            if (lane >= (uint32_t)o) wi += y;
         }
-        if (lane == 31) warp_sum[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t ws = warp_sum[lane], wi = ws;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-                if (lane >= (uint32_t)o) wi += y;
-            }
-            warp_sum[lane] = wi - ws; // exclusive prefix of the warp totals
-        }
-        __syncthreads();
-        const uint32_t c0 = carry;
-        if (q < n) offsets[q] = c0 + warp_sum[warp] + incl - c;
-        __syncthreads();
-        if (tid == 1023) carry = c0 + warp_sum[31] + incl;
-        __syncthreads();
+        warp_sum[lane] = wi - ws; // exclusive prefix of the warp totals
+        if (lane == 31) warp_sum[32] = wi;
     }
-    if (tid == 0) offsets[n] = carry;
+    __syncthreads();
+    total = warp_sum[32];
+    const uint32_t r = warp_sum[warp] + incl - v;
+    __syncthreads(); // warp_sum may be reused by the caller's next round
+    return r;
 }
 
-__global__ void __launch_bounds__(256) result_pack_kernel(const uint32_t *ids, const uint32_t *scores, const uint32_t *counts,
-                                                           const uint32_t *offsets, uint32_t n, uint32_t k_stride,
-                                                           uint32_t *out_counts, uint2 *out_pairs, uint32_t capacity) {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kPackBlock) pack_block_sums_kernel(const uint32_t *counts, uint32_t n, uint32_t k_stride,
+                                                                      uint32_t *offsets) {
+    __shared__ uint32_t warp_sum[33];
+    const uint32_t q = blockIdx.x * kPackBlock + threadIdx.x;
+    uint32_t total;
+    block_excl_scan_1024(q < n ? min(counts[q], k_stride) : 0u, warp_sum, total);
+    if (threadIdx.x == 0) offsets[(size_t)blockIdx.x * kPackBlock] = total;
+}
+
+__global__ void __launch_bounds__(kPackBlock) pack_scan_sums_kernel(uint32_t *offsets, uint32_t n) {
+    __shared__ uint32_t warp_sum[33];
+    const uint32_t n_blocks = (n + kPackBlock - 1) / kPackBlock;
+    uint32_t carry = 0;
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += kPackBlock) {
+        const uint32_t b = b0 + threadIdx.x;
+        const uint32_t v = b < n_blocks ? offsets[(size_t)b * kPackBlock] : 0u;
+        uint32_t total;
+        const uint32_t ex = block_excl_scan_1024(v, warp_sum, total);
+        if (b < n_blocks) offsets[(size_t)b * kPackBlock] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) offsets[n] = carry;
+}
+
+__global__ void __launch_bounds__(kPackBlock) result_pack_kernel(const uint32_t *ids, const uint32_t *scores, const uint32_t *counts,
+                                                                  uint32_t *offsets, uint32_t n, uint32_t k_stride,
+                                                                  uint32_t *out_counts, uint2 *out_pairs, uint32_t capacity) {
+    __shared__ uint32_t warp_sum[33];
+    const uint32_t q = blockIdx.x * kPackBlock + threadIdx.x;
+    const uint32_t c = q < n ? min(counts[q], k_stride) : 0u;
+    const uint32_t base = offsets[(size_t)blockIdx.x * kPackBlock]; // read by every thread before thread 0 rewrites it
+    uint32_t total;
+    const uint32_t o = base + block_excl_scan_1024(c, warp_sum, total);
     if (q >= n) return;
-    const uint32_t c = min(counts[q], k_stride);
+    offsets[q] = o;
     out_counts[q] = c;
-    const uint32_t o = offsets[q];
     for (uint32_t j = 0; j < c && o + j < capacity; ++j)
         out_pairs[o + j] = make_uint2(ids[(size_t)q * k_stride + j], scores[(size_t)q * k_stride + j]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// docid-range shards: merge the shards' packed top-k lists (each already in (score desc, id asc) order, searched with
+// the absolute floor only) into the global list, then the cutoffs of common.zig:153-166 anchored on the global best.
+// One warp per query; lane g walks shard g's list.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) merge_packed_shards_kernel(const uint32_t *packed, unsigned long long stride_words,
+                                                                   uint32_t n_shards, uint32_t n, const SearchOpts *opts,
+                                                                   uint32_t k_stride, uint32_t *out_ids, uint32_t *out_scores,
+                                                                   uint32_t *out_counts) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= n) return;
+    const uint2 *pairs = nullptr;
+    uint32_t cnt = 0, pos = 0;
+    if (lane < n_shards) {
+        const uint32_t *base = packed + (size_t)lane * stride_words;
+        cnt = min(base[q], k_stride);
+        pairs = reinterpret_cast<const uint2 *>(base + 2 * (size_t)n + 2) + base[(size_t)n + q];
+    }
+    unsigned long long key = ~0ull;
+    if (cnt) {
+        const uint2 p = pairs[0];
+        key = rank_key(p.y, p.x);
+    }
+    const SearchOpts o = opts[q];
+    const uint32_t k_eff = min(o.max_results, k_stride);
+    uint32_t ms = o.min_score, n_out = 0;
+    while (n_out < k_eff) {
+        unsigned long long best = key;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, d));
+        if (best == ~0ull) break;
+        const uint32_t score = 0xFFFFFFFFu - (uint32_t)(best >> 32);
+        if (score < ms) break;
+        if (n_out == 0) ms = max(ms, (uint32_t)(score * o.min_score_pct) / 100u); // after the test: the best is always kept
+        if (lane == 0) {
+            out_ids[(size_t)q * k_stride + n_out] = (uint32_t)best;
+            out_scores[(size_t)q * k_stride + n_out] = score;
+        }
+        ++n_out;
+        if (key == best) { // docid ranges are disjoint: exactly one lane
+            ++pos;
+            key = ~0ull;
+            if (pos < cnt) {
+                const uint2 p = pairs[pos];
+                key = rank_key(p.y, p.x);
+            }
+        }
+    }
+    if (lane == 0) out_counts[q] = n_out;
 }
 
 } // namespace
@@ -1785,9 +1866,19 @@ void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms
 void launch_result_pack(const uint32_t *ids, const uint32_t *scores, const uint32_t *counts, uint32_t *offsets, uint32_t n,
                         uint32_t k_stride, uint32_t *out_counts, uint2 *out_pairs, cudaStream_t st, uint32_t capacity) {
     if (n == 0) return;
-    result_offsets_kernel<<<1, 1024, 0, st>>>(counts, n, k_stride, offsets);
-    result_pack_kernel<<<(n + 255) / 256, 256, 0, st>>>(ids, scores, counts, offsets, n, k_stride, out_counts, out_pairs,
-                                                        capacity);
+    const uint32_t nb = (n + kPackBlock - 1) / kPackBlock;
+    pack_block_sums_kernel<<<nb, kPackBlock, 0, st>>>(counts, n, k_stride, offsets);
+    pack_scan_sums_kernel<<<1, kPackBlock, 0, st>>>(offsets, n);
+    result_pack_kernel<<<nb, kPackBlock, 0, st>>>(ids, scores, counts, offsets, n, k_stride, out_counts, out_pairs, capacity);
+}
+
+void launch_merge_packed_shards(const uint32_t *packed, uint64_t stride_words, uint32_t n_shards, uint32_t n,
+                                const SearchOpts *opts, uint32_t k_stride, uint32_t *out_ids, uint32_t *out_scores,
+                                uint32_t *out_counts, cudaStream_t st) {
+    if (n == 0) return;
+    const unsigned blocks = (unsigned)(((unsigned long long)n * 32 + 255) / 256);
+    merge_packed_shards_kernel<<<blocks, 256, 0, st>>>(packed, stride_words, n_shards, n, opts, k_stride, out_ids, out_scores,
+                                                       out_counts);
 }
 
 int wide_ctas(int n_sms) { return n_sms > 64 ? 64 : n_sms; }

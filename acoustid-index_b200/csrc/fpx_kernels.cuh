@@ -136,6 +136,11 @@ void launch_search_wide(const BatchArgs &a, cudaStream_t st, int n_ctas);
 void launch_result_pack(const uint32_t *ids, const uint32_t *scores, const uint32_t *counts, uint32_t *offsets, uint32_t n,
                         uint32_t k_stride, uint32_t *out_counts, uint2 *out_pairs, cudaStream_t st,
                         uint32_t capacity = 0xFFFFFFFFu);
+// merge n_shards packed result blocks (layout of launch_result_pack with out_counts = block, offsets = block + n,
+// pairs = block + 2n + 2; blocks stride_words apart) into k_stride-wide arrays: global top-k + cutoffs per query
+void launch_merge_packed_shards(const uint32_t *packed, uint64_t stride_words, uint32_t n_shards, uint32_t n,
+                                const SearchOpts *opts, uint32_t k_stride, uint32_t *out_ids, uint32_t *out_scores,
+                                uint32_t *out_counts, cudaStream_t st);
 cudaError_t configure_kernels();
 int wide_ctas(int n_sms);
 

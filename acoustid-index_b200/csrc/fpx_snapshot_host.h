@@ -258,7 +258,7 @@ class SnapshotCompiler {
                     return false;
                 }
             }
-            if (ranged && !(id >= lo_ && id < hi_)) {
+            if (ranged && !(id >= lo_ && (hi_ == 0u || id < hi_))) { // hi == 0 with lo > 0: open-ended
                 ++oor;
                 return false;
             }

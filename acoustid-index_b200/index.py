@@ -381,6 +381,26 @@ class IndexReader:
         check(lib().fpx_search_batch(self.snapshot.h, nq, terms_ptr, offsets_ptr, opts_ptr, k_stride, ids_ptr,
                                      scores_ptr, counts_ptr))
 
+    def search_batch_packed_ptr(self, nq, terms_ptr, offsets_ptr, opts_ptr, k_stride, counts_ptr, pairs_ptr,
+                                capacity_pairs):
+        """Raw host pointers; results as {count per query, (id, score) pairs back to back}.  Returns the number of pairs."""
+        n = C.c_uint64(0)
+        check(lib().fpx_search_batch_packed(self.snapshot.h, nq, terms_ptr, offsets_ptr, opts_ptr, k_stride, counts_ptr,
+                                            pairs_ptr, capacity_pairs, C.byref(n)))
+        return n.value
+
+    def search_batch_packed(self, terms, offsets, opts, k_stride, capacity_pairs=None):
+        """numpy in, (counts [nq], pairs [n, 2]) out: the reference's list-per-query result layout."""
+        terms, offsets = _u32(terms), np.ascontiguousarray(offsets, dtype=np.uint64)
+        opts = np.ascontiguousarray(opts, dtype=np.uint32).reshape(-1, 3)
+        nq = len(offsets) - 1
+        cap = int(capacity_pairs if capacity_pairs is not None else nq * k_stride)
+        counts = np.zeros(nq, np.uint32)
+        pairs = np.zeros((max(cap, 1), 2), np.uint32)
+        n = self.search_batch_packed_ptr(nq, terms.ctypes.data if len(terms) else None, offsets.ctypes.data, opts.ctypes.data,
+                                         k_stride, counts.ctypes.data, pairs.ctypes.data, cap)
+        return counts, pairs[:n]
+
     def search_batch_device(self, nq, d_terms, d_offsets, d_opts, k_stride, d_ids, d_scores, d_counts, stream=0):
         """Device pointers (ints), asynchronous on `stream` (a cudaStream_t handle as int)."""
         check(lib().fpx_search_batch_device(self.snapshot.h, nq, d_terms, d_offsets, d_opts, k_stride, d_ids, d_scores,
@@ -490,6 +510,13 @@ def multi_index_search(reader: IndexReader, request: SearchRequest, clamp_http=T
 def pack_results_device(nq, k_stride, d_ids, d_scores, d_counts, d_packed, capacity_pairs, stream=0):
     """Device pointers (ints).  Packs a batch's result arrays for an exchange between GPUs (see fpx.h)."""
     check(lib().fpx_pack_results_device(nq, k_stride, d_ids, d_scores, d_counts, d_packed, capacity_pairs, stream))
+
+
+def merge_packed_shards_device(n_shards, nq, d_packed, shard_stride_words, d_opts, k_stride, d_ids, d_scores, d_counts,
+                               stream=0):
+    """Device pointers (ints).  Merges n_shards packed result blocks into k_stride-wide arrays (see fpx.h)."""
+    check(lib().fpx_merge_packed_shards_device(n_shards, nq, d_packed, shard_stride_words, d_opts, k_stride, d_ids,
+                                               d_scores, d_counts, stream))
 
 
 def unpack_results(packed, nq, k_stride, capacity_pairs):

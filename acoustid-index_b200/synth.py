@@ -82,24 +82,28 @@ class Synth:
         n = doc_index[:, None] * H + slots[None, :]
         return vocab_map(self.rank(draw(self.cfg.seed, n)))
 
-    def corpus_items(self, chunk_docs=1 << 20):
-        """All postings as sorted packed items (hash<<32)|id, plus the docs map.  numpy, host memory."""
+    def corpus_items(self, chunk_docs=1 << 20, doc_lo=0, doc_hi=None):
+        """The postings of docs [doc_lo, doc_hi) (0-based; default: all) as sorted packed items (hash<<32)|id, plus
+        their docs map.  numpy, host memory.  A corpus cut into consecutive doc ranges gives the segments of a
+        multi-segment index (a segment footer counts items in u32, filefmt.zig:76-80)."""
         cfg, dev = self.cfg, self.device
         H = cfg.hashes_per_doc
+        doc_hi = cfg.n_docs if doc_hi is None else doc_hi
+        n = doc_hi - doc_lo
         slots = torch.arange(H, dtype=torch.int64, device=dev)
-        keys = torch.empty(cfg.n_docs * H, dtype=torch.int64, device=dev)
-        for d0 in range(0, cfg.n_docs, chunk_docs):
-            d1 = min(cfg.n_docs, d0 + chunk_docs)
+        keys = torch.empty(n * H, dtype=torch.int64, device=dev)
+        for d0 in range(doc_lo, doc_hi, chunk_docs):
+            d1 = min(doc_hi, d0 + chunk_docs)
             di = torch.arange(d0, d1, dtype=torch.int64, device=dev)
             t = self.corpus_terms(di, slots)
             k = (t << 32) | (di[:, None] + cfg.first_doc_id)
-            keys[d0 * H:d1 * H] = (k ^ _s64(1 << 63)).reshape(-1)  # signed order == unsigned order
+            keys[(d0 - doc_lo) * H:(d1 - doc_lo) * H] = (k ^ _s64(1 << 63)).reshape(-1)  # signed order == unsigned order
         keys = torch.sort(keys).values
         keys ^= _s64(1 << 63)
         items = keys.cpu().numpy().view(np.uint64)
         del keys
-        doc_ids = np.arange(cfg.first_doc_id, cfg.first_doc_id + cfg.n_docs, dtype=np.uint32)
-        doc_alive = np.ones(cfg.n_docs, dtype=np.uint8)
+        doc_ids = np.arange(cfg.first_doc_id + doc_lo, cfg.first_doc_id + doc_hi, dtype=np.uint32)
+        doc_alive = np.ones(n, dtype=np.uint8)
         return items, doc_ids, doc_alive
 
     def doc_hashes(self, doc_index):
@@ -108,10 +112,11 @@ class Synth:
         slots = torch.arange(self.cfg.hashes_per_doc, dtype=torch.int64, device=self.device)
         return self.corpus_terms(di, slots).cpu().numpy().astype(np.uint32)
 
-    def queries(self, n_queries, terms_per_query, seed=0xF1D01001, single_term=False):
-        """uint32 [Q, T] query terms (host numpy) and the source doc index (-1 for random queries)."""
+    def queries(self, n_queries, terms_per_query, seed=0xF1D01001, single_term=False, first=0):
+        """uint32 [Q, T] query terms (host numpy) and the source doc index (-1 for random queries): queries
+        first .. first + n_queries - 1 of the stream `seed` (a slice of a batch equals the batch's slice)."""
         cfg, dev, T = self.cfg, self.device, terms_per_query
-        q = torch.arange(n_queries, dtype=torch.int64, device=dev)
+        q = torch.arange(first, first + n_queries, dtype=torch.int64, device=dev)
         stride = 2 + 2 * T
         head = draw(seed, q * stride)
         is_random = (_lsr(head, 8) % 10) == 0

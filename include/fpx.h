@@ -143,7 +143,9 @@ fpx_status fpx_snapshot_begin(fpx_ctx *ctx, fpx_snapshot_builder **out);
 fpx_status fpx_snapshot_add_file_segment(fpx_snapshot_builder *b, const fpx_file_segment *seg);
 fpx_status fpx_snapshot_add_memory_segment(fpx_snapshot_builder *b, const fpx_memory_segment *seg);
 /* Restrict the snapshot to docids in [lo, hi) (multi-GPU docid-range sharding).  The scan caps and
- * supersession rules are applied on the whole snapshot first, so shards union to the full result. */
+ * supersession rules are applied on the whole snapshot first, so shards union to the full result.
+ * (0, 0) = no restriction; hi = 0 with lo > 0 = open-ended, [lo, 2^32): the last shard, so that the docid
+ * 0xFFFFFFFF belongs to a shard too. */
 fpx_status fpx_snapshot_set_doc_range(fpx_snapshot_builder *b, uint32_t lo, uint32_t hi);
 /* Compile to CSR on the host (idempotent).  Host-built snapshots only (FPX_FLAG_HOST_BUILD / FPX_FLAG_HOST_ONLY):
  * by default a device context decodes the segments and assembles the rows on the GPU at commit. */
@@ -181,6 +183,18 @@ fpx_status fpx_search_batch(fpx_snapshot *s, uint64_t n_queries, const uint32_t 
                             uint32_t k_stride, uint32_t *out_ids, uint32_t *out_scores,
                             uint32_t *out_counts);
 
+/* The same search with the results as the reference hands them out — a list per query (SearchResponse.results,
+ * api.zig:56-72; MultiIndex.zig:327-329 copies exactly the found results into the request arena) instead of
+ * k_stride-wide arrays: out_counts[q] results for query q, whose (id, score) pairs are the words
+ * out_pairs[2*o ...) with o = out_counts[0] + ... + out_counts[q-1].  For a 100 K-query batch of the metric's workload
+ * that is ~1.1 MB coming back from the GPU instead of 32 MB.  capacity_pairs = room in out_pairs (pairs);
+ * *out_n_pairs = pairs needed; FPX_INVALID_ARGUMENT if that exceeds the capacity (counts complete, pairs cut).
+ * k_stride still bounds the results per query. */
+fpx_status fpx_search_batch_packed(fpx_snapshot *s, uint64_t n_queries, const uint32_t *terms,
+                                   const uint64_t *term_offsets, const fpx_search_opts *opts, uint32_t k_stride,
+                                   uint32_t *out_counts, uint32_t *out_pairs, uint64_t capacity_pairs,
+                                   uint64_t *out_n_pairs);
+
 /* Same, all buffers already in device memory, enqueued on `cuda_stream` (a cudaStream_t; NULL = the
  * legacy default stream).  Asynchronous: results are ready when the stream reaches this point. */
 fpx_status fpx_search_batch_device(fpx_snapshot *s, uint64_t n_queries, const uint32_t *d_terms,
@@ -197,6 +211,18 @@ fpx_status fpx_search_batch_device(fpx_snapshot *s, uint64_t n_queries, const ui
 fpx_status fpx_pack_results_device(uint64_t n_queries, uint32_t k_stride, const uint32_t *d_ids,
                                    const uint32_t *d_scores, const uint32_t *d_counts, uint32_t *d_packed,
                                    uint32_t capacity_pairs, void *cuda_stream);
+
+/* Docid-range sharded corpus, device side: merge the shards' packed top-k lists of a batch (n_shards blocks in the
+ * layout of fpx_pack_results_device, shard g's block at d_packed + g * shard_stride_words — e.g. the receive buffer of
+ * an ncclAllGather of every rank's packed block, cut to the largest rank's size) into k_stride-wide arrays: per query
+ * the global best min(max_results, k_stride) under (score desc, id asc), then the relative cutoff anchored on the
+ * global best (common.zig:153-166).  Shards must have been searched with min_score_pct = 0 and hold disjoint docid
+ * ranges; every block's pairs must be complete (word 2n <= its capacity).  One warp per query, lane g walks shard g:
+ * at most 32 shards.  Asynchronous on `cuda_stream`. */
+fpx_status fpx_merge_packed_shards_device(uint32_t n_shards, uint64_t n_queries, const uint32_t *d_packed,
+                                          uint64_t shard_stride_words, const fpx_search_opts *d_opts,
+                                          uint32_t k_stride, uint32_t *d_out_ids, uint32_t *d_out_scores,
+                                          uint32_t *d_out_counts, void *cuda_stream);
 
 /* Merge per-shard top-k lists (docid-range sharded corpus): for each query take the global best
  * min(max_results, k_stride) under (score desc, id asc), then apply the relative cutoff anchored on the

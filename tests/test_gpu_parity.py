@@ -471,6 +471,59 @@ def test_sketch_admission_keeps_requeues_rare(ctx, c2):
         assert prof["overflow_requeues"] <= 0.02 * nq, (ms, prof)
 
 
+def test_doc_range_shards_merge_on_the_device(ctx, c2):
+    """The sharded mode's device side: three docid-range shards of C2 searched with the absolute floor only, their
+    results packed (fpx_pack_results_device), the three blocks laid out as an all-gather delivers them (cut to the
+    largest block), fpx_merge_packed_shards_device -> must equal the unsharded answer and the oracle; several
+    option sets incl. limit 3 (the global top-k cuts across shards) and a 100 % relative cutoff."""
+    import torch
+    syn, seg, snap, ix = c2
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    terms, _ = syn.queries(4000, 100, seed=777)
+    nq, T = terms.shape
+    offs = np.arange(nq + 1, dtype=np.uint64) * T
+    import importlib
+    ranges = importlib.import_module("acoustid_index_b200.multi_gpu").doc_ranges(1, 1_000_000, 3)
+    assert ranges[0][0] == 0 and ranges[-1][1] == 0
+    shards = [pkg.swap_snapshot(ctx, [seg], doc_range=r) for r in ranges]
+    assert sum(s.info()["n_postings"] for s in shards) == snap.info()["n_postings"]
+    d_terms = torch.from_numpy(terms.reshape(-1).view(np.int32)).to(dev)
+    d_offs = torch.from_numpy(offs.view(np.int64)).to(dev)
+    for opt, k in (((40, 5, 10), 40), ((3, 2, 0), 8), ((40, 1, 100), 40), ((100, 3, 50), 64)):
+        opts = np.tile(np.array(opt, dtype=np.uint32), (nq, 1))
+        local = opts.copy()
+        local[:, 2] = 0
+        d_opts = torch.from_numpy(opts.view(np.int32)).to(dev)
+        d_local = torch.from_numpy(local.view(np.int32)).to(dev)
+        cap = nq * k
+        blocks = []
+        for sh in shards:
+            ids = torch.zeros((nq, k), dtype=torch.int32, device=dev)
+            sc = torch.zeros((nq, k), dtype=torch.int32, device=dev)
+            cnt = torch.zeros(nq, dtype=torch.int32, device=dev)
+            pkg.IndexReader(sh).search_batch_device(nq, d_terms.data_ptr(), d_offs.data_ptr(), d_local.data_ptr(), k,
+                                                    ids.data_ptr(), sc.data_ptr(), cnt.data_ptr(), st)
+            packed = torch.zeros(2 * nq + 2 + 2 * cap, dtype=torch.int32, device=dev)
+            pkg.pack_results_device(nq, k, ids.data_ptr(), sc.data_ptr(), cnt.data_ptr(), packed.data_ptr(), cap, st)
+            blocks.append(packed)
+        torch.cuda.synchronize()
+        words = 2 * nq + 2 + 2 * max(int(b[2 * nq].item()) for b in blocks)     # phase 1 of the exchange
+        recv = torch.cat([b[:words] for b in blocks]).contiguous()               # phase 2
+        out = [torch.zeros((nq, k), dtype=torch.int32, device=dev), torch.zeros((nq, k), dtype=torch.int32, device=dev),
+               torch.zeros(nq, dtype=torch.int32, device=dev)]
+        pkg.merge_packed_shards_device(3, nq, recv.data_ptr(), words, d_opts.data_ptr(), k, out[0].data_ptr(),
+                                       out[1].data_ptr(), out[2].data_ptr(), st)
+        torch.cuda.synchronize()
+        got = [o.cpu().numpy().view(np.uint32) for o in out]
+        want = _compare_batch(pkg.IndexReader(snap), ix, terms.reshape(-1), offs, opts, k, threads=16)
+        assert np.array_equal(got[2], want[2])
+        mask = np.arange(k)[None, :] < want[2][:, None]
+        assert np.array_equal(got[0][mask], want[0][mask]) and np.array_equal(got[1][mask], want[1][mask])
+    for sh in shards:
+        sh.release()
+
+
 def test_pack_results_for_exchange(ctx, c2):
     """fpx_pack_results_device + unpack_results round-trip the k_stride-wide result arrays (multi-GPU exchange)."""
     import torch
