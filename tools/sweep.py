@@ -27,13 +27,11 @@ def main():
     pkg = graft.load_package()
     dev = torch.device("cuda", 0)
     wl = args.workload
-    syn, items, doc_ids, doc_alive = bench.build_corpus(pkg, wl, str(dev))
-    seg = pkg.FileSegment.from_items(items, doc_ids, doc_alive, commit_id=1, threads=os.cpu_count())
-    del items
+    syn = bench.make_synth(pkg, wl, str(dev))
     ctx = pkg.Context(device=0, profile=True, host_threads=os.cpu_count())
-    snap = pkg.swap_snapshot(ctx, [seg])
+    snap, _ = bench.build_snapshot(pkg, ctx, syn, wl, os.cpu_count(), keep_segments=False)
     reader = pkg.IndexReader(snap)
-    terms, offs, nq, T = bench.make_queries(syn, wl, 0)
+    terms, offs, nq, T = bench.make_queries(syn, wl, 0, 1, "replicated")
     opts = pkg.synth.http_opts(nq, T)
     torch.cuda.empty_cache()
     d_terms = torch.from_numpy(terms.reshape(-1).view(np.int32)).to(dev)
