@@ -970,12 +970,15 @@ constexpr uint32_t kFbCounted = 3; // +g: counters sync, finisher arrives (it is
 constexpr uint32_t kFbStage = 5;   // +s: producers sync, a finisher arrives (stage released); up to five stages
 constexpr uint32_t kFbMatched = 10; // +g: counters arrive, finisher syncs
 
-template <int GW, int PW, int STAGES, uint32_t STAGE_U4>
+// PF: which roles get the low warp ids (the schedulers do not treat all warp ids alike): false = counters, finishers,
+// producers; true = producers, finishers, counters
+template <int GW, int PW, int STAGES, uint32_t STAGE_U4, bool PF>
 __global__ void __launch_bounds__((2 * GW + 2 + PW) * 32, 1) search_find_kernel(BatchArgs a, uint32_t cls) {
     static_assert(STAGES >= 2 && STAGES <= 5 && (2 * GW + 2 + PW) <= 32, "barrier ids, CTA size");
-    constexpr int kFirstFinisher = 2 * GW;
+    constexpr int kAllWarps = 2 * GW + 2 + PW;
+    constexpr int kFirstFinisher = 2 * GW;     // in role order: counters, finishers, producers
     constexpr int kFirstProducer = 2 * GW + 2;
-    constexpr int kAllThreads = (kFirstProducer + PW) * 32;
+    constexpr int kAllThreads = kAllWarps * 32;
     constexpr uint32_t kGroup = GW * 32; // counter threads per group
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *sketch_base = smem_raw; // one 32 KB sketch per group
@@ -984,7 +987,9 @@ __global__ void __launch_bounds__((2 * GW + 2 + PW) * 32, 1) search_find_kernel(
     __shared__ WorkItem meta[STAGES];
     __shared__ FindGroup fg[2];
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    // role-order warp index: hardware warp w plays role-order warp (w + 2 GW + 2) mod n when the producers come first
+    const uint32_t warp = PF ? ((tid >> 5) + kFirstProducer) % kAllWarps : (tid >> 5);
     const uint32_t count = a.counters->qcount[cls];
     const WorkItem *items = a.items + (size_t)cls * a.n_queries;
     const uint32_t pad = a.snap.pad_id;
@@ -1131,7 +1136,7 @@ __global__ void __launch_bounds__((2 * GW + 2 + PW) * 32, 1) search_find_kernel(
     }
 
     // ===== counters: group g = warps [g * GW, (g + 1) * GW) takes queries it = g, g + 2, ... with sketch g
-    const uint32_t g = warp / GW, gtid = tid - g * kGroup, gwarp = warp - g * GW;
+    const uint32_t g = warp / GW, gwarp = warp - g * GW, gtid = gwarp * 32 + lane;
     const Group G{gtid, kGroup, kFbGroup + g};
     FindGroup &st = fg[g];
     const uint32_t boff = g * kSketchBytes; // folded into the address by the same LOP3 that masks the word offset
@@ -1219,8 +1224,12 @@ __global__ void __launch_bounds__((2 * GW + 2 + PW) * 32, 1) search_find_kernel(
         const uint32_t n_hot = (a.debug & 2u) ? 0u : st.n_hot;
         if (n_hot != 0u && n_hot <= kHotCap) {
             const uint32_t h0 = st.hot[0], h1 = st.hot[n_hot > 1u ? 1 : 0];
-            for (uint32_t i = gtid; i < total4; i += kGroup) {
-                const uint4 v = sg[i];
+            // A true match has a posting in most rows, i.e. a few per warp: a thread only notes what it finds
+            // (one docid and how often; a second distinct docid goes to the table at once), and the warp adds its
+            // findings to the table afterwards — one update per warp and docid, not a chain of shared-memory round
+            // trips per posting found.
+            uint32_t my_d = pad, my_c = 0;
+            auto find4 = [&](const uint4 v) {
                 const uint32_t dd[4] = {v.x, v.y, v.z, v.w};
                 uint32_t cc[4];
                 bool any = false;
@@ -1236,9 +1245,34 @@ __global__ void __launch_bounds__((2 * GW + 2 + PW) * 32, 1) search_find_kernel(
                         const uint32_t c = e == 0 ? cc[0] : e == 1 ? cc[1] : e == 2 ? cc[2] : cc[3];
                         bool hit = c == h0 || c == h1;
                         for (uint32_t k = 2; k < n_hot && !hit; ++k) hit = c == st.hot[k];
-                        if (hit && d < pad) cand_add(st, pad, d, 1u); // padding lies at pad and above
+                        if (hit && d < pad) { // padding lies at pad and above
+                            if (my_c == 0u || my_d == d) {
+                                my_d = d;
+                                ++my_c;
+                            } else {
+                                cand_add(st, pad, d, 1u);
+                            }
+                        }
                     }
                 }
+            };
+            uint32_t i = gtid;
+            for (; i + 3 * kGroup < total4; i += 4 * kGroup) { // four loads in flight
+                const uint4 v0 = sg[i], v1 = sg[i + kGroup], v2 = sg[i + 2 * kGroup], v3 = sg[i + 3 * kGroup];
+                find4(v0);
+                find4(v1);
+                find4(v2);
+                find4(v3);
+            }
+            for (; i < total4; i += kGroup) find4(sg[i]);
+            uint32_t act = __ballot_sync(0xFFFFFFFFu, my_c != 0u);
+            while (act) {
+                const uint32_t leader = __ffs(act) - 1u;
+                const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, my_d, leader);
+                const bool mine = my_c != 0u && my_d == d0;
+                const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, mine ? my_c : 0u);
+                if (lane == leader) cand_add(st, pad, d0, tot);
+                act &= ~__ballot_sync(0xFFFFFFFFu, mine);
             }
         }
         __syncwarp();
@@ -1740,7 +1774,7 @@ __global__ void __launch_bounds__(256) merge_packed_shards_kernel(const uint32_t
 // ------------------------------------------------------------------------------------------------
 // Warp split of the hot kernel: counter / resolver-group / producer warps (FPX_DEBUG_ABLATE bits 24..27 pick another
 // one for A/B runs).
-#define FPX_FIND_CONFIGS(X) X(0, 11, 8, 4) X(1, 10, 10, 4) X(2, 12, 6, 4) X(3, 9, 12, 4) X(4, 11, 8, 5) X(5, 10, 10, 5) X(6, 12, 6, 5)
+#define FPX_FIND_CONFIGS(X) X(0, 11, 8, 4, false) X(1, 11, 8, 4, true) X(2, 12, 6, 4, false) X(3, 12, 6, 4, true) X(4, 11, 8, 5, false) X(5, 11, 8, 5, true) X(6, 12, 6, 5, true) X(7, 10, 10, 5, true)
 
 cudaError_t configure_kernels() {
     cudaError_t e;
@@ -1752,13 +1786,13 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_sketch_kernel<14, 3, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
     if (e != cudaSuccess) return e;
-#define X(I, GW, PW, ST)                                                                                              \
-    e = cudaFuncSetAttribute(search_find_kernel<GW, PW, ST, kStageU4>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+#define X(I, GW, PW, ST, PF)                                                                                          \
+    e = cudaFuncSetAttribute(search_find_kernel<GW, PW, ST, kStageU4, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                              (int)find_smem_bytes<ST, kStageU4>());                                                   \
     if (e != cudaSuccess) return e;
     FPX_FIND_CONFIGS(X)
 #undef X
-    e = cudaFuncSetAttribute(search_find_kernel<11, 8, 3, kStageLargeU4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(search_find_kernel<11, 8, 3, kStageLargeU4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)find_smem_bytes<3, kStageLargeU4>());
     return e;
 }
@@ -1789,15 +1823,15 @@ void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms) {
         return;
     }
     switch ((a.debug >> 24) & 15u) {
-#define X(I, GW, PW, ST)                                                                                              \
+#define X(I, GW, PW, ST, PF)                                                                                          \
     case I:                                                                                                           \
-        search_find_kernel<GW, PW, ST, kStageU4><<<n_sms, (2 * GW + 2 + PW) * 32, find_smem_bytes<ST, kStageU4>(), st>>>(a, kSketchClass); \
+        search_find_kernel<GW, PW, ST, kStageU4, PF><<<n_sms, (2 * GW + 2 + PW) * 32, find_smem_bytes<ST, kStageU4>(), st>>>(a, kSketchClass); \
         break;
         FPX_FIND_CONFIGS(X)
 #undef X
     default: break;
     }
-    search_find_kernel<11, 8, 3, kStageLargeU4><<<n_sms, 1024, find_smem_bytes<3, kStageLargeU4>(), st>>>(a, kSketchLargeClass);
+    search_find_kernel<11, 8, 3, kStageLargeU4, false><<<n_sms, 1024, find_smem_bytes<3, kStageLargeU4>(), st>>>(a, kSketchLargeClass);
 }
 
 void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms) {
