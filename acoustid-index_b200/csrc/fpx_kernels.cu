@@ -92,7 +92,6 @@ __device__ uint32_t make_item(const BatchArgs &a, uint32_t q, uint32_t rows_off,
     // (kHotCap is 32; beyond it the query is re-queued, so this is a matter of speed only).
     bool sketch_ok = a.use_sketch && o.min_score >= 2 && o.min_score <= 128 && total4 <= kStageLargeU4 &&
                      k_eff <= kFastKbuf && n_rows <= kSketchMaxRows;
-    if (!(a.debug & 0x2000u) && !a.snap.pad_spread) sketch_ok = false; // the find pass tells padding by value
     if (a.debug & 0x2000u) { // round-1 kernel (A/B): records candidates while counting, 16384-counter limits
         if (total4 > kStageU4) sketch_ok = false;
         if (o.min_score == 2 && postings > 1500) sketch_ok = false;
@@ -911,85 +910,65 @@ search_sketch_kernel(BatchArgs a) {
 
 // ------------------------------------------------------------------------------------------------
 // sketch path, "count, then find" (the hot kernel; classes kSketchClass and kSketchLargeClass).
-// One persistent CTA per SM.  Producer warps gather posting rows into a ring of shared-memory stages with TMA bulk
-// copies (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP); two groups of counter warps take the staged queries in
-// turn (even / odd), each with its own count sketch, so that one group's barriers and shared-memory round trips hide
-// behind the other group's work; one finisher warp per group ranks and writes the results.  Hand-overs are named
-// barriers (arrive / sync pairs); the TMA completion is the only mbarrier.  Per query, a counter group
-//   1. counts: every staged docid is added to a sketch of 32768 8-bit counters (four per 32-bit word) with shared
-//      atomics whose results are never looked at (SASS: ATOMS with RZ destination): a 128-bit load per four postings,
-//      then per posting one hash multiply, four integer ops and the atomic; no branch, no dependence on the
-//      shared-memory round trip.  h = docid * kRowMult; word = h[29:17], byte = h[16:15];
-//   2. reads its sketch back once — all loads first, shared memory answers slowly under a stream of atomics — which
-//      also clears it to the bias 128 - min_score of the group's next query: "counter >= min_score" is then bit 7 of a
-//      byte, sixteen counters are tested with two logic ops, and the few "hot" counters go to a list;
-//   3. finds: a second pass over the staged postings keeps those whose counter is hot (same hash, one compare) and
-//      counts them per docid in a small table — exactly.
-// Exactness: a counter receives every posting whose docid maps to it, so a docid with count >= min_score makes its
-// counter hot, and every posting of a hot counter is found again in step 3; scores never come from the sketch.  Row
-// padding (unused docids above every live one) is counted in step 1 and dropped in step 3.  A byte that carries into
-// its neighbour (128 + min_score arrivals at one counter) would corrupt the picture: step 2 also sums all bytes
-// (IDP.4A), and the sum equals 32768 * bias + the number of staged postings iff no byte carried; otherwise, and when
-// there are more hot counters or candidates than fit, the query is re-queued to the exact count-table kernels.
-// The finisher applies common.zig:140-166 (floor, order, limit, relative cutoff) to the table.
+// One persistent CTA per SM, warps in three roles, hand-overs by named barriers (arrive / sync pairs; the TMA
+// completion is the only mbarrier), several queries in flight per SM:
+//   producers  TMA bulk copies (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) of the query's posting rows
+//              into a ring of shared-memory stages; all producer warps fill one stage at a time.
+//   counters   add every staged docid to a sketch of 32768 8-bit counters (four per 32-bit word) with shared
+//              atomics whose results are never looked at (SASS: ATOMS without a destination): the loop is a
+//              128-bit load, one hash multiply and five integer ops per posting, no branch, no dependence on the
+//              shared-memory round trip.  h = docid * kRowMult; the counter is h's top 15 bits: word = h[31:19], byte = h[18:17].
+//   resolvers  (groups of four warps, taking queries in turn) read the sketch back once — the pass that clears it
+//              for the query after next — and list the counters that reached min_score ("hot").  The sketch is
+//              cleared to the bias 128 - min_score of its next query, so "hot" is bit 7 of a byte and the test of
+//              sixteen counters is two logic ops.  Rows are sorted by row_key(docid) = h, whose top bits are the
+//              counter, so the postings of a hot counter are one contiguous range in every staged row: a 9-ary
+//              search per (hot counter, row) finds them (a multiply and a compare per probe), the warps list what
+//              they found, and one warp sums the list per docid — exactly — ranks and cuts like common.zig:140-166.
+// Exactness: a counter receives every posting whose docid maps to it, so a docid with count >= min_score makes
+// its counter hot, and a hot counter's postings are all enumerated; scores never come from the sketch.  A byte
+// that carries into its neighbour (128 + min_score arrivals at one counter) would corrupt the picture: the
+// clearing pass also sums all bytes (IDP.4A), and the sum equals 32768 * bias + the number of staged postings
+// iff no byte carried; otherwise, and when there are more hot counters or candidates than fit, the query is
+// re-queued to the exact count-table kernels.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kHotCap = 16;    // hot counters per query handled here
-constexpr uint32_t kCandSlots = 64; // candidate table: docid -> exact count
-constexpr uint32_t kCandMax = 48;   // distinct candidates; more -> exact count-table path
-constexpr uint32_t kSketchBytes = kSketchWords * 4;
+constexpr uint32_t kHotCap = 32;   // hot counters per query handled here
+constexpr uint32_t kFoundCap = 32; // (warp, docid) findings per query; more -> exact count-table path
+// named barrier ids of search_find_kernel (0 is __syncthreads): resolver groups 1..3, counters 4, stage release 5..9,
+// "counted" 10..12 (one per resolver group), "sketch free" 13..14 (one per sketch)
+constexpr uint32_t kFbGroup = 1, kFbCounters = 4, kFbStage = 5, kFbCounted = 10, kFbSkFree = 13;
 
-struct FindGroup { // one per counter group
-    uint32_t hot[kHotCap];            // counters that reached min_score: word * 4 + byte = h[29:15]
-    uint32_t cand_id[kCandSlots], cand_cnt[kCandSlots];
-    unsigned long long r_keys[kCandSlots];
-    uint32_t n_hot, sum, n_cand, ovf, r_count; // sum: all bytes of the sketch after counting
+struct FindState { // private to one resolver group
+    uint32_t hot[kHotCap];                              // counters that reached min_score: word * 4 + byte
+    uint32_t found_id[kFoundCap], found_cnt[kFoundCap]; // what the group's warps found: docid, number of postings
+    uint32_t n_hot, n_found, sum;                       // sum: all bytes of the sketch after counting
 };
 
-__device__ __forceinline__ void cand_add(FindGroup &st, uint32_t pad, uint32_t d, uint32_t c) {
-    uint32_t x = (d * kMult2) >> 26;
-#pragma unroll 1
-    for (uint32_t tries = 0; tries < kCandSlots; ++tries) {
-        const uint32_t old = atomicCAS(st.cand_id + x, pad, d);
-        if (old == pad || old == d) {
-            if (old == pad && atomicAdd(&st.n_cand, 1u) >= kCandMax) st.ovf = 1u;
-            atomicAdd(st.cand_cnt + x, c);
-            return;
-        }
-        x = (x + 1) & (kCandSlots - 1);
-    }
-    st.ovf = 1u;
+// SKLOG: log2 of the sketch's 8-bit counters (15: 32 KB per sketch; 14: 16 KB, which leaves room for a fifth 32 KB
+// stage — measured slower: the chance-hot counters of a C3 query go from 0.1 to 2.3 and each costs the resolvers)
+template <int STAGES, uint32_t STAGE_U4, int SKLOG> constexpr size_t find_smem_bytes() {
+    return 2 * ((size_t)1 << SKLOG) + (size_t)STAGES * STAGE_U4 * 16;
 }
 
-template <int STAGES, uint32_t STAGE_U4> constexpr size_t find_smem_bytes() {
-    return 2 * (size_t)kSketchBytes + (size_t)STAGES * STAGE_U4 * 16;
-}
-
-// named barrier ids of search_find_kernel (0 is __syncthreads)
-constexpr uint32_t kFbGroup = 1;   // +g: the group's counter warps
-constexpr uint32_t kFbCounted = 3; // +g: counters sync, finisher arrives (it is done with the group's table and hot list)
-constexpr uint32_t kFbStage = 5;   // +s: producers sync, a finisher arrives (stage released); up to five stages
-constexpr uint32_t kFbMatched = 10; // +g: counters arrive, finisher syncs
-
-// PF: which roles get the low warp ids (the schedulers do not treat all warp ids alike): false = counters, finishers,
-// producers; true = producers, finishers, counters
-template <int GW, int PW, int STAGES, uint32_t STAGE_U4, bool PF>
-__global__ void __launch_bounds__((2 * GW + 2 + PW) * 32, 1) search_find_kernel(BatchArgs a, uint32_t cls) {
-    static_assert(STAGES >= 2 && STAGES <= 5 && (2 * GW + 2 + PW) <= 32, "barrier ids, CTA size");
-    constexpr int kAllWarps = 2 * GW + 2 + PW;
-    constexpr int kFirstFinisher = 2 * GW;     // in role order: counters, finishers, producers
-    constexpr int kFirstProducer = 2 * GW + 2;
-    constexpr int kAllThreads = kAllWarps * 32;
-    constexpr uint32_t kGroup = GW * 32; // counter threads per group
+template <int CW, int RG, int PW, int STAGES, uint32_t STAGE_U4, int SKLOG>
+__global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) search_find_kernel(BatchArgs a, uint32_t cls) {
+    static_assert(RG >= 2 && RG <= 3 && STAGES >= 2 && STAGES <= 5 && SKLOG >= 13 && SKLOG <= 15, "barrier ids, sketch size");
+    constexpr uint32_t kSketchBytes = 1u << SKLOG;            // one byte per counter
+    constexpr uint32_t kSketchWords = kSketchBytes / 4;       // (shadows the round-1 kernel's constant)
+    constexpr uint32_t kKeyShift = 32 - SKLOG;                // counter = h >> kKeyShift = word * 4 + byte
+    constexpr uint32_t kWordMask = kSketchBytes - 4;          // byte offset of the counter's word
+    constexpr int kFirstResolver = CW;
+    constexpr int kFirstProducer = CW + RG * kSkResolverWarps;
+    constexpr int kAllThreads = (kFirstProducer + PW) * 32;
+    constexpr int kCounters = CW * 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char *sketch_base = smem_raw; // one 32 KB sketch per group
+    unsigned char *sketch_base = smem_raw; // 2 x 32 KB
     uint4 *stage = reinterpret_cast<uint4 *>(smem_raw + 2 * (size_t)kSketchBytes);
     __shared__ uint64_t full[STAGES]; // TMA completion; every other hand-over is a named barrier
-    __shared__ WorkItem meta[STAGES];
-    __shared__ FindGroup fg[2];
+    __shared__ StageMeta meta[STAGES];
+    __shared__ FindState fs[RG];
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
-    // role-order warp index: hardware warp w plays role-order warp (w + 2 GW + 2) mod n when the producers come first
-    const uint32_t warp = PF ? ((tid >> 5) + kFirstProducer) % kAllWarps : (tid >> 5);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t count = a.counters->qcount[cls];
     const WorkItem *items = a.items + (size_t)cls * a.n_queries;
     const uint32_t pad = a.snap.pad_id;
@@ -1003,19 +982,15 @@ __global__ void __launch_bounds__((2 * GW + 2 + PW) * 32, 1) search_find_kernel(
         for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], PW); // every producer warp arrives with its share of the bytes
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // each group's sketch starts at the bias of the group's first query
-    for (uint32_t g = 0; g < 2; ++g) {
-        const unsigned long long idx = blockIdx.x + (unsigned long long)g * gridDim.x;
+    // the two sketches start at the bias of this CTA's first two queries
+    for (uint32_t b = 0; b < 2; ++b) {
+        const unsigned long long idx = blockIdx.x + (unsigned long long)b * gridDim.x;
         const uint32_t ms = idx < count ? items[idx].min_score : 2u;
         const uint32_t bias = (0x80u - ms) * 0x01010101u;
-        uint4 *sk4 = reinterpret_cast<uint4 *>(sketch_base + (size_t)g * kSketchBytes);
+        uint4 *sk4 = reinterpret_cast<uint4 *>(sketch_base + (size_t)b * kSketchBytes);
         for (uint32_t i = tid; i < kSketchWords / 4; i += kAllThreads) sk4[i] = make_uint4(bias, bias, bias, bias);
     }
-    if (tid < 2 * kCandSlots) {
-        fg[tid / kCandSlots].cand_id[tid % kCandSlots] = pad;
-        fg[tid / kCandSlots].cand_cnt[tid % kCandSlots] = 0u;
-    }
-    if (tid < 2) fg[tid].n_hot = fg[tid].sum = fg[tid].n_cand = fg[tid].ovf = 0u;
+    if (tid < RG) fs[tid].n_hot = fs[tid].n_found = fs[tid].sum = 0u;
     __syncthreads();
 
     if (warp >= kFirstProducer) {
@@ -1048,7 +1023,7 @@ __global__ void __launch_bounds__((2 * GW + 2 + PW) * 32, 1) search_find_kernel(
             const bool have1 = item_at(it + 1, w1); // the next query: in flight during wait + issue
             if (have1) rows_of(w1, d1);
             const long long tp0 = clock64();
-            if (it >= (uint32_t)STAGES) // a finisher released the previous tenant of this stage: us + that warp
+            if (it >= (uint32_t)STAGES) // the resolvers released the previous tenant of this stage: us + their warp 0
                 named_sync(kFbStage + s, 32 * kP + 32);
             if (p == 0 && lane == 0) tick(0, tp0);
             uint32_t mine = 0;
@@ -1056,12 +1031,20 @@ __global__ void __launch_bounds__((2 * GW + 2 + PW) * 32, 1) search_find_kernel(
             for (int j = 0; j < kDesc; ++j) mine += (d[j].y + 3) >> 2;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
-            if (p == 0 && lane == 0) meta[s] = w;
+#pragma unroll
+            for (int j = 0; j < kDesc; ++j) { // stage directory for the resolvers (d.z: the row's place, from prepare_kernel)
+                const uint32_t r = (uint32_t)kP * (lane + 32 * j) + p;
+                if (r < kSketchMaxRows) {
+                    meta[s].row_off[r] = d[j].z * 4u;
+                    meta[s].row_len[r] = d[j].y;
+                }
+            }
+            if (p == 0 && lane == 0) meta[s].item = w;
             if (a.debug & 8u) mine = 0;
             __syncwarp();
             if (lane == 0) mbar_expect_tx(&full[s], mine * 16u); // expect_tx precedes my copies (release)
             __syncwarp();
-            if (!(a.debug & 8u)) { // d.z: the row's place in the stage, from prepare_kernel
+            if (!(a.debug & 8u)) {
 #pragma unroll
                 for (int j = 0; j < kDesc; ++j)
                     if (d[j].y) bulk_g2s(dst + d[j].z, docids4 + d[j].x, ((d[j].y + 3) >> 2) * 16u, &full[s]);
@@ -1078,56 +1061,180 @@ __global__ void __launch_bounds__((2 * GW + 2 + PW) * 32, 1) search_find_kernel(
         return;
     }
 
-    if (warp >= kFirstFinisher) {
-        // ===== finishers: warp g ranks and writes the answers of group g's queries
-        const uint32_t g = warp - kFirstFinisher;
-        const Group W{lane, 32u, 0u};
-        FindGroup &st = fg[g];
-        named_arrive(kFbCounted + g, kGroup + 32); // nothing of an earlier query is in the group's table
-        for (uint32_t it = g;; it += 2) {
+    if (warp >= kFirstResolver) {
+        // ===== resolvers: group gidx takes every RG-th query; query `it` used sketch it & 1
+        const uint32_t gidx = (warp - kFirstResolver) / kSkResolverWarps;
+        const uint32_t rwarp = (warp - kFirstResolver) % kSkResolverWarps;
+        const uint32_t rtid = rwarp * 32 + lane;
+        const Group R{rtid, (uint32_t)kSkResolvers, kFbGroup + gidx};
+        FindState &st = fs[gidx];
+        for (uint32_t it = gidx;; it += RG) {
             const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
             if (idx >= count) break;
-            const uint32_t s = it % STAGES;
+            const uint32_t s = it % STAGES, b = it & 1u;
+            uint4 *sk4 = reinterpret_cast<uint4 *>(sketch_base + (size_t)b * kSketchBytes);
+            // the sketch's next tenant is this CTA's query it + 2: clear to its bias
+            const unsigned long long idx2 = idx + 2ull * gridDim.x;
+            const uint32_t ms2 = idx2 < count ? items[idx2].min_score : 2u;
             const long long tr0 = clock64();
-            named_sync(kFbMatched + g, kGroup + 32); // the group's counters are through with query it
-            if (g == 0 && lane == 0) tick(3, tr0);
-            const WorkItem w = meta[s];
-            named_arrive(kFbStage + s, 32 * PW + 32); // the stage goes back to the producers
+            named_sync(kFbCounted + gidx, kCounters + kSkResolvers); // all counter warps are done with query it
+            if (gidx == 0 && rtid == 0) tick(3, tr0);
+            const WorkItem w = meta[s].item;
+            // read the sketch back: hot counters (bit 7 of a byte), the byte sum, and the clear for query it + 2
+            {
+                const uint32_t b2 = (0x80u - ms2) * 0x01010101u;
+                const uint4 clear4 = make_uint4(b2, b2, b2, b2);
+                uint32_t acc = 0;
+#pragma unroll 8
+                for (uint32_t i = rtid; i < kSketchWords / 4; i += kSkResolvers) { // the loads of a round first: shared memory
+                    const uint4 v = sk4[i];                                         // answers slowly under the counters' atomics
+                    if (!(a.debug & 16u)) sk4[i] = clear4;
+                    acc = __dp4a(v.x, 0x01010101u, acc);
+                    acc = __dp4a(v.y, 0x01010101u, acc);
+                    acc = __dp4a(v.z, 0x01010101u, acc);
+                    acc = __dp4a(v.w, 0x01010101u, acc);
+                    if ((v.x | v.y | v.z | v.w) & 0x80808080u) {
+                        const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll 1
+                        for (uint32_t e = 0; e < 4; ++e) {
+                            uint32_t m = ws[e] & 0x80808080u;
+                            while (m) {
+                                const uint32_t bit = __ffs(m) - 1u;
+                                m &= m - 1u;
+                                const uint32_t pos = atomicAdd(&st.n_hot, 1u);
+                                if (pos < kHotCap) st.hot[pos] = ((i * 4u + e) << 2) | (bit >> 3); // word * 4 + byte
+                            }
+                        }
+                    }
+                }
+                acc = __reduce_add_sync(0xFFFFFFFFu, acc);
+                if (lane == 0) atomicAdd(&st.sum, acc);
+            }
+            R.sync();
+            if (rwarp == 0) named_arrive(kFbSkFree + b, kCounters + 32); // the counters may start query it + 2 on this sketch
+            if (gidx == 0 && rtid == 0) tick(4, tr0);
             const uint32_t n_hot = (a.debug & 2u) ? 0u : st.n_hot;
             // no byte carried <=> the bytes add up to the bias of every counter plus one per staged posting
-            bool redo = st.sum != 32768u * (0x80u - w.min_score) + 4u * w.total4 && !(a.debug & 3u);
-            redo = redo || n_hot > kHotCap || st.ovf != 0u;
-            uint32_t n = 0;
-            if (n_hot != 0u) { // common.zig:140-145: keep score >= min_score; the table is left empty for the next query
+            bool redo = st.sum != kSketchBytes * (0x80u - w.min_score) + 4u * w.total4 && !(a.debug & 3u);
+            redo = redo || n_hot > kHotCap;
+            if (n_hot != 0u && !redo) {
+                // Find the postings of the hot counters: thread rtid owns row rtid of the stage (<= 128 rows); the
+                // postings of counter c are the range of row keys whose top bits are c.  Every dependent shared-memory
+                // round trip costs hundreds of cycles while the counters' atomics fill the pipe, and the stage is held
+                // all the while, so the lower bound is a 9-ary search (eight independent probes per round, two rounds
+                // for a row of <= 80, the last round's values stay in registers) and a warp reports what it found with
+                // one append to a list, not a probe chain into a table.
+                const bool has_row = rtid < w.n_rows;
+                const uint32_t *row = reinterpret_cast<const uint32_t *>(stage + (size_t)s * STAGE_U4) +
+                                      (has_row ? meta[s].row_off[rtid] : 0u);
+                const uint32_t len = has_row ? meta[s].row_len[rtid] : 0u;
+#pragma unroll 1
+                for (uint32_t c = 0; c < n_hot; ++c) {
+                    const uint32_t kp = st.hot[c] << kKeyShift; // first row key of the counter
+                    uint32_t lo = 0, hi = len; // every key before lo is below kp, every key from hi on is not
+                    while (hi - lo > 8u) {
+                        const uint32_t step = (hi - lo) / 9u + 1u;
+                        uint32_t below = 0;
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const uint32_t id = st.cand_id[lane + 32 * half], cn = st.cand_cnt[lane + 32 * half];
-                    st.cand_id[lane + 32 * half] = pad;
-                    st.cand_cnt[lane + 32 * half] = 0u;
-                    const bool keep = id != pad && cn >= w.min_score;
-                    const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
-                    if (keep) st.r_keys[n + __popc(km & ((1u << lane) - 1u))] = rank_key(cn, id);
-                    n += __popc(km);
+                        for (uint32_t j = 1; j <= 8; ++j) {
+                            const uint32_t pj = lo + j * step - 1u;
+                            if (pj < hi && row[pj] * kRowMult < kp) ++below; // the pivots below kp form a prefix
+                        }
+                        const uint32_t nxt = lo + (below + 1u) * step - 1u; // first pivot not below kp, if there is one
+                        if (below < 8u && nxt < hi) hi = nxt;
+                        lo += below * step;
+                    }
+                    uint32_t e[9], below = 0; // the window [lo, hi] (hi - lo <= 8): the lower bound lies in it
+#pragma unroll
+                    for (uint32_t j = 0; j < 9; ++j) {
+                        e[j] = lo + j < len ? row[lo + j] : 0u;
+                        if (lo + j < hi && e[j] * kRowMult < kp) ++below;
+                    }
+                    uint32_t d = e[0];
+#pragma unroll
+                    for (uint32_t j = 1; j < 9; ++j) d = below == j ? e[j] : d;
+                    uint32_t pos = lo + below;
+                    const bool has = pos < len && ((d * kRowMult ^ kp) >> kKeyShift) == 0u;
+                    // a true match is found in most rows: one list entry per warp and docid, not one per row
+                    uint32_t act = __ballot_sync(0xFFFFFFFFu, has);
+                    while (act) {
+                        const uint32_t leader = __ffs(act) - 1u;
+                        const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, d, leader);
+                        const uint32_t same = __ballot_sync(0xFFFFFFFFu, has && d == d0);
+                        if (lane == leader) {
+                            const uint32_t at = atomicAdd(&st.n_found, 1u);
+                            if (at < kFoundCap) {
+                                st.found_id[at] = d0;
+                                st.found_cnt[at] = __popc(same);
+                            }
+                        }
+                        act &= ~same;
+                    }
+                    // further postings of this counter in my row: repeated (hash, id) pairs, other docids
+                    if (has) {
+                        for (++pos; pos < len; ++pos) {
+                            d = row[pos];
+                            if (((d * kRowMult ^ kp) >> kKeyShift) != 0u) break;
+                            const uint32_t at = atomicAdd(&st.n_found, 1u);
+                            if (at < kFoundCap) {
+                                st.found_id[at] = d;
+                                st.found_cnt[at] = 1u;
+                            }
+                        }
+                    }
                 }
             }
-            __syncwarp();
-            if (lane == 0) st.n_hot = st.sum = st.n_cand = st.ovf = 0u;
-            __syncwarp();
-            named_arrive(kFbCounted + g, kGroup + 32); // table and hot list are free for the group's next query
-            if (redo) {
+            R.sync(); // everyone is done with the stage; the findings are complete
+            if (gidx == 0 && rtid == 0) tick(11, tr0);
+            if (rwarp == 0) {
+                named_arrive(kFbStage + s, 32 * PW + 32); // the stage goes back to the producers
+                const uint32_t n_found = n_hot != 0u && !redo ? st.n_found : 0u;
+                redo = redo || n_found > kFoundCap;
+                // lane i takes finding i: sum the findings of its docid, keep the first of each docid with
+                // score >= min_score (common.zig:140-145), rank and cut in registers (common.zig:147-166)
+                const uint32_t d = lane < n_found ? st.found_id[lane] : pad, sc = lane < n_found ? st.found_cnt[lane] : 0u;
+                __syncwarp();
+                if (lane == 0) st.n_hot = st.n_found = st.sum = 0u;
+                uint32_t n_out = 0;
+                if (!redo && n_found != 0u) {
+                    uint32_t total = 0;
+                    bool first = true;
+                    for (uint32_t j = 0; j < n_found; ++j) {
+                        const uint32_t dj = __shfl_sync(0xFFFFFFFFu, d, j), cj = __shfl_sync(0xFFFFFFFFu, sc, j);
+                        if (dj == d) {
+                            total += cj;
+                            if (j < lane) first = false;
+                        }
+                    }
+                    const bool keep = lane < n_found && first && total >= w.min_score;
+                    const unsigned long long key = keep ? rank_key(total, d) : ~0ull;
+                    uint32_t rank = 0;
+                    for (uint32_t j = 0; j < n_found; ++j) rank += (__shfl_sync(0xFFFFFFFFu, key, j) < key) ? 1u : 0u;
+                    const uint32_t best = __reduce_max_sync(0xFFFFFFFFu, keep ? total : 0u);
+                    // u32 wrapping product, truncating division; the best is emitted before the cutoff is raised
+                    const uint32_t ms = max(w.min_score, (uint32_t)(best * w.min_score_pct) / 100u);
+                    const bool emit = keep && rank < w.k_eff && (rank == 0u || total >= ms);
+                    if (emit) {
+                        a.out_ids[(size_t)w.q * a.k_stride + rank] = d;
+                        a.out_scores[(size_t)w.q * a.k_stride + rank] = total;
+                    }
+                    n_out = __popc(__ballot_sync(0xFFFFFFFFu, emit));
+                }
                 if (lane == 0) {
-                    enqueue(a, exact_class_for(w.postings, w.k_eff), w);
-                    if (a.stats) atomicAdd(&a.stats->overflow_requeues, 1ull);
+                    if (redo) { // not decidable here: the exact count-table kernels take the query
+                        enqueue(a, exact_class_for(w.postings, w.k_eff), w);
+                        if (a.stats) atomicAdd(&a.stats->overflow_requeues, 1ull);
+                    } else {
+                        a.out_counts[w.q] = n_out;
+                        if (a.stats) {
+                            atomicAdd(&a.stats->results, (unsigned long long)n_out);
+                            atomicAdd(&a.stats->sketch_queries, 1ull);
+                        }
+                    }
                 }
-            } else if (n == 0) {
-                if (lane == 0) a.out_counts[w.q] = 0;
-            } else {
-                group_sort_keys(W, st.r_keys, n, kCandSlots);
-                group_emit_results(W, a, w, st.r_keys, n, &st.r_count);
             }
-            if (lane == 0 && a.stats && !redo) atomicAdd(&a.stats->sketch_queries, 1ull);
-            __syncwarp();
-            if (g == 0 && lane == 0) {
+            R.sync(); // the group's scratch is reused by its next query
+            if (gidx == 0 && rtid == 0) {
                 tick(5, tr0);
                 if (timed) atomicAdd(&a.stats->dbg[6], 1ull);
             }
@@ -1135,149 +1242,49 @@ __global__ void __launch_bounds__((2 * GW + 2 + PW) * 32, 1) search_find_kernel(
         return;
     }
 
-    // ===== counters: group g = warps [g * GW, (g + 1) * GW) takes queries it = g, g + 2, ... with sketch g
-    const uint32_t g = warp / GW, gwarp = warp - g * GW, gtid = gwarp * 32 + lane;
-    const Group G{gtid, kGroup, kFbGroup + g};
-    FindGroup &st = fg[g];
-    const uint32_t boff = g * kSketchBytes; // folded into the address by the same LOP3 that masks the word offset
-    uint4 *sk4 = reinterpret_cast<uint4 *>(sketch_base + boff);
-    constexpr int kScan = (int)((kSketchWords / 4 + kGroup - 1) / kGroup); // 16-byte pieces of the sketch per thread
-    for (uint32_t it = g;; it += 2) {
+    // ===== counters: each warp streams its slice of every query and arrives on `counted`
+    for (uint32_t it = 0;; ++it) {
         const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
         if (idx >= count) break;
-        const uint32_t s = it % STAGES;
-        const unsigned long long idx2 = idx + 2ull * gridDim.x; // the sketch's next tenant
-        const uint32_t ms2 = idx2 < count ? items[idx2].min_score : 2u;
+        const uint32_t s = it % STAGES, b = it & 1u;
         const long long tc0 = clock64();
-        if (gwarp == 0) { // one warp polls the TMA completion, the others park on the named barrier
+        if (it >= 2) // sketch b was read back and cleared by the resolvers of query it - 2
+            named_sync(kFbSkFree + b, kCounters + 32);
+        if (warp == 0) { // one warp polls the TMA completion, the others park on a named barrier
             if (lane == 0) {
                 mbar_wait(&full[s], (it / STAGES) & 1, 0);
-                if (g == 0) tick(7, tc0);
+                tick(7, tc0);
             }
             __syncwarp();
         }
-        G.sync();
-        const uint32_t total4 = meta[s].total4;
+        named_sync(kFbCounters, kCounters);
+        const uint32_t total4 = meta[s].item.total4;
         const uint4 *sg = stage + (size_t)s * STAGE_U4;
-        // ---- 1. count
+        const uint32_t boff = b * kSketchBytes; // folded into the address by the same LOP3 that masks the word offset
+        // Row padding is made of unused docids spread over many values: counted like anything else (the byte sum
+        // expects it), never found by the resolvers (they search the true row lengths).
         auto add4 = [&](const uint4 v) {
             const uint32_t dd[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const uint32_t t = (dd[e] * kMult) >> 15; // word = h[29:17], byte = h[16:15]
-                atomicAdd(reinterpret_cast<uint32_t *>(sketch_base + ((t & 0x7FFCu) | boff)), __funnelshift_l(0u, 1u, t << 3));
+                const uint32_t t = (dd[e] * kMult) >> kKeyShift; // counter: word = t >> 2, byte = t & 3
+                atomicAdd(reinterpret_cast<uint32_t *>(sketch_base + ((t & kWordMask) | boff)), __funnelshift_l(0u, 1u, t << 3));
             }
         };
         if (!(a.debug & 1u)) {
-            uint32_t i = gtid;
-            for (; i + 3 * kGroup < total4; i += 4 * kGroup) { // four loads in flight, then sixteen adds
-                const uint4 v0 = sg[i], v1 = sg[i + kGroup], v2 = sg[i + 2 * kGroup], v3 = sg[i + 3 * kGroup];
+            uint32_t i = tid;
+            for (; i + 3 * kCounters < total4; i += 4 * kCounters) { // four loads in flight, then sixteen adds
+                const uint4 v0 = sg[i], v1 = sg[i + kCounters], v2 = sg[i + 2 * kCounters], v3 = sg[i + 3 * kCounters];
                 add4(v0);
                 add4(v1);
                 add4(v2);
                 add4(v3);
             }
-            for (; i < total4; i += kGroup) add4(sg[i]);
-        }
-        if (g == 0 && gtid == 0) tick(8, tc0);
-        // every counter warp of the group has counted, and the finisher is done with the group's previous query
-        named_sync(kFbCounted + g, kGroup + 32);
-        if (g == 0 && gtid == 0) tick(12, tc0);
-        // ---- 2. read the sketch back: byte sum, hot counters, clear to the bias of the next tenant
-        {
-            const uint32_t b2 = (0x80u - ms2) * 0x01010101u;
-            const uint4 clear4 = make_uint4(b2, b2, b2, b2);
-            uint4 v[kScan];
-#pragma unroll
-            for (int k = 0; k < kScan; ++k) {
-                const uint32_t i = gtid + (uint32_t)k * kGroup;
-                v[k] = i < kSketchWords / 4 ? sk4[i] : make_uint4(0u, 0u, 0u, 0u);
-            }
-            uint32_t acc = 0;
-#pragma unroll
-            for (int k = 0; k < kScan; ++k) {
-                const uint32_t i = gtid + (uint32_t)k * kGroup;
-                if (i < kSketchWords / 4 && !(a.debug & 16u)) sk4[i] = clear4;
-                acc = __dp4a(v[k].x, 0x01010101u, acc);
-                acc = __dp4a(v[k].y, 0x01010101u, acc);
-                acc = __dp4a(v[k].z, 0x01010101u, acc);
-                acc = __dp4a(v[k].w, 0x01010101u, acc);
-                if ((v[k].x | v[k].y | v[k].z | v[k].w) & 0x80808080u) { // rare: a counter at bias + min_score or more
-#pragma unroll 1
-                    for (uint32_t e = 0; e < 4; ++e) {
-                        uint32_t hm = (e == 0 ? v[k].x : e == 1 ? v[k].y : e == 2 ? v[k].z : v[k].w) & 0x80808080u;
-                        while (hm) {
-                            const uint32_t bit = __ffs(hm) - 1u;
-                            hm &= hm - 1u;
-                            const uint32_t pos = atomicAdd(&st.n_hot, 1u);
-                            if (pos < kHotCap) st.hot[pos] = ((i * 4u + e) << 2) | (bit >> 3); // word * 4 + byte
-                        }
-                    }
-                }
-            }
-            acc = __reduce_add_sync(0xFFFFFFFFu, acc);
-            if (lane == 0) atomicAdd(&st.sum, acc);
-        }
-        G.sync();
-        if (g == 0 && gtid == 0) tick(13, tc0);
-        // ---- 3. find the postings of the hot counters (usually one: the true match) and count them per docid
-        const uint32_t n_hot = (a.debug & 2u) ? 0u : st.n_hot;
-        if (n_hot != 0u && n_hot <= kHotCap) {
-            const uint32_t h0 = st.hot[0], h1 = st.hot[n_hot > 1u ? 1 : 0];
-            // A true match has a posting in most rows, i.e. a few per warp: a thread only notes what it finds
-            // (one docid and how often; a second distinct docid goes to the table at once), and the warp adds its
-            // findings to the table afterwards — one update per warp and docid, not a chain of shared-memory round
-            // trips per posting found.
-            uint32_t my_d = pad, my_c = 0;
-            auto find4 = [&](const uint4 v) {
-                const uint32_t dd[4] = {v.x, v.y, v.z, v.w};
-                uint32_t cc[4];
-                bool any = false;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    cc[e] = ((dd[e] * kMult) >> 15) & 0x7FFFu;
-                    any = any || cc[e] == h0 || cc[e] == h1;
-                }
-                if (any || n_hot > 2u) {
-#pragma unroll 1
-                    for (uint32_t e = 0; e < 4; ++e) {
-                        const uint32_t d = e == 0 ? dd[0] : e == 1 ? dd[1] : e == 2 ? dd[2] : dd[3];
-                        const uint32_t c = e == 0 ? cc[0] : e == 1 ? cc[1] : e == 2 ? cc[2] : cc[3];
-                        bool hit = c == h0 || c == h1;
-                        for (uint32_t k = 2; k < n_hot && !hit; ++k) hit = c == st.hot[k];
-                        if (hit && d < pad) { // padding lies at pad and above
-                            if (my_c == 0u || my_d == d) {
-                                my_d = d;
-                                ++my_c;
-                            } else {
-                                cand_add(st, pad, d, 1u);
-                            }
-                        }
-                    }
-                }
-            };
-            uint32_t i = gtid;
-            for (; i + 3 * kGroup < total4; i += 4 * kGroup) { // four loads in flight
-                const uint4 v0 = sg[i], v1 = sg[i + kGroup], v2 = sg[i + 2 * kGroup], v3 = sg[i + 3 * kGroup];
-                find4(v0);
-                find4(v1);
-                find4(v2);
-                find4(v3);
-            }
-            for (; i < total4; i += kGroup) find4(sg[i]);
-            uint32_t act = __ballot_sync(0xFFFFFFFFu, my_c != 0u);
-            while (act) {
-                const uint32_t leader = __ffs(act) - 1u;
-                const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, my_d, leader);
-                const bool mine = my_c != 0u && my_d == d0;
-                const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, mine ? my_c : 0u);
-                if (lane == leader) cand_add(st, pad, d0, tot);
-                act &= ~__ballot_sync(0xFFFFFFFFu, mine);
-            }
+            for (; i < total4; i += kCounters) add4(sg[i]);
         }
         __syncwarp();
-        named_arrive(kFbMatched + g, kGroup + 32); // the finisher takes it from here
-        if (g == 0 && gtid == 0) {
+        named_arrive(kFbCounted + it % RG, kCounters + kSkResolvers); // my slice of query it is in the sketch
+        if (warp == 0 && lane == 0) {
             tick(9, tc0);
             if (timed) atomicAdd(&a.stats->dbg[10], 1ull);
         }
@@ -1774,7 +1781,7 @@ __global__ void __launch_bounds__(256) merge_packed_shards_kernel(const uint32_t
 // ------------------------------------------------------------------------------------------------
 // Warp split of the hot kernel: counter / resolver-group / producer warps (FPX_DEBUG_ABLATE bits 24..27 pick another
 // one for A/B runs).
-#define FPX_FIND_CONFIGS(X) X(0, 11, 8, 4, false) X(1, 11, 8, 4, true) X(2, 12, 6, 4, false) X(3, 12, 6, 4, true) X(4, 11, 8, 5, false) X(5, 11, 8, 5, true) X(6, 12, 6, 5, true) X(7, 10, 10, 5, true)
+#define FPX_FIND_CONFIGS(X) X(0, 10, 3, 10, 4, 15) X(1, 12, 3, 8, 4, 15) X(2, 8, 3, 12, 4, 15) X(3, 14, 3, 6, 4, 15) X(4, 12, 2, 12, 4, 15) X(5, 10, 3, 10, 5, 14)
 
 cudaError_t configure_kernels() {
     cudaError_t e;
@@ -1786,14 +1793,14 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_sketch_kernel<14, 3, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
     if (e != cudaSuccess) return e;
-#define X(I, GW, PW, ST, PF)                                                                                          \
-    e = cudaFuncSetAttribute(search_find_kernel<GW, PW, ST, kStageU4, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                             (int)find_smem_bytes<ST, kStageU4>());                                                   \
+#define X(I, CW, RG, PW, ST, SK)                                                                                      \
+    e = cudaFuncSetAttribute(search_find_kernel<CW, RG, PW, ST, kStageU4, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)find_smem_bytes<ST, kStageU4, SK>());                                               \
     if (e != cudaSuccess) return e;
     FPX_FIND_CONFIGS(X)
 #undef X
-    e = cudaFuncSetAttribute(search_find_kernel<11, 8, 3, kStageLargeU4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)find_smem_bytes<3, kStageLargeU4>());
+    e = cudaFuncSetAttribute(search_find_kernel<12, 3, 8, 3, kStageLargeU4, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)find_smem_bytes<3, kStageLargeU4, 15>());
     return e;
 }
 
@@ -1823,15 +1830,16 @@ void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms) {
         return;
     }
     switch ((a.debug >> 24) & 15u) {
-#define X(I, GW, PW, ST, PF)                                                                                          \
+#define X(I, CW, RG, PW, ST, SK)                                                                                      \
     case I:                                                                                                           \
-        search_find_kernel<GW, PW, ST, kStageU4, PF><<<n_sms, (2 * GW + 2 + PW) * 32, find_smem_bytes<ST, kStageU4>(), st>>>(a, kSketchClass); \
+        search_find_kernel<CW, RG, PW, ST, kStageU4, SK>                                                              \
+            <<<n_sms, (CW + 4 * RG + PW) * 32, find_smem_bytes<ST, kStageU4, SK>(), st>>>(a, kSketchClass);           \
         break;
         FPX_FIND_CONFIGS(X)
 #undef X
     default: break;
     }
-    search_find_kernel<11, 8, 3, kStageLargeU4, false><<<n_sms, 1024, find_smem_bytes<3, kStageLargeU4>(), st>>>(a, kSketchLargeClass);
+    search_find_kernel<12, 3, 8, 3, kStageLargeU4, 15><<<n_sms, 1024, find_smem_bytes<3, kStageLargeU4, 15>(), st>>>(a, kSketchLargeClass);
 }
 
 void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms) {

@@ -23,15 +23,13 @@ struct SnapshotDev {
     uint32_t pad_spread; // 1: pad_id and all row padding are larger than every live docid
 };
 
-// Order of the docids inside a row in HBM: ascending row_key.  h = d * kRowMult is the hash the sketch kernel
-// counts with: 32768 8-bit counters, four per 32-bit word; word = h[29:17], byte = h[16:15].  row_key is a bit
-// permutation of h whose top 15 bits are the counter — first the word's shared-memory bank h[21:17], then the rest
-// of the word index h[29:22], then the byte h[16:15] — followed by the remaining bits h[31:30], h[14:0].  So
-//  * the postings of one counter are one contiguous range of every row (the resolvers of search_find_kernel
-//    binary-search it), equal docids stay adjacent, and a row is still searchable by key;
-//  * a warp of counter threads takes 32 consecutive 16-byte granules, i.e. every fourth posting of ~1.8 rows: in
-//    this order their banks sweep 0..31 once per row instead of being random, which cuts the bank conflicts of the
-//    shared atomics (~3.5 -> ~2.9 wavefronts per instruction, measured in round 1).
+// Order of the docids inside a row in HBM: ascending row_key(d) = d * kRowMult (an odd multiplier: a bijection on u32),
+// the hash the sketch kernel counts with.  Its top 15 bits are the sketch counter of d (32768 8-bit counters, four per
+// 32-bit word: word = h[31:19], byte = h[18:17]), so the postings of one counter are one contiguous range of every
+// row — the resolvers of search_find_kernel binary-search it with a multiply and a compare per probe — equal docids
+// stay adjacent, and a row is still searchable by key.  (Round 1 ordered rows by the shared-memory bank of the counter
+// word to save a fifth of the atomics' bank conflicts; that measured -0.5 % and would cost the search a bit
+// permutation per probe.)
 constexpr uint32_t kRowMult = 0x9E3779B1u;
 constexpr uint32_t row_inv32(uint32_t a) {
     uint32_t x = a;
@@ -39,16 +37,8 @@ constexpr uint32_t row_inv32(uint32_t a) {
     return x;
 }
 constexpr uint32_t kRowMultInv = row_inv32(kRowMult);
-__host__ __device__ __forceinline__ uint32_t row_key(uint32_t d) {
-    const uint32_t h = d * kRowMult;
-    return ((h << 10) & 0xF8000000u) | ((h >> 3) & 0x07F80000u) | ((h << 2) & 0x00060000u) | ((h >> 15) & 0x00018000u) |
-           (h & 0x00007FFFu);
-}
-__host__ __device__ __forceinline__ uint32_t row_key_inv(uint32_t k) {
-    const uint32_t h = ((k >> 10) & 0x003E0000u) | ((k << 3) & 0x3FC00000u) | ((k >> 2) & 0x00018000u) |
-                       ((k << 15) & 0xC0000000u) | (k & 0x00007FFFu);
-    return h * kRowMultInv;
-}
+__host__ __device__ __forceinline__ uint32_t row_key(uint32_t d) { return d * kRowMult; }
+__host__ __device__ __forceinline__ uint32_t row_key_inv(uint32_t k) { return k * kRowMultInv; }
 
 struct SearchOpts { // == fpx_search_opts
     uint32_t max_results, min_score, min_score_pct;
