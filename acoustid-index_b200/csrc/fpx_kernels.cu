@@ -1085,24 +1085,33 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
                 const uint32_t b2 = (0x80u - ms2) * 0x01010101u;
                 const uint4 clear4 = make_uint4(b2, b2, b2, b2);
                 uint32_t acc = 0;
-#pragma unroll 8
-                for (uint32_t i = rtid; i < kSketchWords / 4; i += kSkResolvers) { // the loads of a round first: shared memory
-                    const uint4 v = sk4[i];                                         // answers slowly under the counters' atomics
-                    if (!(a.debug & 16u)) sk4[i] = clear4;
-                    acc = __dp4a(v.x, 0x01010101u, acc);
-                    acc = __dp4a(v.y, 0x01010101u, acc);
-                    acc = __dp4a(v.z, 0x01010101u, acc);
-                    acc = __dp4a(v.w, 0x01010101u, acc);
-                    if ((v.x | v.y | v.z | v.w) & 0x80808080u) {
-                        const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+                // eight 16-byte pieces per thread and round, all loads of a round before anything else: shared memory
+                // answers slowly under the counters' atomics (the compiler keeps load - use pairs together otherwise)
+                constexpr uint32_t kPieces = kSketchWords / 4 / kSkResolvers; // 16 (8 with the 16 KB sketch)
+                static_assert(kPieces % 8 == 0, "rounds of eight loads");
 #pragma unroll 1
-                        for (uint32_t e = 0; e < 4; ++e) {
-                            uint32_t m = ws[e] & 0x80808080u;
-                            while (m) {
-                                const uint32_t bit = __ffs(m) - 1u;
-                                m &= m - 1u;
-                                const uint32_t pos = atomicAdd(&st.n_hot, 1u);
-                                if (pos < kHotCap) st.hot[pos] = ((i * 4u + e) << 2) | (bit >> 3); // word * 4 + byte
+                for (uint32_t r = 0; r < kPieces / 8; ++r) {
+                    uint4 v[8];
+#pragma unroll
+                    for (uint32_t k = 0; k < 8; ++k) v[k] = sk4[rtid + (r * 8 + k) * kSkResolvers];
+#pragma unroll
+                    for (uint32_t k = 0; k < 8; ++k) {
+                        const uint32_t i = rtid + (r * 8 + k) * kSkResolvers;
+                        if (!(a.debug & 16u)) sk4[i] = clear4;
+                        acc = __dp4a(v[k].x, 0x01010101u, acc);
+                        acc = __dp4a(v[k].y, 0x01010101u, acc);
+                        acc = __dp4a(v[k].z, 0x01010101u, acc);
+                        acc = __dp4a(v[k].w, 0x01010101u, acc);
+                        if ((v[k].x | v[k].y | v[k].z | v[k].w) & 0x80808080u) { // rare: a counter at bias + min_score or more
+#pragma unroll 1
+                            for (uint32_t e = 0; e < 4; ++e) {
+                                uint32_t m = (e == 0 ? v[k].x : e == 1 ? v[k].y : e == 2 ? v[k].z : v[k].w) & 0x80808080u;
+                                while (m) {
+                                    const uint32_t bit = __ffs(m) - 1u;
+                                    m &= m - 1u;
+                                    const uint32_t pos = atomicAdd(&st.n_hot, 1u);
+                                    if (pos < kHotCap) st.hot[pos] = ((i * 4u + e) << 2) | (bit >> 3); // word * 4 + byte
+                                }
                             }
                         }
                     }
