@@ -1013,15 +1013,21 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
                 d[j] = r < w.n_rows ? a.rows[w.rows_off + r] : make_uint4(0u, 0u, 0u, 0u);
             }
         };
-        WorkItem w{}, w1{};
-        uint4 d[kDesc], d1[kDesc];
+        // Row descriptors and work items are read two and three queries ahead: they come from DRAM (the batch's
+        // descriptors are larger than L2) behind the copies' own traffic, ~1.5 us away, and a load that is waited for at
+        // the top of the loop pins the whole kernel to that latency.
+        WorkItem w{}, w1{}, w2{}, w3{};
+        uint4 d[kDesc], d1[kDesc], d2[kDesc];
         bool have = item_at(0, w);
         if (have) rows_of(w, d);
+        bool have1 = item_at(1, w1);
+        if (have1) rows_of(w1, d1);
+        bool have2 = item_at(2, w2);
         for (uint32_t it = 0; have; ++it) {
             const uint32_t s = it % STAGES;
             uint4 *dst = stage + (size_t)s * STAGE_U4;
-            const bool have1 = item_at(it + 1, w1); // the next query: in flight during wait + issue
-            if (have1) rows_of(w1, d1);
+            if (have2) rows_of(w2, d2);
+            const bool have3 = item_at(it + 3, w3);
             const long long tp0 = clock64();
             if (it >= (uint32_t)STAGES) // the resolvers released the previous tenant of this stage: us + their warp 0
                 named_sync(kFbStage + s, 32 * kP + 32);
@@ -1050,9 +1056,16 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
                     if (d[j].y) bulk_g2s(dst + d[j].z, docids4 + d[j].x, ((d[j].y + 3) >> 2) * 16u, &full[s]);
             }
             have = have1;
+            have1 = have2;
+            have2 = have3;
             w = w1;
+            w1 = w2;
+            w2 = w3;
 #pragma unroll
-            for (int j = 0; j < kDesc; ++j) d[j] = d1[j];
+            for (int j = 0; j < kDesc; ++j) {
+                d[j] = d1[j];
+                d1[j] = d2[j];
+            }
             if (p == 0 && lane == 0) {
                 tick(1, tp0);
                 if (timed) atomicAdd(&a.stats->dbg[2], 1ull);
@@ -1790,7 +1803,7 @@ __global__ void __launch_bounds__(256) merge_packed_shards_kernel(const uint32_t
 // ------------------------------------------------------------------------------------------------
 // Warp split of the hot kernel: counter / resolver-group / producer warps (FPX_DEBUG_ABLATE bits 24..27 pick another
 // one for A/B runs).
-#define FPX_FIND_CONFIGS(X) X(0, 10, 3, 10, 4, 15) X(1, 12, 3, 8, 4, 15) X(2, 8, 3, 12, 4, 15) X(3, 14, 3, 6, 4, 15) X(4, 12, 2, 12, 4, 15) X(5, 10, 3, 10, 5, 14)
+#define FPX_FIND_CONFIGS(X) X(0, 10, 3, 10, 5, 15) X(1, 10, 3, 10, 4, 15) X(2, 12, 3, 8, 5, 15) X(3, 8, 3, 12, 5, 15) X(4, 12, 2, 12, 5, 15) X(5, 14, 3, 6, 5, 15)
 
 cudaError_t configure_kernels() {
     cudaError_t e;

@@ -109,7 +109,8 @@ constexpr uint32_t kFastKbuf = 512;       // candidate buffer of the shared-memo
 constexpr uint32_t kWideKbuf = 2048;      // candidate buffer of the global-memory path
 constexpr uint32_t kMaxResults = 1024;    // FPX_MAX_RESULTS
 constexpr uint32_t kRowsChunk = 256;      // row descriptors staged per round
-constexpr uint32_t kStageU4 = 2048;       // sketch path: one query's padded rows must fit 32 KB ...
+constexpr uint32_t kStageU4 = 2000;       // sketch path: one query's padded rows must fit a 32000-byte stage (five of
+                                          // them and two 32 KB sketches fill the SM's shared memory) ...
 constexpr uint32_t kStageLargeU4 = 3072;  // ... or 48 KB in the large-stage class
 constexpr uint32_t kSketchMaxRows = 128;  // sketch path: row descriptors live in producer registers
 
