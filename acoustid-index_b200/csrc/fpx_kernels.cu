@@ -911,20 +911,25 @@ search_sketch_kernel(BatchArgs a) {
 // ------------------------------------------------------------------------------------------------
 // sketch path, "count, then find" (the hot kernel; classes kSketchClass and kSketchLargeClass).
 // One persistent CTA per SM, warps in three roles, hand-overs by named barriers (arrive / sync pairs; the TMA
-// completion is the only mbarrier), several queries in flight per SM:
+// completion is the only mbarrier), up to five queries in flight per SM:
 //   producers  TMA bulk copies (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) of the query's posting rows
 //              into a ring of shared-memory stages; all producer warps fill one stage at a time.
-//   counters   add every staged docid to a sketch of 32768 8-bit counters (four per 32-bit word) with shared
-//              atomics whose results are never looked at (SASS: ATOMS without a destination): the loop is a
-//              128-bit load, one hash multiply and five integer ops per posting, no branch, no dependence on the
-//              shared-memory round trip.  h = docid * kRowMult; the counter is h's top 15 bits: word = h[31:19], byte = h[18:17].
-//   resolvers  (groups of four warps, taking queries in turn) read the sketch back once — the pass that clears it
-//              for the query after next — and list the counters that reached min_score ("hot").  The sketch is
-//              cleared to the bias 128 - min_score of its next query, so "hot" is bit 7 of a byte and the test of
-//              sixteen counters is two logic ops.  Rows are sorted by row_key(docid) = h, whose top bits are the
-//              counter, so the postings of a hot counter are one contiguous range in every staged row: a 9-ary
-//              search per (hot counter, row) finds them (a multiply and a compare per probe), the warps list what
-//              they found, and one warp sums the list per docid — exactly — ranks and cuts like common.zig:140-166.
+//   counters   two groups, each with its own sketch of 32768 8-bit counters (four per 32-bit word), take the staged
+//              queries in turn (even / odd).  A group adds every staged docid to its sketch with shared atomics whose
+//              results are never looked at (SASS: ATOMS with RZ destination): a 128-bit load per four postings, then
+//              per posting one hash multiply, four integer ops and the atomic; no branch, no dependence on the
+//              shared-memory round trip.  h = docid * kRowMult; the counter is h's top 15 bits: word = h[31:19],
+//              byte = h[18:17].  Then the group reads its sketch back once — all loads first: shared memory answers
+//              slowly under the other group's atomics — which also clears it to the bias 128 - min_score of the
+//              group's next query: "counter >= min_score" is then bit 7 of a byte, sixteen counters are tested with
+//              two logic ops, and the few "hot" counters go to a list that travels with the stage.
+//   resolvers  (groups of four warps, taking queries in turn) find the postings of the hot counters: rows are sorted by
+//              row_key(docid) = h, whose top bits are the counter, so they are one contiguous range in every staged
+//              row: a 9-ary search per (hot counter, row) finds them (a multiply and a compare per probe), the warps
+//              list what they found, and one warp sums the list per docid — exactly — ranks and cuts like
+//              common.zig:140-166.
+// Why two counter groups: a sketch is busy from the first add until its read-back is done, and count + read-back of
+// one query take longer than the other roles need per query; with one sketch per group the groups overlap.
 // Exactness: a counter receives every posting whose docid maps to it, so a docid with count >= min_score makes
 // its counter hot, and a hot counter's postings are all enumerated; scores never come from the sketch.  A byte
 // that carries into its neighbour (128 + min_score arrivals at one counter) would corrupt the picture: the
@@ -934,14 +939,22 @@ search_sketch_kernel(BatchArgs a) {
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kHotCap = 32;   // hot counters per query handled here
 constexpr uint32_t kFoundCap = 32; // (warp, docid) findings per query; more -> exact count-table path
-// named barrier ids of search_find_kernel (0 is __syncthreads): resolver groups 1..3, counters 4, stage release 5..9,
-// "counted" 10..12 (one per resolver group), "sketch free" 13..14 (one per sketch)
-constexpr uint32_t kFbGroup = 1, kFbCounters = 4, kFbStage = 5, kFbCounted = 10, kFbSkFree = 13;
+// named barrier ids of search_find_kernel (0 is __syncthreads): counter groups 1..2, resolver groups 3..5, stage
+// release 6..10, "counted" 11..15 (one per stage: a stage's barrier cannot be arrived at again before the resolvers
+// that waited on it have released the stage)
+constexpr uint32_t kFbCounters = 1, kFbGroup = 3, kFbStage = 6, kFbCounted = 11;
+
+struct FindMeta { // one per stage: what travels with the staged query
+    WorkItem item;
+    uint32_t row_off[kSketchMaxRows]; // first docid of row r inside the stage
+    uint32_t row_len[kSketchMaxRows]; // postings in row r (without padding)
+    uint32_t hot[kHotCap];            // counters that reached min_score: word * 4 + byte
+    uint32_t n_hot, sum;              // sum: all bytes of the sketch after counting
+};
 
 struct FindState { // private to one resolver group
-    uint32_t hot[kHotCap];                              // counters that reached min_score: word * 4 + byte
     uint32_t found_id[kFoundCap], found_cnt[kFoundCap]; // what the group's warps found: docid, number of postings
-    uint32_t n_hot, n_found, sum;                       // sum: all bytes of the sketch after counting
+    uint32_t n_found;
 };
 
 // SKLOG: log2 of the sketch's 8-bit counters (15: 32 KB per sketch; 14: 16 KB, which leaves room for a fifth 32 KB
@@ -950,22 +963,22 @@ template <int STAGES, uint32_t STAGE_U4, int SKLOG> constexpr size_t find_smem_b
     return 2 * ((size_t)1 << SKLOG) + (size_t)STAGES * STAGE_U4 * 16;
 }
 
-template <int CW, int RG, int PW, int STAGES, uint32_t STAGE_U4, int SKLOG>
-__global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) search_find_kernel(BatchArgs a, uint32_t cls) {
-    static_assert(RG >= 2 && RG <= 3 && STAGES >= 2 && STAGES <= 5 && SKLOG >= 13 && SKLOG <= 15, "barrier ids, sketch size");
+template <int GW, int RG, int PW, int STAGES, uint32_t STAGE_U4, int SKLOG>
+__global__ void __launch_bounds__((2 * GW + RG * kSkResolverWarps + PW) * 32, 1) search_find_kernel(BatchArgs a, uint32_t cls) {
+    static_assert(RG >= 1 && RG <= 3 && STAGES >= 2 && STAGES <= 5 && SKLOG >= 13 && SKLOG <= 15, "barrier ids, sketch size");
     constexpr uint32_t kSketchBytes = 1u << SKLOG;            // one byte per counter
     constexpr uint32_t kSketchWords = kSketchBytes / 4;       // (shadows the round-1 kernel's constant)
     constexpr uint32_t kKeyShift = 32 - SKLOG;                // counter = h >> kKeyShift = word * 4 + byte
     constexpr uint32_t kWordMask = kSketchBytes - 4;          // byte offset of the counter's word
-    constexpr int kFirstResolver = CW;
-    constexpr int kFirstProducer = CW + RG * kSkResolverWarps;
+    constexpr int kFirstResolver = 2 * GW;
+    constexpr int kFirstProducer = 2 * GW + RG * kSkResolverWarps;
     constexpr int kAllThreads = (kFirstProducer + PW) * 32;
-    constexpr int kCounters = CW * 32;
+    constexpr uint32_t kGroup = GW * 32; // counter threads per group
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char *sketch_base = smem_raw; // 2 x 32 KB
+    unsigned char *sketch_base = smem_raw; // one sketch per counter group
     uint4 *stage = reinterpret_cast<uint4 *>(smem_raw + 2 * (size_t)kSketchBytes);
     __shared__ uint64_t full[STAGES]; // TMA completion; every other hand-over is a named barrier
-    __shared__ StageMeta meta[STAGES];
+    __shared__ FindMeta meta[STAGES];
     __shared__ FindState fs[RG];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -982,15 +995,16 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
         for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], PW); // every producer warp arrives with its share of the bytes
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // the two sketches start at the bias of this CTA's first two queries
-    for (uint32_t b = 0; b < 2; ++b) {
-        const unsigned long long idx = blockIdx.x + (unsigned long long)b * gridDim.x;
+    // each group's sketch starts at the bias of the group's first query
+    for (uint32_t g = 0; g < 2; ++g) {
+        const unsigned long long idx = blockIdx.x + (unsigned long long)g * gridDim.x;
         const uint32_t ms = idx < count ? items[idx].min_score : 2u;
         const uint32_t bias = (0x80u - ms) * 0x01010101u;
-        uint4 *sk4 = reinterpret_cast<uint4 *>(sketch_base + (size_t)b * kSketchBytes);
+        uint4 *sk4 = reinterpret_cast<uint4 *>(sketch_base + (size_t)g * kSketchBytes);
         for (uint32_t i = tid; i < kSketchWords / 4; i += kAllThreads) sk4[i] = make_uint4(bias, bias, bias, bias);
     }
-    if (tid < RG) fs[tid].n_hot = fs[tid].n_found = fs[tid].sum = 0u;
+    if (tid < RG) fs[tid].n_found = 0u;
+    if (tid < STAGES) meta[tid].n_hot = meta[tid].sum = 0u;
     __syncthreads();
 
     if (warp >= kFirstProducer) {
@@ -1084,60 +1098,15 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
         for (uint32_t it = gidx;; it += RG) {
             const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
             if (idx >= count) break;
-            const uint32_t s = it % STAGES, b = it & 1u;
-            uint4 *sk4 = reinterpret_cast<uint4 *>(sketch_base + (size_t)b * kSketchBytes);
-            // the sketch's next tenant is this CTA's query it + 2: clear to its bias
-            const unsigned long long idx2 = idx + 2ull * gridDim.x;
-            const uint32_t ms2 = idx2 < count ? items[idx2].min_score : 2u;
+            const uint32_t s = it % STAGES;
+            FindMeta &m = meta[s];
             const long long tr0 = clock64();
-            named_sync(kFbCounted + gidx, kCounters + kSkResolvers); // all counter warps are done with query it
+            named_sync(kFbCounted + s, kGroup + kSkResolvers); // a counter group has counted query it and read its sketch back
             if (gidx == 0 && rtid == 0) tick(3, tr0);
-            const WorkItem w = meta[s].item;
-            // read the sketch back: hot counters (bit 7 of a byte), the byte sum, and the clear for query it + 2
-            {
-                const uint32_t b2 = (0x80u - ms2) * 0x01010101u;
-                const uint4 clear4 = make_uint4(b2, b2, b2, b2);
-                uint32_t acc = 0;
-                // eight 16-byte pieces per thread and round, all loads of a round before anything else: shared memory
-                // answers slowly under the counters' atomics (the compiler keeps load - use pairs together otherwise)
-                constexpr uint32_t kPieces = kSketchWords / 4 / kSkResolvers; // 16 (8 with the 16 KB sketch)
-                static_assert(kPieces % 8 == 0, "rounds of eight loads");
-#pragma unroll 1
-                for (uint32_t r = 0; r < kPieces / 8; ++r) {
-                    uint4 v[8];
-#pragma unroll
-                    for (uint32_t k = 0; k < 8; ++k) v[k] = sk4[rtid + (r * 8 + k) * kSkResolvers];
-#pragma unroll
-                    for (uint32_t k = 0; k < 8; ++k) {
-                        const uint32_t i = rtid + (r * 8 + k) * kSkResolvers;
-                        if (!(a.debug & 16u)) sk4[i] = clear4;
-                        acc = __dp4a(v[k].x, 0x01010101u, acc);
-                        acc = __dp4a(v[k].y, 0x01010101u, acc);
-                        acc = __dp4a(v[k].z, 0x01010101u, acc);
-                        acc = __dp4a(v[k].w, 0x01010101u, acc);
-                        if ((v[k].x | v[k].y | v[k].z | v[k].w) & 0x80808080u) { // rare: a counter at bias + min_score or more
-#pragma unroll 1
-                            for (uint32_t e = 0; e < 4; ++e) {
-                                uint32_t m = (e == 0 ? v[k].x : e == 1 ? v[k].y : e == 2 ? v[k].z : v[k].w) & 0x80808080u;
-                                while (m) {
-                                    const uint32_t bit = __ffs(m) - 1u;
-                                    m &= m - 1u;
-                                    const uint32_t pos = atomicAdd(&st.n_hot, 1u);
-                                    if (pos < kHotCap) st.hot[pos] = ((i * 4u + e) << 2) | (bit >> 3); // word * 4 + byte
-                                }
-                            }
-                        }
-                    }
-                }
-                acc = __reduce_add_sync(0xFFFFFFFFu, acc);
-                if (lane == 0) atomicAdd(&st.sum, acc);
-            }
-            R.sync();
-            if (rwarp == 0) named_arrive(kFbSkFree + b, kCounters + 32); // the counters may start query it + 2 on this sketch
-            if (gidx == 0 && rtid == 0) tick(4, tr0);
-            const uint32_t n_hot = (a.debug & 2u) ? 0u : st.n_hot;
+            const WorkItem w = m.item;
+            const uint32_t n_hot = (a.debug & 2u) ? 0u : m.n_hot;
             // no byte carried <=> the bytes add up to the bias of every counter plus one per staged posting
-            bool redo = st.sum != kSketchBytes * (0x80u - w.min_score) + 4u * w.total4 && !(a.debug & 3u);
+            bool redo = m.sum != kSketchBytes * (0x80u - w.min_score) + 4u * w.total4 && !(a.debug & 3u);
             redo = redo || n_hot > kHotCap;
             if (n_hot != 0u && !redo) {
                 // Find the postings of the hot counters: thread rtid owns row rtid of the stage (<= 128 rows); the
@@ -1148,11 +1117,11 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
                 // one append to a list, not a probe chain into a table.
                 const bool has_row = rtid < w.n_rows;
                 const uint32_t *row = reinterpret_cast<const uint32_t *>(stage + (size_t)s * STAGE_U4) +
-                                      (has_row ? meta[s].row_off[rtid] : 0u);
-                const uint32_t len = has_row ? meta[s].row_len[rtid] : 0u;
+                                      (has_row ? m.row_off[rtid] : 0u);
+                const uint32_t len = has_row ? m.row_len[rtid] : 0u;
 #pragma unroll 1
                 for (uint32_t c = 0; c < n_hot; ++c) {
-                    const uint32_t kp = st.hot[c] << kKeyShift; // first row key of the counter
+                    const uint32_t kp = m.hot[c] << kKeyShift; // first row key of the counter
                     uint32_t lo = 0, hi = len; // every key before lo is below kp, every key from hi on is not
                     while (hi - lo > 8u) {
                         const uint32_t step = (hi - lo) / 9u + 1u;
@@ -1209,6 +1178,7 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
             R.sync(); // everyone is done with the stage; the findings are complete
             if (gidx == 0 && rtid == 0) tick(11, tr0);
             if (rwarp == 0) {
+                if (lane == 0) m.n_hot = m.sum = 0u;      // for the stage's next tenant
                 named_arrive(kFbStage + s, 32 * PW + 32); // the stage goes back to the producers
                 const uint32_t n_found = n_hot != 0u && !redo ? st.n_found : 0u;
                 redo = redo || n_found > kFoundCap;
@@ -1216,7 +1186,7 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
                 // score >= min_score (common.zig:140-145), rank and cut in registers (common.zig:147-166)
                 const uint32_t d = lane < n_found ? st.found_id[lane] : pad, sc = lane < n_found ? st.found_cnt[lane] : 0u;
                 __syncwarp();
-                if (lane == 0) st.n_hot = st.n_found = st.sum = 0u;
+                if (lane == 0) st.n_found = 0u;
                 uint32_t n_out = 0;
                 if (!redo && n_found != 0u) {
                     uint32_t total = 0;
@@ -1264,25 +1234,31 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
         return;
     }
 
-    // ===== counters: each warp streams its slice of every query and arrives on `counted`
-    for (uint32_t it = 0;; ++it) {
+    // ===== counters: group g = warps [g * GW, (g + 1) * GW) takes queries it = g, g + 2, ... with sketch g: count, then
+    // (the whole group together) read the sketch back: byte sum, hot counters, clear to the bias of the sketch's next
+    // tenant, this CTA's query it + 2
+    const uint32_t g = warp / GW, gwarp = warp - g * GW, gtid = gwarp * 32 + lane;
+    const uint32_t boff = g * kSketchBytes; // folded into the address by the same LOP3 that masks the word offset
+    uint4 *sk4 = reinterpret_cast<uint4 *>(sketch_base + boff);
+    constexpr int kScan = (int)((kSketchWords / 4 + kGroup - 1) / kGroup); // 16-byte pieces of the sketch per thread
+    for (uint32_t it = g;; it += 2) {
         const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
         if (idx >= count) break;
-        const uint32_t s = it % STAGES, b = it & 1u;
+        const uint32_t s = it % STAGES;
+        const unsigned long long idx2 = idx + 2ull * gridDim.x;
+        const uint32_t ms2 = idx2 < count ? items[idx2].min_score : 2u;
         const long long tc0 = clock64();
-        if (it >= 2) // sketch b was read back and cleared by the resolvers of query it - 2
-            named_sync(kFbSkFree + b, kCounters + 32);
-        if (warp == 0) { // one warp polls the TMA completion, the others park on a named barrier
+        if (gwarp == 0) { // one warp polls the TMA completion, the others park on the named barrier
             if (lane == 0) {
                 mbar_wait(&full[s], (it / STAGES) & 1, 0);
-                tick(7, tc0);
+                if (g == 0) tick(7, tc0);
             }
             __syncwarp();
         }
-        named_sync(kFbCounters, kCounters);
-        const uint32_t total4 = meta[s].item.total4;
+        named_sync(kFbCounters + g, kGroup);
+        FindMeta &m = meta[s];
+        const uint32_t total4 = m.item.total4;
         const uint4 *sg = stage + (size_t)s * STAGE_U4;
-        const uint32_t boff = b * kSketchBytes; // folded into the address by the same LOP3 that masks the word offset
         // Row padding is made of unused docids spread over many values: counted like anything else (the byte sum
         // expects it), never found by the resolvers (they search the true row lengths).
         auto add4 = [&](const uint4 v) {
@@ -1294,19 +1270,58 @@ __global__ void __launch_bounds__((CW + RG * kSkResolverWarps + PW) * 32, 1) sea
             }
         };
         if (!(a.debug & 1u)) {
-            uint32_t i = tid;
-            for (; i + 3 * kCounters < total4; i += 4 * kCounters) { // four loads in flight, then sixteen adds
-                const uint4 v0 = sg[i], v1 = sg[i + kCounters], v2 = sg[i + 2 * kCounters], v3 = sg[i + 3 * kCounters];
+            uint32_t i = gtid;
+            for (; i + 3 * kGroup < total4; i += 4 * kGroup) { // four loads in flight, then sixteen adds
+                const uint4 v0 = sg[i], v1 = sg[i + kGroup], v2 = sg[i + 2 * kGroup], v3 = sg[i + 3 * kGroup];
                 add4(v0);
                 add4(v1);
                 add4(v2);
                 add4(v3);
             }
-            for (; i < total4; i += kCounters) add4(sg[i]);
+            for (; i < total4; i += kGroup) add4(sg[i]);
+        }
+        if (g == 0 && gtid == 0) tick(8, tc0);
+        named_sync(kFbCounters + g, kGroup); // every warp of the group is done counting query it
+        {
+            const uint32_t b2 = (0x80u - ms2) * 0x01010101u;
+            const uint4 clear4 = make_uint4(b2, b2, b2, b2);
+            uint32_t acc = 0;
+#pragma unroll 1
+            for (int r0 = 0; r0 < kScan; r0 += 8) { // rounds of up to eight loads, all of them before anything else
+                uint4 v[8];
+#pragma unroll
+                for (int k8 = 0; k8 < 8; ++k8) {
+                    const uint32_t i = gtid + (uint32_t)(r0 + k8) * kGroup;
+                    v[k8] = (r0 + k8 < kScan && i < kSketchWords / 4) ? sk4[i] : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int k8 = 0; k8 < 8; ++k8) {
+                    const uint32_t i = gtid + (uint32_t)(r0 + k8) * kGroup;
+                    if (r0 + k8 < kScan && i < kSketchWords / 4 && !(a.debug & 16u)) sk4[i] = clear4;
+                    acc = __dp4a(v[k8].x, 0x01010101u, acc);
+                    acc = __dp4a(v[k8].y, 0x01010101u, acc);
+                    acc = __dp4a(v[k8].z, 0x01010101u, acc);
+                    acc = __dp4a(v[k8].w, 0x01010101u, acc);
+                    if ((v[k8].x | v[k8].y | v[k8].z | v[k8].w) & 0x80808080u) { // rare: a counter at bias + min_score or more
+#pragma unroll 1
+                        for (uint32_t e = 0; e < 4; ++e) {
+                            uint32_t hm = (e == 0 ? v[k8].x : e == 1 ? v[k8].y : e == 2 ? v[k8].z : v[k8].w) & 0x80808080u;
+                            while (hm) {
+                                const uint32_t bit = __ffs(hm) - 1u;
+                                hm &= hm - 1u;
+                                const uint32_t pos = atomicAdd(&m.n_hot, 1u);
+                                if (pos < kHotCap) m.hot[pos] = ((i * 4u + e) << 2) | (bit >> 3); // word * 4 + byte
+                            }
+                        }
+                    }
+                }
+            }
+            acc = __reduce_add_sync(0xFFFFFFFFu, acc);
+            if (lane == 0) atomicAdd(&m.sum, acc);
         }
         __syncwarp();
-        named_arrive(kFbCounted + it % RG, kCounters + kSkResolvers); // my slice of query it is in the sketch
-        if (warp == 0 && lane == 0) {
+        named_arrive(kFbCounted + s, kGroup + kSkResolvers); // query it is counted and its sketch read back
+        if (g == 0 && gtid == 0) {
             tick(9, tc0);
             if (timed) atomicAdd(&a.stats->dbg[10], 1ull);
         }
@@ -1803,7 +1818,7 @@ __global__ void __launch_bounds__(256) merge_packed_shards_kernel(const uint32_t
 // ------------------------------------------------------------------------------------------------
 // Warp split of the hot kernel: counter / resolver-group / producer warps (FPX_DEBUG_ABLATE bits 24..27 pick another
 // one for A/B runs).
-#define FPX_FIND_CONFIGS(X) X(0, 10, 3, 10, 5, 15) X(1, 10, 3, 10, 4, 15) X(2, 12, 3, 8, 5, 15) X(3, 8, 3, 12, 5, 15) X(4, 12, 2, 12, 5, 15) X(5, 14, 3, 6, 5, 15)
+#define FPX_FIND_CONFIGS(X) X(0, 8, 2, 8, 5, 15) X(1, 7, 2, 10, 5, 15) X(2, 6, 3, 8, 5, 15) X(3, 7, 3, 6, 5, 15) X(4, 9, 2, 6, 5, 15) X(5, 8, 2, 8, 4, 15) X(6, 10, 1, 8, 5, 15)
 
 cudaError_t configure_kernels() {
     cudaError_t e;
@@ -1815,13 +1830,13 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_sketch_kernel<14, 3, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
     if (e != cudaSuccess) return e;
-#define X(I, CW, RG, PW, ST, SK)                                                                                      \
-    e = cudaFuncSetAttribute(search_find_kernel<CW, RG, PW, ST, kStageU4, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+#define X(I, GW, RG, PW, ST, SK)                                                                                      \
+    e = cudaFuncSetAttribute(search_find_kernel<GW, RG, PW, ST, kStageU4, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                              (int)find_smem_bytes<ST, kStageU4, SK>());                                               \
     if (e != cudaSuccess) return e;
     FPX_FIND_CONFIGS(X)
 #undef X
-    e = cudaFuncSetAttribute(search_find_kernel<12, 3, 8, 3, kStageLargeU4, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(search_find_kernel<8, 2, 8, 3, kStageLargeU4, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)find_smem_bytes<3, kStageLargeU4, 15>());
     return e;
 }
@@ -1852,16 +1867,16 @@ void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms) {
         return;
     }
     switch ((a.debug >> 24) & 15u) {
-#define X(I, CW, RG, PW, ST, SK)                                                                                      \
+#define X(I, GW, RG, PW, ST, SK)                                                                                      \
     case I:                                                                                                           \
-        search_find_kernel<CW, RG, PW, ST, kStageU4, SK>                                                              \
-            <<<n_sms, (CW + 4 * RG + PW) * 32, find_smem_bytes<ST, kStageU4, SK>(), st>>>(a, kSketchClass);           \
+        search_find_kernel<GW, RG, PW, ST, kStageU4, SK>                                                              \
+            <<<n_sms, (2 * GW + 4 * RG + PW) * 32, find_smem_bytes<ST, kStageU4, SK>(), st>>>(a, kSketchClass);       \
         break;
         FPX_FIND_CONFIGS(X)
 #undef X
     default: break;
     }
-    search_find_kernel<12, 3, 8, 3, kStageLargeU4, 15><<<n_sms, 1024, find_smem_bytes<3, kStageLargeU4, 15>(), st>>>(a, kSketchLargeClass);
+    search_find_kernel<8, 2, 8, 3, kStageLargeU4, 15><<<n_sms, 1024, find_smem_bytes<3, kStageLargeU4, 15>(), st>>>(a, kSketchLargeClass);
 }
 
 void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms) {
