@@ -315,12 +315,6 @@ __global__ void keep_flags_kernel(const unsigned long long *keys, unsigned long 
     }
 }
 
-struct HashOf {
-    __host__ __device__ __forceinline__ uint32_t operator()(const unsigned long long &k) const { return (uint32_t)(k >> 32); }
-};
-struct DocOf {
-    __host__ __device__ __forceinline__ uint32_t operator()(const unsigned long long &k) const { return (uint32_t)k; }
-};
 struct Quads { // 64-bit so that the scan accumulates in 64 bits
     __host__ __device__ __forceinline__ unsigned long long operator()(const uint32_t &len) const { return (len + 3) >> 2; }
 };

@@ -5,13 +5,14 @@
 // Here, over a whole batch, against the CSR built by fpx_snapshot_host.h:
 //   prepare_kernel       one warp per query: dedup terms, probe the term directory, emit row
 //                        descriptors, bin the query by posting volume
-//   search_sketch_kernel the hot path (min_score >= 2, i.e. every HTTP-default query of >= 21 terms):
-//                        warp-specialised persistent CTAs.  Producer warps gather the query's posting rows
-//                        into a shared-memory stage with TMA bulk copies (cp.async.bulk + mbarrier
-//                        complete_tx); counter warps add every docid to a per-query sketch of 8-bit
-//                        counters with shared atomics and record the docids whose counter reaches
-//                        min_score; resolver warps count those few exactly in the staged rows and rank
-//                        them.  The sketch never under-counts, so this is exact.
+//   search_find_kernel   the hot path (2 <= min_score <= 128, i.e. every HTTP-default query of >= 21 terms whose
+//                        padded rows fit a shared-memory stage): warp-specialised persistent CTAs.  Producer warps
+//                        gather the query's posting rows into a stage with TMA bulk copies (cp.async.bulk + mbarrier
+//                        complete_tx); two groups of counter warps add every docid to a sketch of 8-bit counters with
+//                        fire-and-forget shared atomics, then read the sketch back for the counters that reached
+//                        min_score; resolver warps find those counters' postings in the staged rows (sorted by the
+//                        sketch hash), count them per docid exactly and rank.  The sketch never under-counts and
+//                        scores never come from it, so this is exact.
 //   search_smem_kernel   persistent CTAs, one query at a time: stream the rows with 128-bit loads,
 //                        count docids in a shared-memory open-addressing table (one packed 32-bit word
 //                        per doc: quotient tag | probe number | count), then scan the table, rank the
@@ -92,15 +93,9 @@ __device__ uint32_t make_item(const BatchArgs &a, uint32_t q, uint32_t rows_off,
     // (kHotCap is 32; beyond it the query is re-queued, so this is a matter of speed only).
     bool sketch_ok = a.use_sketch && o.min_score >= 2 && o.min_score <= 128 && total4 <= kStageLargeU4 &&
                      k_eff <= kFastKbuf && n_rows <= kSketchMaxRows;
-    if (a.debug & 0x2000u) { // round-1 kernel (A/B): records candidates while counting, 16384-counter limits
-        if (total4 > kStageU4) sketch_ok = false;
-        if (o.min_score == 2 && postings > 1500) sketch_ok = false;
-        if (o.min_score == 3 && postings > 4500) sketch_ok = false;
-    } else {
-        if (o.min_score == 2 && postings > 512) sketch_ok = false;
-        if (o.min_score == 3 && postings > 2900) sketch_ok = false;
-        if (o.min_score == 4 && postings > 7600) sketch_ok = false;
-    }
+    if (o.min_score == 2 && postings > 512) sketch_ok = false;
+    if (o.min_score == 3 && postings > 2900) sketch_ok = false;
+    if (o.min_score == 4 && postings > 7600) sketch_ok = false;
     if (!sketch_ok) return exact_class_for(postings, k_eff);
     return total4 <= kStageU4 ? (uint32_t)kSketchClass : (uint32_t)kSketchLargeClass;
 }
@@ -463,9 +458,6 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 // Two flavours of waiting.  try_wait with a suspend-time hint parks the thread in hardware (no issue slots
 // burnt, but the wake-up is not immediate); the plain form returns quickly and is polled.
 __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parity, uint32_t ns) {
@@ -495,7 +487,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32
         while (!mbar_try_wait(bar, parity)) __nanosleep(32);
     }
 }
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) { mbar_wait(bar, parity); }
 // global -> shared bulk copy (16-byte aligned, size multiple of 16), completion counted on `bar`
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -504,409 +495,8 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
-// ------------------------------------------------------------------------------------------------
-// sketch path (class 0): one persistent CTA per SM, 32 warps in three roles, no CTA-wide barrier anywhere —
-// every hand-over is an mbarrier, so each warp streams at its own pace and up to four queries are in
-// flight per SM (4 stages, 2 sketches):
-//   producers (8 warps)   TMA bulk copies (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) of the query's
-//                         posting rows into a ring of four 32 KB shared-memory stages.  Issue is the scarce
-//                         resource (~10 SASS instructions per copy through uniform registers), so the warps
-//                         split every query row-wise; row descriptors (with the row's place in the stage,
-//                         precomputed by prepare_kernel) sit in registers, loaded one query ahead.
-//   counters  (14 warps)  scatter-add every staged docid into a 32768 x u8 count sketch (two sketches,
-//                         alternating queries) with shared atomics.  The add returns the counter's previous
-//                         value; a posting that finds its counter already at min_score-1 or more records its
-//                         docid as a candidate.  A warp that finishes its slice arrives on `counted` and
-//                         moves straight on to the next query.
-//   resolvers (3 x 4 warps, taking queries in turn)  clear the sketch, de-duplicate the few candidates, count
-//                         each exactly by binary search in the staged rows (sorted by row_key(docid)), rank, apply the
-//                         reference's cutoffs, write the results, hand the stage back.
-// Why this is exact: a counter holds the sum of the true counts of all docids hashing to it and only grows
-// by one per posting.  If doc d has c >= min_score postings in the query, at most min_score-1 of them can
-// be among the first min_score-1 arrivals at its counter, so at least one posting of d arrives when the
-// counter is already >= min_score-1 and d is recorded.  Its exact count is then taken from the rows.
-// What bounds it: the request rate of the ~100 bulk copies per query and the counters'
-// shared atomics, about equally; not HBM bandwidth.
-// ------------------------------------------------------------------------------------------------
-constexpr int kSkResolverWarps = 4; // per group
-constexpr int kSkStages = 4;
+constexpr int kSkResolverWarps = 4; // per resolver group
 constexpr int kSkResolvers = kSkResolverWarps * 32;
-constexpr uint32_t kSketchLog = 14;       // 8192 words = 32 KB per sketch (search_sketch_kernel: 32768 u8 counters;
-                                          // search_sketch2_kernel: 16384 u16 counters)
-constexpr uint32_t kSketchWords = (1u << kSketchLog) / 2;
-constexpr uint32_t kRecCap = 512;         // candidate records per query (with repeats)
-constexpr uint32_t kSetSlots = 64;        // distinct-candidate hash set
-constexpr uint32_t kMaxCand = 32;         // distinct candidates handled here; more -> exact count-table path
-constexpr size_t kSkSmemBytes = 2 * (size_t)kSketchWords * 4 + (size_t)kSkStages * kStageU4 * 16 + 2 * kRecCap * 4;
-
-struct StageMeta {
-    WorkItem item;
-    uint32_t row_off[kSketchMaxRows]; // first docid of row r inside the stage
-    uint32_t row_len[kSketchMaxRows]; // postings in row r (without padding)
-};
-
-struct ResolverState { // private to one resolver group
-    uint32_t set_keys[kSetSlots];
-    uint32_t c_ids[kMaxCand], c_cnts[kMaxCand];
-    unsigned long long r_keys[kMaxCand];
-    uint32_t nset, ovf, c_n, r_count;
-};
-
-// named barrier ids (0 is __syncthreads): resolver groups 1..3, counters 4, stage release 5..8, "counted" 9..11 (one
-// per resolver group: two groups must never wait on the same id), "sketch free" 12..13 (one per sketch)
-constexpr uint32_t kBarGroup = 1, kBarCounters = 4, kBarStage = 5, kBarCounted = 9, kBarSkFree = 12, kBarTaken = 12;
-
-template <int kSkCounterWarps, int kSkResolverGroups, int kSkProducerWarps>
-__global__ void __launch_bounds__((kSkCounterWarps + kSkResolverGroups * kSkResolverWarps + kSkProducerWarps) * 32, 1)
-search_sketch_kernel(BatchArgs a) {
-    static_assert(kSkResolverGroups >= 2 && kSkResolverGroups <= 3, "barrier ids");
-    constexpr int kSkFirstResolver = kSkCounterWarps;
-    constexpr int kSkFirstProducer = kSkCounterWarps + kSkResolverGroups * kSkResolverWarps;
-    constexpr int kSkThreads = (kSkFirstProducer + kSkProducerWarps) * 32;
-    constexpr int kSkCounters = kSkCounterWarps * 32;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char *sketch_base = smem_raw;                                   // 2 x 32 KB
-    uint4 *stage = reinterpret_cast<uint4 *>(smem_raw + 2 * (size_t)kSketchWords * 4);
-    uint32_t *rec_base = reinterpret_cast<uint32_t *>(smem_raw + 2 * (size_t)kSketchWords * 4 + (size_t)kSkStages * kStageU4 * 16);
-    __shared__ uint64_t full[kSkStages]; // TMA completion; every other hand-over is a named barrier (ids 1..14)
-    __shared__ StageMeta meta[kSkStages];
-    __shared__ uint32_t s_nrec[2], s_known[2];
-    __shared__ ResolverState rs[kSkResolverGroups];
-
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t count = a.counters->qcount[kSketchClass];
-    const WorkItem *items = a.items + (size_t)kSketchClass * a.n_queries;
-    const uint32_t pad = a.snap.pad_id;
-    const uint32_t wm = (a.debug >> 6) & 3u; // wait flavour (profiling knob)
-    const bool timed = (a.debug & 512u) && blockIdx.x == 0 && a.stats != nullptr;
-    auto tick = [&](int slot, long long t0) {
-        if (timed) atomicAdd(&a.stats->dbg[slot], (unsigned long long)(clock64() - t0));
-    };
-
-    if (tid == 0) {
-        for (int s = 0; s < kSkStages; ++s) {
-            mbar_init(&full[s], kSkProducerWarps); // every producer warp arrives with its share of the bytes
-        }
-        for (int b = 0; b < 2; ++b) {
-            s_nrec[b] = 0;
-            s_known[b] = pad;
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (uint32_t i = tid; i < 2 * kSketchWords / 4; i += kSkThreads)
-        reinterpret_cast<uint4 *>(sketch_base)[i] = make_uint4(0, 0, 0, 0);
-    if (tid < kSkResolverGroups * kSetSlots) rs[tid / kSetSlots].set_keys[tid % kSetSlots] = pad;
-    if (tid < kSkResolverGroups) rs[tid].nset = rs[tid].ovf = 0;
-    __syncthreads();
-
-    if (warp >= kSkFirstProducer) {
-        // ===== producers: ALL producer warps fill one stage at a time, query after query (stage = it % kSkStages);
-        // warp p issues rows p, p + P, p + 2P, ... (lane l holds row P*l + p: one descriptor per lane, four with
-        // P = 8 for a 100-row query).  Issuing a bulk copy costs ~80 cycles of a warp, so spreading a query over
-        // every producer warp fills its stage in ~1 K cycles instead of ~4 K with a warp pair per stage: the stages
-        // turn over faster, and with four stages that is what bounds the kernel (Little's law).
-        constexpr int kP = kSkProducerWarps, kDesc = (kSketchMaxRows + 32 * kP - 1) / (32 * kP);
-        const uint32_t p = warp - kSkFirstProducer;
-        const uint4 *docids4 = reinterpret_cast<const uint4 *>(a.snap.docids);
-        auto item_at = [&](uint32_t it, WorkItem &w) -> bool {
-            const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
-            if (idx >= count) return false;
-            w = items[idx];
-            return true;
-        };
-        auto rows_of = [&](const WorkItem &w, uint4 (&d)[kDesc]) {
-#pragma unroll
-            for (int j = 0; j < kDesc; ++j) {
-                const uint32_t r = (uint32_t)kP * (lane + 32 * j) + p;
-                d[j] = r < w.n_rows ? a.rows[w.rows_off + r] : make_uint4(0u, 0u, 0u, 0u);
-            }
-        };
-        WorkItem w{}, w1{};
-        uint4 d[kDesc], d1[kDesc];
-        bool have = item_at(0, w);
-        if (have) rows_of(w, d);
-        for (uint32_t it = 0; have; ++it) {
-            const uint32_t s = it % kSkStages;
-            uint4 *dst = stage + (size_t)s * kStageU4;
-            const bool have1 = item_at(it + 1, w1); // the next query: in flight during wait + issue
-            if (have1) rows_of(w1, d1);
-            const long long tp0 = clock64();
-            if (it >= kSkStages) // wait until the resolvers released the previous tenant of this stage: us + their warp 0
-                named_sync(kBarStage + s, 32 * kP + 32);
-            if (p == 0 && lane == 0) tick(0, tp0);
-            // the row's place in the stage (d.z) was computed by prepare_kernel
-            uint32_t mine = 0;
-#pragma unroll
-            for (int j = 0; j < kDesc; ++j) mine += (d[j].y + 3) >> 2;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
-#pragma unroll
-            for (int j = 0; j < kDesc; ++j) { // stage directory for the exact recount
-                const uint32_t r = (uint32_t)kP * (lane + 32 * j) + p;
-                if (r < kSketchMaxRows) {
-                    meta[s].row_off[r] = d[j].z * 4u;
-                    meta[s].row_len[r] = d[j].y;
-                }
-            }
-            if (p == 0 && lane == 0) meta[s].item = w;
-            if (a.debug & 8u) mine = 0;
-            __syncwarp();
-            if (lane == 0) mbar_expect_tx(&full[s], mine * 16u); // expect_tx precedes my copies (release)
-            __syncwarp();
-            if (!(a.debug & 8u)) {
-#pragma unroll
-                for (int j = 0; j < kDesc; ++j)
-                    if (d[j].y) bulk_g2s(dst + d[j].z, docids4 + d[j].x, ((d[j].y + 3) >> 2) * 16u, &full[s]);
-            }
-            have = have1;
-            w = w1;
-#pragma unroll
-            for (int j = 0; j < kDesc; ++j) d[j] = d1[j];
-            if (p == 0 && lane == 0) {
-                tick(1, tp0);
-                if (timed) atomicAdd(&a.stats->dbg[2], 1ull);
-            }
-        }
-        return;
-    }
-
-    if (warp >= kSkFirstResolver) {
-        // ===== resolvers: group gidx takes every kSkResolverGroups-th query; query `it` used sketch / record buffer it & 1
-        const uint32_t gidx = (warp - kSkFirstResolver) / kSkResolverWarps;
-        const uint32_t rwarp = (warp - kSkFirstResolver) % kSkResolverWarps;
-        const uint32_t rtid = rwarp * 32 + lane;
-        const Group R{rtid, (uint32_t)kSkResolvers, kBarGroup + gidx};
-        const Group W{lane, 32u, 0u};
-        ResolverState &st = rs[gidx];
-        for (uint32_t it = gidx;; it += kSkResolverGroups) {
-            const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
-            if (idx >= count) break;
-            const uint32_t s = it % kSkStages, b = it & 1u;
-            uint4 *sk4 = reinterpret_cast<uint4 *>(sketch_base + (size_t)b * kSketchWords * 4);
-            const uint32_t *rec = rec_base + b * kRecCap;
-            const long long tr0 = clock64();
-            // all counter warps are done with query it (they arrive, this group waits)
-            named_sync(kBarCounted + gidx, kSkCounters + kSkResolvers);
-            if (gidx == 0 && rtid == 0) tick(3, tr0);
-            const WorkItem w = meta[s].item;
-            const uint32_t nrec = (a.debug & 2u) ? 0u : s_nrec[b];
-            // the sketch is no longer needed: clear it for query it+2
-            if (!(a.debug & 16u))
-                for (uint32_t i = rtid; i < kSketchWords / 4; i += kSkResolvers) sk4[i] = make_uint4(0, 0, 0, 0);
-            // distinct candidates (the true match is recorded a few times at most, see s_known)
-            if (nrec != 0u) {
-                if (nrec <= kRecCap) {
-                    for (uint32_t i = rtid; i < nrec; i += kSkResolvers) {
-                        const uint32_t d = rec[i];
-                        uint32_t x = (d * kMult2) >> 26;
-                        for (uint32_t tries = 0;; ++tries) {
-                            const uint32_t old = atomicCAS(st.set_keys + x, pad, d);
-                            if (old == pad) {
-                                if (atomicAdd(&st.nset, 1u) >= kMaxCand) st.ovf = 1u;
-                                break;
-                            }
-                            if (old == d) break;
-                            x = (x + 1) & (kSetSlots - 1);
-                            if (tries >= kSetSlots || st.ovf) {
-                                st.ovf = 1u;
-                                break;
-                            }
-                        }
-                    }
-                } else if (rtid == 0) {
-                    st.ovf = 1u;
-                }
-            }
-            R.sync();
-            if (rtid == 0) { // sketch cleared, records consumed: the counters may start query it+2 on them
-                s_nrec[b] = 0;
-                s_known[b] = pad;
-                if (gidx == 0) tick(4, tr0);
-            }
-            if (rwarp == 0) named_arrive(kBarSkFree + b, kSkCounters + 32);
-            uint32_t n = 0;
-            bool redo = false;
-            if (nrec != 0u) {
-                if (rwarp == 0) { // compact the set, reset it
-                    uint32_t nc = 0;
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const uint32_t k = st.set_keys[lane + 32 * half];
-                        const bool occ = k != pad;
-                        const uint32_t om = __ballot_sync(0xFFFFFFFFu, occ);
-                        const uint32_t pos = nc + __popc(om & ((1u << lane) - 1u));
-                        if (occ && pos < kMaxCand) {
-                            st.c_ids[pos] = k;
-                            st.c_cnts[pos] = 0;
-                        }
-                        nc += __popc(om);
-                        st.set_keys[lane + 32 * half] = pad;
-                    }
-                    if (lane == 0) st.c_n = min(nc, kMaxCand);
-                }
-                R.sync();
-                if (gidx == 0 && rtid == 0) tick(11, tr0);
-                redo = st.ovf != 0u;
-                const uint32_t nc = st.c_n;
-                if (!redo && nc != 0u) {
-                    // exact recount: every (candidate, row) pair is an equal-range search in a sorted row;
-                    // thread rtid owns row rtid (a query has at most 128 rows here; a thread without a row searches
-                    // an empty one, so that whole warps reach the reductions below)
-                    const bool has_row = rtid < w.n_rows;
-                    const uint32_t *row = reinterpret_cast<const uint32_t *>(stage + (size_t)s * kStageU4) +
-                                          (has_row ? meta[s].row_off[rtid] : 0u);
-                    const uint32_t len = has_row ? meta[s].row_len[rtid] : 0u;
-                    const uint32_t top = 1u << (31 - __clz(len | 1u));
-                    // four candidates at a time: the same halving steps for all (they depend on the row length only),
-                    // so the four chains of dependent loads overlap
-                    for (uint32_t c = 0; c < nc; c += 4) {
-                        const uint32_t nj = min(4u, nc - c); // the same for every thread: no divergence, no idle loads
-                        uint32_t d[4], dk[4], lo[4], m[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            d[j] = (uint32_t)j < nj ? st.c_ids[c + j] : 0u;
-                            dk[j] = row_key(d[j]); // rows are ascending by row_key (fpx_kernels.cuh)
-                            lo[j] = 0; // lower bound by halving steps: lo = #elements before d
-                            m[j] = 0;
-                        }
-                        for (uint32_t step = top; step; step >>= 1) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const uint32_t probe = lo[j] + step;
-                                if ((uint32_t)j < nj && probe <= len && row_key(row[probe - 1]) < dk[j]) lo[j] = probe;
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if ((uint32_t)j < nj)
-                                while (lo[j] + m[j] < len && row[lo[j] + m[j]] == d[j]) ++m[j]; // repeated (hash, id) pairs all count
-                        // the true match is found in most rows: one add per warp, not one per row (adds to one
-                        // address are served one after the other)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if ((uint32_t)j < nj) {
-                                const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, m[j]);
-                                if (lane == 0 && tot) atomicAdd(&st.c_cnts[c + j], tot);
-                            }
-                    }
-                }
-                R.sync();
-                if (gidx == 0 && rtid == 0) tick(12, tr0);
-                if (rwarp == 0 && !redo) {
-                    const bool keep = lane < nc && st.c_cnts[lane] >= w.min_score; // common.zig:140-145
-                    const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
-                    if (keep) st.r_keys[__popc(km & ((1u << lane) - 1u))] = rank_key(st.c_cnts[lane], st.c_ids[lane]);
-                    n = __popc(km);
-                    __syncwarp();
-                }
-            }
-            if (rtid == 0) st.nset = st.ovf = 0;
-            if (rwarp == 0) // the stage goes back to the producers
-                named_arrive(kBarStage + s, 32 * kSkProducerWarps + 32);
-            if (rwarp == 0) {
-                if (redo) {
-                    // too many candidates for this path: the exact count-table kernels take the query
-                    if (lane == 0) {
-                        enqueue(a, exact_class_for(w.postings, w.k_eff), w);
-                        if (a.stats) atomicAdd(&a.stats->overflow_requeues, 1ull);
-                    }
-                } else if (n == 0) {
-                    if (lane == 0) a.out_counts[w.q] = 0;
-                } else {
-                    group_sort_keys(W, st.r_keys, n, kMaxCand);
-                    group_emit_results(W, a, w, st.r_keys, n, &st.r_count);
-                }
-                if (lane == 0 && a.stats && !redo) atomicAdd(&a.stats->sketch_queries, 1ull);
-            }
-            if (gidx == 0 && rtid == 0) tick(13, tr0);
-            R.sync(); // the group's scratch is reused by its next query
-            if (gidx == 0 && rtid == 0) {
-                tick(5, tr0);
-                if (timed) atomicAdd(&a.stats->dbg[6], 1ull);
-            }
-        }
-        return;
-    }
-
-    // ===== counters: no CTA barrier — each warp streams its slice of every query and arrives on `counted`
-    for (uint32_t it = 0;; ++it) {
-        const unsigned long long idx = blockIdx.x + (unsigned long long)it * gridDim.x;
-        if (idx >= count) break;
-        const uint32_t s = it % kSkStages, b = it & 1u;
-        const long long tc0 = clock64();
-        // Hand-overs between the roles are named barriers (arrive / sync): parked warps cost no issue slots, polling
-        // loops do, and the kernel is issue bound.  Only the TMA completion needs an mbarrier: one counter warp
-        // polls it, the other fifteen wait on a named barrier.
-        if (it >= 2) // sketch b cleared, records consumed by the resolvers of query it-2
-            named_sync(kBarSkFree + b, kSkCounters + 32);
-        if (warp == 0) {
-            if (lane == 0) {
-                mbar_wait(&full[s], (it / kSkStages) & 1, wm);
-                tick(7, tc0);
-            }
-            __syncwarp();
-        }
-        named_sync(kBarCounters, kSkCounters);
-        const uint32_t total4 = meta[s].item.total4;
-        const uint32_t thr_m1 = meta[s].item.min_score - 1u; // min_score >= 2 in this class
-        const uint4 *st = stage + (size_t)s * kStageU4;
-        unsigned char *sketch_b = sketch_base + (size_t)b * kSketchWords * 4;
-        uint32_t *rec = rec_base + b * kRecCap;
-        // "some byte >= thr_m1" in two ALU ops: add (0x80 - thr_m1) to all four bytes, test bit 7 of each.
-        // Nothing carries across bytes while every counter of the word is <= 128; the first add that finds a
-        // counter at 128 necessarily takes the hot branch below and hands the query to the exact path.
-        const uint32_t bias = (0x80u - thr_m1) * 0x01010101u; // 2 <= min_score <= 128 in this class
-
-        // count sketch, four 8-bit counters per word (32768 counters): hash bits 29..17 pick the word, bits
-        // 31..30 the byte.  All four adds of a 16-byte granule are issued before any result is used.  Row padding
-        // is made of unused docids spread over many values, so it needs no test here: it is counted like
-        // anything else, can only make a counter too high, and an exact recount gives it score 0.
-        if (!(a.debug & 1u)) {
-#pragma unroll 2
-            for (uint32_t i = tid; i < total4; i += kSkCounters) {
-                const uint4 v = st[i];
-                const uint32_t dd[4] = {v.x, v.y, v.z, v.w};
-                uint32_t oo[4], sh[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const uint32_t hv = dd[e] * kMult;
-                    sh[e] = (hv >> 27) & 0x18u;
-                    oo[e] = atomicAdd(reinterpret_cast<uint32_t *>(sketch_b + ((hv >> 15) & 0x7FFCu)), 1u << sh[e]);
-                }
-                uint32_t t[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) t[e] = oo[e] + bias;
-                if ((t[0] | t[1] | t[2] | t[3]) & 0x80808080u) { // some counter in one of the four words is hot
-                    // a counter at 128: past this the byte tests can carry and the counter itself can wrap
-                    if ((oo[0] | oo[1] | oo[2] | oo[3]) & 0x80808080u) atomicAdd(&s_nrec[b], kRecCap + 1u);
-                    // The true match lands here once per matching row.  After its first record its docid is
-                    // "known": neutralise it and re-test, so the repeats leave after a dozen instructions
-                    // (a stale s_known only costs a repeated record).  (Reading it together with the granule instead
-                    // was measured slower.)
-                    const uint32_t known = s_known[b];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) t[e] = dd[e] == known ? 0u : t[e];
-                    if ((t[0] | t[1] | t[2] | t[3]) & 0x80808080u) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (t[e] & (0x80u << sh[e])) { // this posting's own counter
-                                const uint32_t p = atomicAdd(&s_nrec[b], 1u);
-                                if (p < kRecCap) rec[p] = dd[e];
-                                s_known[b] = dd[e];
-                            }
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        // my slice of query it is in the sketch
-        named_arrive(kBarCounted + it % kSkResolverGroups, kSkCounters + kSkResolvers);
-        if (warp == 0 && lane == 0) {
-            tick(9, tc0);
-            if (timed) atomicAdd(&a.stats->dbg[10], 1ull);
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // sketch path, "count, then find" (the hot kernel; classes kSketchClass and kSketchLargeClass).
@@ -967,7 +557,7 @@ template <int GW, int RG, int PW, int STAGES, uint32_t STAGE_U4, int SKLOG>
 __global__ void __launch_bounds__((2 * GW + RG * kSkResolverWarps + PW) * 32, 1) search_find_kernel(BatchArgs a, uint32_t cls) {
     static_assert(RG >= 1 && RG <= 3 && STAGES >= 2 && STAGES <= 5 && SKLOG >= 13 && SKLOG <= 15, "barrier ids, sketch size");
     constexpr uint32_t kSketchBytes = 1u << SKLOG;            // one byte per counter
-    constexpr uint32_t kSketchWords = kSketchBytes / 4;       // (shadows the round-1 kernel's constant)
+    constexpr uint32_t kSketchWords = kSketchBytes / 4;
     constexpr uint32_t kKeyShift = 32 - SKLOG;                // counter = h >> kKeyShift = word * 4 + byte
     constexpr uint32_t kWordMask = kSketchBytes - 4;          // byte offset of the counter's word
     constexpr int kFirstResolver = 2 * GW;
@@ -1818,7 +1408,9 @@ __global__ void __launch_bounds__(256) merge_packed_shards_kernel(const uint32_t
 // ------------------------------------------------------------------------------------------------
 // Warp split of the hot kernel: counter / resolver-group / producer warps (FPX_DEBUG_ABLATE bits 24..27 pick another
 // one for A/B runs).
-#define FPX_FIND_CONFIGS(X) X(0, 8, 2, 8, 5, 15) X(1, 7, 2, 10, 5, 15) X(2, 6, 3, 8, 5, 15) X(3, 7, 3, 6, 5, 15) X(4, 9, 2, 6, 5, 15) X(5, 8, 2, 8, 4, 15) X(6, 10, 1, 8, 5, 15)
+// Measured on C3 (tools/sweep.py, hot kernel per 100 K queries, profiles/r02/): 8/2/8 with four stages 1.120 ms,
+// five stages 1.145; 7/2/10 1.205; 6/3/8 1.200; 7/3/6 1.240; 9/2/6 1.161; 10/1/8 1.420; round-1 kernel 1.215.
+#define FPX_FIND_CONFIGS(X) X(0, 8, 2, 8, 4, 15) X(1, 8, 2, 8, 5, 15) X(2, 6, 3, 8, 5, 15) X(3, 9, 2, 6, 4, 15) X(4, 7, 2, 10, 4, 15)
 
 cudaError_t configure_kernels() {
     cudaError_t e;
@@ -1827,8 +1419,6 @@ cudaError_t configure_kernels() {
     e = cudaFuncSetAttribute(search_smem_kernel<14, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for<14, 256>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_smem_kernel<15, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for<15, 1024>());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(search_sketch_kernel<14, 3, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkSmemBytes);
     if (e != cudaSuccess) return e;
 #define X(I, GW, RG, PW, ST, SK)                                                                                      \
     e = cudaFuncSetAttribute(search_find_kernel<GW, RG, PW, ST, kStageU4, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -1862,10 +1452,6 @@ void launch_prepare_long(const BatchArgs &a, cudaStream_t st, int n_sms) {
 }
 
 void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms) {
-    if (a.debug & 0x2000u) { // round-1 kernel (A/B)
-        search_sketch_kernel<14, 3, 6><<<n_sms, 1024, kSkSmemBytes, st>>>(a);
-        return;
-    }
     switch ((a.debug >> 24) & 15u) {
 #define X(I, GW, RG, PW, ST, SK)                                                                                      \
     case I:                                                                                                           \
