@@ -185,7 +185,7 @@ struct fpx_ctx {
     int device = 0;
     int n_sms = 148;
     unsigned host_threads = 1;
-    uint32_t chunk_queries = 32768;
+    uint32_t chunk_queries = 65536;
     uint32_t flags = 0;
     bool host_only = false;
     bool use_sketch = true;
@@ -811,20 +811,23 @@ fpx_status search_batch_host(fpx_snapshot *s, uint64_t n_queries, const uint32_t
     uint64_t max_nq = 0, max_nt = 0;
     {
         const uint64_t chunk = std::max<uint64_t>(ctx->chunk_queries, (n_queries + kErrSlots - 17) / (kErrSlots - 16));
-        const uint64_t small = std::max<uint64_t>(1024, chunk / 8);
+        // every chunk costs a dozen kernel launches and a fill / drain of the persistent kernels (~0.05 ms), and the
+        // copy engine feeds queries faster than the kernels answer them: a small first chunk so that the kernels start
+        // early, then quickly growing ones
+        const uint64_t small = std::max<uint64_t>(1024, chunk / 16);
         uint64_t q = 0, step = small;
         bounds.push_back(0);
         while (q < n_queries) {
             const uint64_t left = n_queries - q;
             uint64_t take = std::min(step, left);
             if (left - take < small) take = left;                        // no tiny remainder ...
-            if (take == left && left >= 2 * small) take = left - small;  // ... but a small last chunk
-            const uint64_t q1 = q + take;
+            if (take == left && left >= 4 * small) take = left - small;  // ... but a small last chunk: little is left to
+            const uint64_t q1 = q + take;                                // copy back when the GPU is done
             max_nq = std::max(max_nq, q1 - q);
             max_nt = std::max(max_nt, term_offsets[q1] - term_offsets[q]);
             q = q1;
             bounds.push_back(q);
-            step = std::min(chunk, step * 2);
+            step = std::min(chunk, step * 4);
         }
     }
     const uint64_t n_chunks = bounds.size() - 1;

@@ -10,8 +10,9 @@ configuration BASELINE.json's metric is quoted on: 10 M fingerprints x 120 hashe
 
   value     whole-job queries/s with the batch already resident in HBM (fpx_search_batch_device), CUDA-event
             timed over exactly K steps, max over ranks
-  e2e       the same batch through the host-buffer C-ABI call fpx_search_batch (pinned host memory; H2D of the
-            queries and D2H of the results inside the timed region)
+  e2e       the same batch through the host-buffer C-ABI call fpx_search_batch_packed (pinned host memory; H2D of
+            the queries and D2H of the results — a list per query, as the reference returns them — inside the timed
+            region)
   roofline  the dominant kernel (search_find_kernel: TMA row gather + count sketch + exact resolve + top-k) —
             algorithmic bytes / its CUDA-event time, against the measured HBM peak in MEASURED_PEAKS.json
   cpu_baseline  the C++ restatement of the reference CPU path (oracle/), all host threads, bounded sample
@@ -375,13 +376,14 @@ def main():
         h_terms = torch.from_numpy(terms.reshape(-1).view(np.int32).copy()).pin_memory()
         h_offs = torch.from_numpy(offs.view(np.int64).copy()).pin_memory()
         h_opts = torch.from_numpy(opts.view(np.int32).copy()).pin_memory()
-        h_ids = torch.zeros((nq, K_STRIDE), dtype=torch.int32).pin_memory()
-        h_sc = torch.zeros((nq, K_STRIDE), dtype=torch.int32).pin_memory()
+        # results as the reference hands them out: a list per query (fpx_search_batch_packed: counts + pairs back to back)
         h_cnt = torch.zeros(nq, dtype=torch.int32).pin_memory()
+        h_pairs = torch.zeros((nq * K_STRIDE, 2), dtype=torch.int32).pin_memory()
+        n_pairs = [0]
 
         def e2e_step():
-            reader.search_batch_ptr(nq, h_terms.data_ptr(), h_offs.data_ptr(), h_opts.data_ptr(), K_STRIDE,
-                                    h_ids.data_ptr(), h_sc.data_ptr(), h_cnt.data_ptr())
+            n_pairs[0] = reader.search_batch_packed_ptr(nq, h_terms.data_ptr(), h_offs.data_ptr(), h_opts.data_ptr(), K_STRIDE,
+                                                        h_cnt.data_ptr(), h_pairs.data_ptr(), nq * K_STRIDE)
 
         for _ in range(3):
             e2e_step()
@@ -405,10 +407,12 @@ def main():
         h2d = int(h_terms.numel() * 4 + h_offs.numel() * 8 + h_opts.numel() * 4)
         d2h = int(prof_e2e["d2h_bytes"] // args.steps)   # counted by the library from what it moved
         # the e2e results must equal the device-resident ones
-        assert np.array_equal(h_cnt.numpy().view(np.uint32), r_cnt), "e2e and device-resident results differ"
+        e_cnt = h_cnt.numpy().view(np.uint32)
+        assert np.array_equal(e_cnt, r_cnt) and n_pairs[0] == int(r_cnt.sum()), "e2e and device-resident results differ"
         _m = np.arange(K_STRIDE)[None, :] < r_cnt[:, None]
-        assert np.array_equal(h_ids.numpy().view(np.uint32)[_m], r_ids[_m]) and \
-            np.array_equal(h_sc.numpy().view(np.uint32)[_m], r_sc[_m]), "e2e and device-resident results differ"
+        e_pairs = h_pairs.numpy().view(np.uint32)[:n_pairs[0]]
+        assert np.array_equal(e_pairs[:, 0], r_ids[_m]) and np.array_equal(e_pairs[:, 1], r_sc[_m]), \
+            "e2e and device-resident results differ"
         e2e = {"value": nq_total * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
                "h2d_ms_per_step": prof_e2e["h2d_ms"] / args.steps, "d2h_ms_per_step": prof_e2e["d2h_ms"] / args.steps,

@@ -406,7 +406,32 @@ def test_pinned_dma_and_pageable_packed_paths_agree(ctx, c2):
         got = reader.search_batch(terms.reshape(-1), offs, opts, 40)                    # packed path, same chunking
         assert np.array_equal(got[2], want[2]) and np.array_equal(got[0][mask], want[0][mask]) \
             and np.array_equal(got[1][mask], want[1][mask])
-    ctx.set_chunk_queries(32768)
+    ctx.set_chunk_queries(65536)
+
+
+def test_packed_result_api_matches_the_strided_one(ctx, c2):
+    """fpx_search_batch_packed (a list per query, as the reference returns results) against fpx_search_batch: same
+    counts, same (id, score) pairs in the same order, under fine chunking too; a too small pair buffer is reported
+    with the size needed and complete counts."""
+    syn, seg, snap, ix = c2
+    reader = pkg.IndexReader(snap)
+    terms, _ = syn.queries(6000, 100, seed=5150)
+    nq, T = terms.shape
+    offs = np.arange(nq + 1, dtype=np.uint64) * T
+    opts = pkg.synth.http_opts(nq, T)
+    opts[::3] = (40, 1, 0)                              # floor 1: dozens of results for a third of the queries
+    want = reader.search_batch(terms.reshape(-1), offs, opts, 40)
+    mask = np.arange(40)[None, :] < want[2][:, None]
+    for chunk in (65536, 1024):
+        ctx.set_chunk_queries(chunk)
+        cnt, pairs = reader.search_batch_packed(terms.reshape(-1), offs, opts, 40)
+        assert np.array_equal(cnt, want[2]) and len(pairs) == int(want[2].sum())
+        assert np.array_equal(pairs[:, 0], want[0][mask]) and np.array_equal(pairs[:, 1], want[1][mask])
+    ctx.set_chunk_queries(65536)
+    with pytest.raises(pkg.FpxError):
+        reader.search_batch_packed(terms.reshape(-1), offs, opts, 40, capacity_pairs=10)
+    e_cnt, e_pairs = reader.search_batch_packed(np.zeros(0, np.uint32), np.zeros(1, np.uint64), np.zeros((0, 3), np.uint32), 40)
+    assert len(e_cnt) == 0 and len(e_pairs) == 0
 
 
 def test_hot_kernel_variants_agree_with_the_oracle(ctx, c2):
