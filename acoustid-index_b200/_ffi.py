@@ -108,7 +108,7 @@ EXPORTS = [
     "fpx_snapshot_set_doc_range", "fpx_snapshot_compile", "fpx_snapshot_csr", "fpx_snapshot_commit",
     "fpx_snapshot_abort", "fpx_snapshot_acquire", "fpx_snapshot_release", "fpx_snapshot_get_info",
     "fpx_snapshot_row_lengths", "fpx_snapshot_read_row", "fpx_default_min_score", "fpx_search", "fpx_search_batch",
-    "fpx_search_batch_packed",
+    "fpx_search_batch_packed", "fpx_search_batch_timeout", "fpx_search_batch_device_async",
     "fpx_search_batch_device", "fpx_merge_shard_results", "fpx_profile_reset", "fpx_profile_read", "fpx_debug_set", "fpx_set_chunk_queries", "fpx_set_profile", "fpx_pack_results_device", "fpx_merge_packed_shards_device",
     "fpx_segment_write", "fpx_segment_buf_blocks", "fpx_segment_buf_block_index",
     "fpx_segment_buf_num_blocks", "fpx_segment_buf_num_items", "fpx_segment_buf_block_size",
@@ -174,6 +174,8 @@ def lib():
     L.fpx_debug_set.argtypes = [vp, C.c_uint32]
     L.fpx_set_chunk_queries.argtypes = [vp, C.c_uint32]
     L.fpx_set_profile.argtypes = [vp, C.c_int]
+    L.fpx_search_batch_timeout.argtypes = [vp, C.c_uint64, vp, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint32]
+    L.fpx_search_batch_device_async.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, vp, C.c_uint32, vp, vp, vp, vp, vp]
     L.fpx_search_batch_packed.argtypes = [vp, C.c_uint64, vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, vp]
     L.fpx_pack_results_device.argtypes = [C.c_uint64, C.c_uint32, vp, vp, vp, vp, C.c_uint32, vp]
     L.fpx_merge_packed_shards_device.argtypes = [C.c_uint32, C.c_uint64, vp, C.c_uint64, vp, C.c_uint32, vp, vp, vp, vp]

@@ -92,7 +92,6 @@ struct Workspace {
         DevBuf<uint32_t> d_ids, d_scores, d_counts, d_pack_offsets; // host batches: results before packing
         cudaEvent_t front_done = nullptr;
     } slot[kSlots];
-    DevBuf<unsigned long long> wide_tables; // only the (in-order) tail stream touches them
     cudaStream_t tail_stream = nullptr;
     cudaStream_t d2h_stream = nullptr; // result DMA of chunk c must not hold up the trailing kernels of chunk c+1
     cudaEvent_t tail_done = nullptr;
@@ -153,7 +152,6 @@ struct Workspace {
             if (sl.counters) cudaFree(sl.counters);
             if (sl.front_done) cudaEventDestroy(sl.front_done);
         }
-        wide_tables.release();
         d_terms.release();
         d_offsets.release();
         d_opts.release();
@@ -185,13 +183,18 @@ struct fpx_ctx {
     int device = 0;
     int n_sms = 148;
     unsigned host_threads = 1;
-    uint32_t chunk_queries = 65536;
+    uint32_t chunk_queries = 131072;
     uint32_t flags = 0;
     bool host_only = false;
     bool use_sketch = true;
     uint32_t debug = 0; // FPX_DEBUG_ABLATE environment variable, profiling only
     std::mutex mu;
     std::vector<Workspace *> free_ws;
+    // one pool of global-memory count tables for the rare wide path, shared by all workspaces: concurrent batches'
+    // wide kernels are chained on the device by `wide_done`
+    unsigned long long *d_wide = nullptr;
+    cudaEvent_t wide_done = nullptr;
+    std::mutex wide_mu;
     DeviceStats *d_stats = nullptr;
     std::vector<EventPair> pending;
     fpx_profile prof{};
@@ -240,7 +243,6 @@ fpx_status acquire_workspace(fpx_ctx *ctx, Workspace **out) {
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.front_done, cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaMallocHost(&w->h_error, kErrSlots * sizeof(uint32_t));
-    if (e == cudaSuccess) e = w->wide_tables.reserve((size_t)wide_ctas(ctx->n_sms) << kWideCapLog2);
     if (e != cudaSuccess) {
         delete w;
         return cuda_fail(e, "workspace allocation");
@@ -250,9 +252,18 @@ fpx_status acquire_workspace(fpx_ctx *ctx, Workspace **out) {
     return FPX_OK;
 }
 
+constexpr size_t kMaxIdleWorkspaces = 8; // a burst of concurrent callers does not pin its staging memory for good
+
 void release_workspace(fpx_ctx *ctx, Workspace *w) {
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    ctx->free_ws.push_back(w);
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (ctx->free_ws.size() < kMaxIdleWorkspaces) {
+            ctx->free_ws.push_back(w);
+            return;
+        }
+    }
+    if (w->done_pending) cudaEventSynchronize(w->done); // its last batch may still be running
+    delete w;
 }
 
 struct Timed {
@@ -310,7 +321,8 @@ fpx_status enqueue_batch(fpx_snapshot *s, Workspace *w, Workspace::Slot &sl, cud
     a.long_queue = sl.long_queue.p;
     a.counters = sl.counters;
     a.stats = (ctx->flags & FPX_FLAG_PROFILE) ? ctx->d_stats : nullptr;
-    a.wide_tables = w->wide_tables.p;
+    a.wide_tables = ctx->d_wide;
+    a.n_terms_total = n_terms_total;
     a.wide_cap_log2 = kWideCapLog2;
     a.use_sketch = ctx->use_sketch ? 1u : 0u;
     a.debug = ctx->debug;
@@ -336,8 +348,13 @@ fpx_status enqueue_batch(fpx_snapshot *s, Workspace *w, Workspace::Slot &sl, cud
         for (int c = 1; c <= 3; ++c) launch_search_class(a, c, ts, ctx->n_sms);
     }
     {
-        Timed t(ctx, ts, KK_WIDE);
-        launch_search_wide(a, ts, wide_ctas(ctx->n_sms));
+        std::lock_guard<std::mutex> lk(ctx->wide_mu); // wait, launch and record as one step of the chain
+        FPX_CUDA(cudaStreamWaitEvent(ts, ctx->wide_done, 0));
+        {
+            Timed t(ctx, ts, KK_WIDE);
+            launch_search_wide(a, ts, wide_ctas(ctx->n_sms));
+        }
+        FPX_CUDA(cudaEventRecord(ctx->wide_done, ts));
     }
     if (trace) cudaEventRecord(trace[2], ts);
     FPX_CUDA(cudaGetLastError());
@@ -464,8 +481,13 @@ fpx_status fpx_init(const fpx_config *config, fpx_ctx **out) {
         }
         if (e == cudaSuccess) e = cudaMalloc(&ctx->d_stats, sizeof(DeviceStats));
         if (e == cudaSuccess) e = cudaMemset(ctx->d_stats, 0, sizeof(DeviceStats));
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->d_wide, ((size_t)wide_ctas(ctx->n_sms) << kWideCapLog2) * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->wide_done, cudaEventDisableTiming);
         if (e != cudaSuccess) {
             fpx_status st = cuda_fail(e, "fpx_init");
+            if (ctx->d_stats) cudaFree(ctx->d_stats);
+            if (ctx->d_wide) cudaFree(ctx->d_wide);
+            if (ctx->wide_done) cudaEventDestroy(ctx->wide_done);
             delete ctx;
             return st;
         }
@@ -485,6 +507,8 @@ void fpx_shutdown(fpx_ctx *ctx) {
             cudaEventDestroy(p.b);
         }
         if (ctx->d_stats) cudaFree(ctx->d_stats);
+        if (ctx->d_wide) cudaFree(ctx->d_wide);
+        if (ctx->wide_done) cudaEventDestroy(ctx->wide_done);
     }
     delete ctx;
 }
@@ -711,11 +735,6 @@ fpx_status fpx_snapshot_read_row(const fpx_snapshot *s, uint32_t term, uint32_t 
 
 uint32_t fpx_default_min_score(uint64_t raw_query_len) { return (uint32_t)((raw_query_len + 19) / 20); }
 
-fpx_status fpx_search_batch_device(fpx_snapshot *s, uint64_t n_queries, const uint32_t *d_terms,
-                                   const uint64_t *d_term_offsets, const fpx_search_opts *d_opts, uint32_t k_stride,
-                                   uint32_t *d_out_ids, uint32_t *d_out_scores, uint32_t *d_out_counts,
-                                   void *cuda_stream);
-
 } // extern "C"
 
 namespace {
@@ -733,38 +752,56 @@ fpx_status device_total_terms(const uint64_t *d_offsets, uint64_t n_queries, cud
 
 extern "C" {
 
+fpx_status fpx_search_batch_device_async(fpx_snapshot *s, uint64_t n_queries, uint64_t term_base, uint64_t n_terms_total,
+                                         const uint32_t *d_terms, const uint64_t *d_term_offsets, const fpx_search_opts *d_opts,
+                                         uint32_t k_stride, uint32_t *d_out_ids, uint32_t *d_out_scores, uint32_t *d_out_counts,
+                                         uint32_t *d_status, void *cuda_stream) {
+    if (!s) return set_error(FPX_INVALID_ARGUMENT, "null snapshot");
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if (n_queries == 0) {
+        if (d_status) FPX_CUDA(cudaMemsetAsync(d_status, 0, sizeof(uint32_t), st));
+        return FPX_OK;
+    }
+    if (!d_term_offsets || !d_opts || !d_out_counts || (k_stride && (!d_out_ids || !d_out_scores)) || (n_terms_total && !d_terms))
+        return set_error(FPX_INVALID_ARGUMENT, "null buffer");
+    if (k_stride > FPX_MAX_RESULTS) return set_error(FPX_UNSUPPORTED, "k_stride exceeds FPX_MAX_RESULTS");
+    fpx_ctx *ctx = s->ctx;
+    FPX_CUDA(cudaSetDevice(ctx->device));
+    Workspace *w = nullptr;
+    fpx_status rc = acquire_workspace(ctx, &w);
+    if (rc != FPX_OK) return rc;
+    if (w->done_pending) { // its previous batch may still be running on another stream
+        cudaStreamWaitEvent(st, w->done, 0);
+        w->done_pending = false;
+    }
+    // term_offsets index d_terms absolutely; the row workspace is indexed relative to term_base
+    rc = enqueue_batch(s, w, w->slot[0], st, st, n_queries, n_terms_total, d_terms ? d_terms + term_base : nullptr, d_term_offsets,
+                       term_base, reinterpret_cast<const SearchOpts *>(d_opts), k_stride, d_out_ids, d_out_scores, d_out_counts);
+    if (rc == FPX_OK) {
+        // what the kernels raised (FPX_UNSUPPORTED / FPX_INVALID_ARGUMENT for a query outside the limits, else 0)
+        if (d_status) cudaMemcpyAsync(d_status, &w->slot[0].counters->error, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
+        cudaEventRecord(w->done, st);
+        w->done_pending = true;
+    }
+    release_workspace(ctx, w);
+    return rc;
+}
+
 fpx_status fpx_search_batch_device(fpx_snapshot *s, uint64_t n_queries, const uint32_t *d_terms,
                                    const uint64_t *d_term_offsets, const fpx_search_opts *d_opts, uint32_t k_stride,
                                    uint32_t *d_out_ids, uint32_t *d_out_scores, uint32_t *d_out_counts,
                                    void *cuda_stream) {
     if (!s) return set_error(FPX_INVALID_ARGUMENT, "null snapshot");
     if (n_queries == 0) return FPX_OK;
-    if (!d_term_offsets || !d_opts || !d_out_counts || (k_stride && (!d_out_ids || !d_out_scores)))
-        return set_error(FPX_INVALID_ARGUMENT, "null buffer");
-    if (k_stride > FPX_MAX_RESULTS) return set_error(FPX_UNSUPPORTED, "k_stride exceeds FPX_MAX_RESULTS");
-    fpx_ctx *ctx = s->ctx;
-    FPX_CUDA(cudaSetDevice(ctx->device));
+    if (!d_term_offsets) return set_error(FPX_INVALID_ARGUMENT, "null buffer");
+    FPX_CUDA(cudaSetDevice(s->ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    uint64_t first = 0, last = 0;
+    uint64_t first = 0, last = 0; // the one host round trip of this variant: the size of the batch's terms
     fpx_status rc = device_total_terms(d_term_offsets, n_queries, st, &first, &last);
     if (rc != FPX_OK) return rc;
     if (last < first) return set_error(FPX_INVALID_ARGUMENT, "term_offsets not ascending");
-    Workspace *w = nullptr;
-    rc = acquire_workspace(ctx, &w);
-    if (rc != FPX_OK) return rc;
-    if (w->done_pending) { // its previous batch may still be running on another stream
-        cudaStreamWaitEvent(st, w->done, 0);
-        w->done_pending = false;
-    }
-    // term_offsets index d_terms absolutely; the row workspace is indexed relative to the first offset
-    rc = enqueue_batch(s, w, w->slot[0], st, st, n_queries, last - first, d_terms ? d_terms + first : nullptr, d_term_offsets,
-                       first, reinterpret_cast<const SearchOpts *>(d_opts), k_stride, d_out_ids, d_out_scores, d_out_counts);
-    if (rc == FPX_OK) {
-        cudaEventRecord(w->done, st);
-        w->done_pending = true;
-    }
-    release_workspace(ctx, w);
-    return rc;
+    return fpx_search_batch_device_async(s, n_queries, first, last - first, d_terms, d_term_offsets, d_opts, k_stride, d_out_ids,
+                                         d_out_scores, d_out_counts, nullptr, cuda_stream);
 }
 
 } // extern "C"
@@ -779,7 +816,7 @@ struct PackedOut { // results as {count per query, (id, score) pairs back to bac
 
 fpx_status search_batch_host(fpx_snapshot *s, uint64_t n_queries, const uint32_t *terms, const uint64_t *term_offsets,
                              const fpx_search_opts *opts, uint32_t k_stride, uint32_t *out_ids, uint32_t *out_scores,
-                             uint32_t *out_counts, PackedOut *packed) {
+                             uint32_t *out_counts, PackedOut *packed, uint32_t timeout_ms = 0) {
     if (!s) return set_error(FPX_INVALID_ARGUMENT, "null snapshot");
     if (n_queries == 0) return FPX_OK;
     if (!term_offsets || !opts || !out_counts || (!packed && k_stride && (!out_ids || !out_scores)))
@@ -984,7 +1021,16 @@ fpx_status search_batch_host(fpx_snapshot *s, uint64_t n_queries, const uint32_t
     uint64_t d2h_bytes = 0;
     for (uint64_t c = 0; c < n_chunks && rc == FPX_OK; ++c) {
         if (tracing) tr[c].host_col0 = host_ms();
-        e = cudaEventSynchronize(w->chunk_done[c]);
+        if (timeout_ms) { // MultiIndex.zig:311-322: the request's deadline cancels the search (error.SearchTimeout)
+            while ((e = cudaEventQuery(w->chunk_done[c])) == cudaErrorNotReady && host_ms() < (double)timeout_ms) std::this_thread::yield();
+            if (e == cudaErrorNotReady) {
+                cudaGetLastError();
+                rc = set_error(FPX_TIMEOUT, "search timed out");
+                break; // what is in flight still writes the library's own buffers: the streams are drained below
+            }
+        } else {
+            e = cudaEventSynchronize(w->chunk_done[c]);
+        }
         if (e != cudaSuccess) {
             rc = cuda_fail(e, "search batch");
             break;
@@ -1073,6 +1119,12 @@ fpx_status fpx_search_batch(fpx_snapshot *s, uint64_t n_queries, const uint32_t 
                             const fpx_search_opts *opts, uint32_t k_stride, uint32_t *out_ids, uint32_t *out_scores,
                             uint32_t *out_counts) {
     return search_batch_host(s, n_queries, terms, term_offsets, opts, k_stride, out_ids, out_scores, out_counts, nullptr);
+}
+
+fpx_status fpx_search_batch_timeout(fpx_snapshot *s, uint64_t n_queries, const uint32_t *terms, const uint64_t *term_offsets,
+                                    const fpx_search_opts *opts, uint32_t k_stride, uint32_t *out_ids, uint32_t *out_scores,
+                                    uint32_t *out_counts, uint32_t timeout_ms) {
+    return search_batch_host(s, n_queries, terms, term_offsets, opts, k_stride, out_ids, out_scores, out_counts, nullptr, timeout_ms);
 }
 
 fpx_status fpx_search_batch_packed(fpx_snapshot *s, uint64_t n_queries, const uint32_t *terms, const uint64_t *term_offsets,

@@ -38,7 +38,7 @@ constexpr uint32_t kMultInv = inv32(kMult);
 static_assert(kMult * kMultInv == 1u, "modular inverse");
 static_assert(kMult == kRowMult, "rows are ordered by the hash the sketch counts with");
 
-constexpr uint32_t FPX_UNSUPPORTED_CODE = 7;
+constexpr uint32_t FPX_UNSUPPORTED_CODE = 7, FPX_INVALID_ARGUMENT_CODE = 2;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 
@@ -170,6 +170,14 @@ __global__ void __launch_bounds__(kThreads, 5) prepare_kernel(BatchArgs a) {
     for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < a.n_queries; q += warps_total) {
         const unsigned long long o0 = a.term_offsets[q] - a.term_base;
         const unsigned long long T64 = a.term_offsets[q + 1] - a.term_offsets[q];
+        // offsets that do not lie inside the batch's terms (the device API takes them on trust from device memory)
+        if (a.term_offsets[q] < a.term_base || a.term_offsets[q + 1] < a.term_offsets[q] || o0 + T64 > a.n_terms_total) {
+            if (lane == 0) {
+                a.counters->error = FPX_INVALID_ARGUMENT_CODE;
+                a.out_counts[q] = 0;
+            }
+            continue;
+        }
         if (T64 > kMaxQueryTerms) {
             if (lane == 0) {
                 a.counters->error = FPX_UNSUPPORTED_CODE;

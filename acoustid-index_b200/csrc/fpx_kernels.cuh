@@ -88,6 +88,7 @@ struct BatchArgs {
     const uint32_t *terms;
     const uint64_t *term_offsets;
     uint64_t term_base; // subtracted from term_offsets (chunked host batches)
+    uint64_t n_terms_total; // terms of the batch: term_offsets must stay within [term_base, term_base + n_terms_total]
     const SearchOpts *opts;
     uint32_t *out_ids, *out_scores, *out_counts;
     // workspace

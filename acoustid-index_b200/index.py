@@ -401,6 +401,23 @@ class IndexReader:
                                          k_stride, counts.ctypes.data, pairs.ctypes.data, cap)
         return counts, pairs[:n]
 
+    def search_batch_device_async(self, nq, term_base, n_terms_total, d_terms, d_offsets, d_opts, k_stride, d_ids, d_scores,
+                                  d_counts, d_status=None, stream=0):
+        """Device pointers (ints); never waits for the device (see fpx.h).  d_status: device word for what the kernels raise."""
+        check(lib().fpx_search_batch_device_async(self.snapshot.h, nq, term_base, n_terms_total, d_terms, d_offsets, d_opts,
+                                                  k_stride, d_ids, d_scores, d_counts, d_status, stream))
+
+    def search_batch_timeout(self, terms, offsets, opts, k_stride, timeout_ms):
+        """search_batch with a deadline: raises FpxError(FPX_TIMEOUT) like error.SearchTimeout."""
+        terms, offsets = _u32(terms), np.ascontiguousarray(offsets, dtype=np.uint64)
+        opts = np.ascontiguousarray(opts, dtype=np.uint32).reshape(-1, 3)
+        nq = len(offsets) - 1
+        ids, sc, cnt = np.zeros((nq, k_stride), np.uint32), np.zeros((nq, k_stride), np.uint32), np.zeros(nq, np.uint32)
+        check(lib().fpx_search_batch_timeout(self.snapshot.h, nq, terms.ctypes.data if len(terms) else None, offsets.ctypes.data,
+                                             opts.ctypes.data, k_stride, ids.ctypes.data, sc.ctypes.data, cnt.ctypes.data,
+                                             int(timeout_ms)))
+        return ids, sc, cnt
+
     def search_batch_device(self, nq, d_terms, d_offsets, d_opts, k_stride, d_ids, d_scores, d_counts, stream=0):
         """Device pointers (ints), asynchronous on `stream` (a cudaStream_t handle as int)."""
         check(lib().fpx_search_batch_device(self.snapshot.h, nq, d_terms, d_offsets, d_opts, k_stride, d_ids, d_scores,

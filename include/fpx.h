@@ -195,8 +195,28 @@ fpx_status fpx_search_batch_packed(fpx_snapshot *s, uint64_t n_queries, const ui
                                    uint32_t *out_counts, uint32_t *out_pairs, uint64_t capacity_pairs,
                                    uint64_t *out_n_pairs);
 
-/* Same, all buffers already in device memory, enqueued on `cuda_stream` (a cudaStream_t; NULL = the
- * legacy default stream).  Asynchronous: results are ready when the stream reaches this point. */
+/* fpx_search_batch with the request's deadline (api.SearchRequest.timeout, api.zig:7-8; MultiIndex.zig:311-322 cancels
+ * the search and returns error.SearchTimeout): FPX_TIMEOUT when the batch is not answered within timeout_ms
+ * (0 = no deadline); the output arrays are then undefined.  The call still returns only after the GPU work it
+ * enqueued has drained (it writes the library's own buffers). */
+fpx_status fpx_search_batch_timeout(fpx_snapshot *s, uint64_t n_queries, const uint32_t *terms,
+                                    const uint64_t *term_offsets, const fpx_search_opts *opts, uint32_t k_stride,
+                                    uint32_t *out_ids, uint32_t *out_scores, uint32_t *out_counts,
+                                    uint32_t timeout_ms);
+
+/* The batch with all buffers already in device memory, enqueued on `cuda_stream` (a cudaStream_t; NULL = the legacy
+ * default stream).  fpx_search_batch_device_async never waits for the device: the caller states where the batch's
+ * terms lie — term_base = term_offsets[0], n_terms_total = term_offsets[n_queries] - term_offsets[0] (this sizes the
+ * row workspace; offsets outside that window are rejected on the device) — and results are ready when the stream
+ * reaches this point, so calls can be queued back to back or captured in a CUDA graph.  What the kernels raise cannot
+ * come back as a return value: *d_status (device memory, optional) receives 0, or FPX_UNSUPPORTED /
+ * FPX_INVALID_ARGUMENT when a query lies outside the limits below / has bad offsets; such a query has count 0.
+ * fpx_search_batch_device reads the two offsets back itself (one stream synchronisation) and has no status word. */
+fpx_status fpx_search_batch_device_async(fpx_snapshot *s, uint64_t n_queries, uint64_t term_base,
+                                         uint64_t n_terms_total, const uint32_t *d_terms,
+                                         const uint64_t *d_term_offsets, const fpx_search_opts *d_opts,
+                                         uint32_t k_stride, uint32_t *d_out_ids, uint32_t *d_out_scores,
+                                         uint32_t *d_out_counts, uint32_t *d_status, void *cuda_stream);
 fpx_status fpx_search_batch_device(fpx_snapshot *s, uint64_t n_queries, const uint32_t *d_terms,
                                    const uint64_t *d_term_offsets, const fpx_search_opts *d_opts,
                                    uint32_t k_stride, uint32_t *d_out_ids, uint32_t *d_out_scores,

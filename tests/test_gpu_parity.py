@@ -406,7 +406,79 @@ def test_pinned_dma_and_pageable_packed_paths_agree(ctx, c2):
         got = reader.search_batch(terms.reshape(-1), offs, opts, 40)                    # packed path, same chunking
         assert np.array_equal(got[2], want[2]) and np.array_equal(got[0][mask], want[0][mask]) \
             and np.array_equal(got[1][mask], want[1][mask])
-    ctx.set_chunk_queries(65536)
+    ctx.set_chunk_queries(131072)
+
+
+def test_async_device_api_queues_batches_without_a_sync(ctx, c2):
+    """fpx_search_batch_device_async: 20 batches enqueued back to back on one stream with no host synchronisation in
+    between (each into its own output arrays), then one sync: every batch must carry the oracle's answers.  The status
+    word reports what the kernels raised: 0 for good batches, FPX_UNSUPPORTED for a batch holding a query with more than
+    FPX_MAX_QUERY_TERMS terms (count 0 for that query, the others answered), FPX_INVALID_ARGUMENT for offsets outside
+    the stated window."""
+    import torch
+    syn, seg, snap, ix = c2
+    reader = pkg.IndexReader(snap)
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.Stream(device=dev)
+    nb, nq, T = 20, 700, 100
+    terms, _ = syn.queries(nb * nq, T, seed=2468)
+    opts = pkg.synth.http_opts(nb * nq, T)
+    d_terms = torch.from_numpy(terms.reshape(-1).view(np.int32)).to(dev)
+    d_offs = torch.from_numpy((np.arange(nb * nq + 1, dtype=np.uint64) * T).view(np.int64)).to(dev)
+    d_opts = torch.from_numpy(opts.view(np.int32)).to(dev)
+    outs = [(torch.zeros((nq, 40), dtype=torch.int32, device=dev), torch.zeros((nq, 40), dtype=torch.int32, device=dev),
+             torch.zeros(nq, dtype=torch.int32, device=dev), torch.full((1,), 99, dtype=torch.int32, device=dev)) for _ in range(nb)]
+    torch.cuda.synchronize()
+    for b in range(nb):                                  # the offsets of batch b start at element b * nq of d_offs
+        o = outs[b]
+        reader.search_batch_device_async(nq, b * nq * T, nq * T, d_terms.data_ptr(), d_offs.data_ptr() + 8 * b * nq,
+                                         d_opts.data_ptr() + 12 * b * nq, 40, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(),
+                                         o[3].data_ptr(), stream.cuda_stream)
+    stream.synchronize()
+    oi, os_, oc, _ = ix.search_batch(terms.reshape(-1), np.arange(nb * nq + 1, dtype=np.uint64) * T, opts, 40, n_threads=16)
+    for b in range(nb):
+        ids, sc, cnt, status = [x.cpu().numpy().view(np.uint32) for x in outs[b]]
+        assert status[0] == 0
+        sl = slice(b * nq, (b + 1) * nq)
+        assert np.array_equal(cnt, oc[sl])
+        mask = np.arange(40)[None, :] < cnt[:, None]
+        assert np.array_equal(ids[mask], oi[sl][mask]) and np.array_equal(sc[mask], os_[sl][mask])
+    # a batch with one oversize query (8193 terms): status FPX_UNSUPPORTED, count 0 there, the neighbours answered
+    big = np.concatenate([terms[0], np.arange(8193, dtype=np.uint32), terms[1]])
+    offs2 = np.array([0, T, T + 8193, 2 * T + 8193], dtype=np.uint64)
+    d_t2 = torch.from_numpy(big.view(np.int32)).to(dev)
+    d_o2 = torch.from_numpy(offs2.view(np.int64)).to(dev)
+    o = [torch.zeros((3, 40), dtype=torch.int32, device=dev), torch.zeros((3, 40), dtype=torch.int32, device=dev),
+         torch.full((3,), 7, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev)]
+    reader.search_batch_device_async(3, 0, len(big), d_t2.data_ptr(), d_o2.data_ptr(), d_opts.data_ptr(), 40, o[0].data_ptr(),
+                                     o[1].data_ptr(), o[2].data_ptr(), o[3].data_ptr(), stream.cuda_stream)
+    stream.synchronize()
+    cnt = o[2].cpu().numpy().view(np.uint32)
+    assert int(o[3].item()) == pkg._ffi.FPX_UNSUPPORTED and cnt[1] == 0 and cnt[0] == oc[0] and cnt[2] == oc[1]
+    # offsets that leave the stated window: FPX_INVALID_ARGUMENT on the device, nothing read out of bounds
+    reader.search_batch_device_async(3, 0, 50, d_t2.data_ptr(), d_o2.data_ptr(), d_opts.data_ptr(), 40, o[0].data_ptr(),
+                                     o[1].data_ptr(), o[2].data_ptr(), o[3].data_ptr(), stream.cuda_stream)
+    stream.synchronize()
+    assert int(o[3].item()) == pkg._ffi.FPX_INVALID_ARGUMENT and (o[2].cpu().numpy() == 0).all()
+
+
+def test_batch_deadline_mirrors_search_timeout(ctx, c2):
+    """fpx_search_batch_timeout: a generous deadline gives the normal answer, an impossible one FPX_TIMEOUT
+    (error.SearchTimeout, MultiIndex.zig:311-322) — and the context keeps working afterwards."""
+    syn, seg, snap, ix = c2
+    reader = pkg.IndexReader(snap)
+    terms, _ = syn.queries(40000, 100, seed=1357)
+    nq, T = terms.shape
+    offs = np.arange(nq + 1, dtype=np.uint64) * T
+    opts = np.tile(np.array((100, 1, 0), dtype=np.uint32), (nq, 1))     # floor 1: the exact count-table path, several ms
+    want = reader.search_batch(terms.reshape(-1), offs, opts, 100)
+    got = reader.search_batch_timeout(terms.reshape(-1), offs, opts, 100, 60_000)
+    assert np.array_equal(got[2], want[2]) and np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    with pytest.raises(pkg.FpxError) as err:
+        reader.search_batch_timeout(terms.reshape(-1), offs, opts, 100, 1)
+    assert err.value.status == pkg._ffi.FPX_TIMEOUT
+    again = reader.search_batch(terms.reshape(-1), offs, opts, 100)
+    assert np.array_equal(again[2], want[2]) and np.array_equal(again[0], want[0])
 
 
 def test_packed_result_api_matches_the_strided_one(ctx, c2):
@@ -422,12 +494,12 @@ def test_packed_result_api_matches_the_strided_one(ctx, c2):
     opts[::3] = (40, 1, 0)                              # floor 1: dozens of results for a third of the queries
     want = reader.search_batch(terms.reshape(-1), offs, opts, 40)
     mask = np.arange(40)[None, :] < want[2][:, None]
-    for chunk in (65536, 1024):
+    for chunk in (131072, 1024):
         ctx.set_chunk_queries(chunk)
         cnt, pairs = reader.search_batch_packed(terms.reshape(-1), offs, opts, 40)
         assert np.array_equal(cnt, want[2]) and len(pairs) == int(want[2].sum())
         assert np.array_equal(pairs[:, 0], want[0][mask]) and np.array_equal(pairs[:, 1], want[1][mask])
-    ctx.set_chunk_queries(65536)
+    ctx.set_chunk_queries(131072)
     with pytest.raises(pkg.FpxError):
         reader.search_batch_packed(terms.reshape(-1), offs, opts, 40, capacity_pairs=10)
     e_cnt, e_pairs = reader.search_batch_packed(np.zeros(0, np.uint32), np.zeros(1, np.uint64), np.zeros((0, 3), np.uint32), 40)

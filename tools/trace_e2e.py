@@ -1,28 +1,42 @@
 #!/usr/bin/env python
-"""Timeline of one fpx_search_batch call (FPX debug bit 11): python tools/trace_e2e.py [chunk]"""
-import os, sys
+"""The host-buffer call fpx_search_batch_packed on c3 with pinned buffers: wall time per chunk size, and the per-chunk
+timeline of one call (FPX debug bit 11).   python tools/trace_e2e.py [chunk ...]"""
+import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench, torch
 import __graft_entry__ as graft
 pkg = graft.load_package()
-wl = "c3"
-syn, items, doc_ids, doc_alive = bench.build_corpus(pkg, wl, "cuda:0")
-seg = pkg.FileSegment.from_items(items, doc_ids, doc_alive, commit_id=1, threads=os.cpu_count())
-del items
+wl = os.environ.get("WL", "c3")
+syn = bench.make_synth(pkg, wl, "cuda:0")
 ctx = pkg.Context(device=0, profile=False, host_threads=os.cpu_count())
-snap = pkg.swap_snapshot(ctx, [seg])
+snap, _ = bench.build_snapshot(pkg, ctx, syn, wl, os.cpu_count(), keep_segments=False)
 reader = pkg.IndexReader(snap)
-terms, offs, nq, T = bench.make_queries(syn, wl, 0)
+terms, offs, nq, T = bench.make_queries(syn, wl, 0, 1, "replicated")
 opts = pkg.synth.http_opts(nq, T)
 K = bench.K_STRIDE
 h = [torch.from_numpy(terms.reshape(-1).view(np.int32).copy()).pin_memory(), torch.from_numpy(offs.view(np.int64).copy()).pin_memory(),
-     torch.from_numpy(opts.view(np.int32).copy()).pin_memory(), torch.zeros((nq, K), dtype=torch.int32).pin_memory(),
-     torch.zeros((nq, K), dtype=torch.int32).pin_memory(), torch.zeros(nq, dtype=torch.int32).pin_memory()]
-for ch in [int(x) for x in (sys.argv[1:] or ["32768"])]:
+     torch.from_numpy(opts.view(np.int32).copy()).pin_memory(), torch.zeros(nq, dtype=torch.int32).pin_memory(),
+     torch.zeros((nq * K, 2), dtype=torch.int32).pin_memory()]
+
+
+def step():
+    reader.search_batch_packed_ptr(nq, h[0].data_ptr(), h[1].data_ptr(), h[2].data_ptr(), K, h[3].data_ptr(), h[4].data_ptr(), nq * K)
+
+
+for ch in [int(x) for x in (sys.argv[1:] or ["65536"])]:
     ctx.set_chunk_queries(ch)
-    for i in range(4):
-        ctx.debug_set(2048 if i == 3 else 0)
-        reader.search_batch_ptr(nq, h[0].data_ptr(), h[1].data_ptr(), h[2].data_ptr(), K, h[3].data_ptr(), h[4].data_ptr(), h[5].data_ptr())
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        step()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / 10 * 1e3
+    print("chunk %6d: %.3f ms per call, %.1fM q/s" % (ch, ms, nq / ms / 1e3), flush=True)
+    ctx.debug_set(2048)
+    step()
+    ctx.debug_set(0)
     print("---- chunk", ch, flush=True)
