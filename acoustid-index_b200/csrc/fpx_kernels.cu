@@ -942,9 +942,11 @@ template <int LOG> struct Packed {
 // One packed word per distinct docid:  [ rem : 32-LOG | probe : 5 | count : LOG-5 ].
 // hv = d*kMult is a bijection; its top LOG bits are the home slot, the rest is `rem`.  Probing is double
 // hashing with an odd step derived from rem, so (slot, probe, rem) identifies d exactly.
-template <int LOG> __device__ __forceinline__ void table_insert(uint32_t *tab, uint32_t d, uint32_t *ovf) {
+// `rot`: multi-pass queries split the key space by the top `rot` bits of hv (one key range per pass, see
+// search_smem_kernel), so those bits are the same for every docid of a pass: the key is rotated left by `rot` first.
+template <int LOG> __device__ __forceinline__ void table_insert(uint32_t *tab, uint32_t d, uint32_t *ovf, uint32_t rot = 0) {
     using P = Packed<LOG>;
-    const uint32_t hv = d * kMult;
+    const uint32_t hv = __funnelshift_l(d * kMult, d * kMult, rot);
     const uint32_t rem = hv & P::kRemMask;
     const uint32_t step = ((rem << 1) | 1u) & P::kSlotMask;
     const uint32_t tagbase = rem << (P::kProbeBits + P::kCntBits);
@@ -964,13 +966,14 @@ template <int LOG> __device__ __forceinline__ void table_insert(uint32_t *tab, u
     *ovf = 1u; // probe number does not fit
 }
 
-template <int LOG> __device__ __forceinline__ uint32_t table_docid(uint32_t word, uint32_t slot) {
+template <int LOG> __device__ __forceinline__ uint32_t table_docid(uint32_t word, uint32_t slot, uint32_t rot = 0) {
     using P = Packed<LOG>;
     const uint32_t rem = word >> (P::kProbeBits + P::kCntBits);
     const uint32_t probe = (word >> P::kCntBits) & 31u;
     const uint32_t step = ((rem << 1) | 1u) & P::kSlotMask;
     const uint32_t home = (slot - probe * step) & P::kSlotMask;
-    return ((home << P::kRemBits) | rem) * kMultInv;
+    const uint32_t hv = (home << P::kRemBits) | rem;
+    return __funnelshift_r(hv, hv, rot) * kMultInv;
 }
 
 constexpr uint32_t kSmemRowsChunk = 128; // row descriptors staged per round by the shared-memory kernels
@@ -993,6 +996,7 @@ __global__ void __launch_bounds__(THREADS, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))
     unsigned long long *kbuf = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)P::kSlots * 4);
     uint4 *rows_s = reinterpret_cast<uint4 *>(smem_raw + (size_t)P::kSlots * 4 + kKbufCap * 8);
     __shared__ uint32_t s_idx, s_ncand, s_ovf, s_count, s_qual;
+    __shared__ uint32_t s_cur[kSmemRowsChunk]; // multi-pass: per row, the first granule of the next pass
     __shared__ unsigned long long s_kth; // running threshold: only keys below it can still make the top k_eff
 
     constexpr int cls = LOG - 12;
@@ -1020,10 +1024,16 @@ __global__ void __launch_bounds__(THREADS, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))
         const uint32_t thr = max(w.min_score, 1u); // a doc in the table has score >= 1
         const uint32_t k_eff = min(w.k_eff, kFastKbuf);
         const uint4 *rows = a.rows + w.rows_off;
-        uint32_t passes = 1;
+        // More postings than the table holds: several passes, pass p counting the docids whose key h = docid * kMult
+        // has the top log2(passes) bits p.  Rows are sorted by h (fpx_kernels.cuh: row_key), so a pass's postings are one
+        // contiguous piece of every row and each pass reads only its piece: the warp that owns a row keeps a cursor.
+        uint32_t passes = 1, rot = 0;
         if (LOG == 15)
-            while ((unsigned long long)passes * 12288ull < w.postings && w.postings > 16384u) passes <<= 1;
-        const uint32_t pmask = passes - 1u;
+            while ((unsigned long long)passes * 12288ull < w.postings && w.postings > 16384u) {
+                passes <<= 1;
+                ++rot;
+            }
+        const bool keep_cursors = w.n_rows <= kRows; // one chunk of rows: the cursors survive from pass to pass
 
         for (uint32_t pass = 0; pass < passes; ++pass) {
             for (uint32_t r0 = 0; r0 < w.n_rows; r0 += kRows) {
@@ -1031,24 +1041,66 @@ __global__ void __launch_bounds__(THREADS, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))
                 __syncthreads();
                 for (uint32_t i = tid; i < nr; i += kThreads) rows_s[i] = rows[r0 + i];
                 __syncthreads();
-                // a warp per posting row, 128-bit loads, two rows in flight; the tail of a row's last
-                // 16-byte granule is padding (a repeat of the last docid) and is masked by position
-                for (uint32_t r = warp * 2; r < nr; r += kWarps * 2) {
-                    const uint4 ra = rows_s[r];
-                    const uint4 rb = (r + 1 < nr) ? rows_s[r + 1] : make_uint4(0u, 0u, 0u, 0u);
-                    const uint32_t na = (ra.y + 3) >> 2, nb = (rb.y + 3) >> 2;
-                    const uint32_t nmax = max(na, nb);
-                    for (uint32_t i = lane; i < nmax; i += 32) {
-                        uint4 va = make_uint4(0, 0, 0, 0), vb = va;
-                        if (i < na) va = __ldg(docids4 + ra.x + i);
-                        if (i < nb) vb = __ldg(docids4 + rb.x + i);
-                        const uint32_t d[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+                if (passes == 1) {
+                    // a warp per posting row, 128-bit loads, two rows in flight; the tail of a row's last
+                    // 16-byte granule is padding and is masked by position
+                    for (uint32_t r = warp * 2; r < nr; r += kWarps * 2) {
+                        const uint4 ra = rows_s[r];
+                        const uint4 rb = (r + 1 < nr) ? rows_s[r + 1] : make_uint4(0u, 0u, 0u, 0u);
+                        const uint32_t na = (ra.y + 3) >> 2, nb = (rb.y + 3) >> 2;
+                        const uint32_t nmax = max(na, nb);
+                        for (uint32_t i = lane; i < nmax; i += 32) {
+                            uint4 va = make_uint4(0, 0, 0, 0), vb = va;
+                            if (i < na) va = __ldg(docids4 + ra.x + i);
+                            if (i < nb) vb = __ldg(docids4 + rb.x + i);
+                            const uint32_t d[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            if (4 * i + (e & 3) >= (e < 4 ? ra.y : rb.y)) continue;
-                            if (pmask && (((d[e] * kMult2) >> 16) & pmask) != pass) continue;
-                            table_insert<LOG>(tab, d[e], &s_ovf);
+                            for (int e = 0; e < 8; ++e) {
+                                if (4 * i + (e & 3) >= (e < 4 ? ra.y : rb.y)) continue;
+                                table_insert<LOG>(tab, d[e], &s_ovf);
+                            }
                         }
+                    }
+                } else {
+                    const uint32_t shift = 32 - rot;
+                    for (uint32_t r = warp; r < nr; r += kWarps) {
+                        const uint4 ra = rows_s[r];
+                        const uint32_t na = (ra.y + 3) >> 2;
+                        uint32_t g0 = 0; // first granule that can hold a posting of this pass
+                        if (pass != 0) {
+                            if (keep_cursors) {
+                                g0 = s_cur[r];
+                            } else { // many rows: no room for cursors, search the granule (first key >= this pass's range)
+                                uint32_t lo = 0, hi = na;
+                                while (lo < hi) {
+                                    const uint32_t mid = (lo + hi) >> 1;
+                                    const uint32_t last = min(4 * mid + 3, ra.y - 1); // last real posting of the granule
+                                    if (((__ldg(a.snap.docids + (size_t)ra.x * 4 + last) * kMult) >> shift) < pass) lo = mid + 1; else hi = mid;
+                                }
+                                g0 = lo;
+                            }
+                        }
+                        uint32_t next = na;
+                        for (uint32_t i0 = g0; i0 < na; i0 += 32) {
+                            const uint32_t i = i0 + lane;
+                            uint4 va = make_uint4(0, 0, 0, 0);
+                            if (i < na) va = __ldg(docids4 + ra.x + i);
+                            const uint32_t d[4] = {va.x, va.y, va.z, va.w};
+                            bool past = false; // a real posting of my granule belongs to a later pass
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                if (i >= na || 4 * i + e >= ra.y) continue;
+                                const uint32_t part = (d[e] * kMult) >> shift;
+                                if (part == pass) table_insert<LOG>(tab, d[e], &s_ovf, rot);
+                                past = past || part > pass;
+                            }
+                            const uint32_t pm = __ballot_sync(0xFFFFFFFFu, past);
+                            if (pm) { // the next pass starts at the first granule that reaches beyond this one
+                                next = i0 + (__ffs(pm) - 1);
+                                break;
+                            }
+                        }
+                        if (keep_cursors && lane == 0) s_cur[r] = next;
                     }
                 }
             }
@@ -1066,7 +1118,7 @@ __global__ void __launch_bounds__(THREADS, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const uint32_t cnt = ws[e] & P::kCntMask;
-                    if (ws[e] != 0u && cnt >= thr && rank_key(cnt, table_docid<LOG>(ws[e], i * 4 + e)) < kth) ++mine;
+                    if (ws[e] != 0u && cnt >= thr && rank_key(cnt, table_docid<LOG>(ws[e], i * 4 + e, rot)) < kth) ++mine;
                 }
             }
             if (mine) atomicAdd(&s_qual, mine);
@@ -1085,7 +1137,7 @@ __global__ void __launch_bounds__(THREADS, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))
                     for (int e = 0; e < 4; ++e) {
                         const uint32_t cnt = ws[e] & P::kCntMask;
                         if (ws[e] != 0u && cnt >= thr) {
-                            const unsigned long long key = rank_key(cnt, table_docid<LOG>(ws[e], i * 4 + e));
+                            const unsigned long long key = rank_key(cnt, table_docid<LOG>(ws[e], i * 4 + e, rot));
                             if (key < kth) kbuf[atomicAdd(&s_ncand, 1u)] = key;
                         }
                     }
@@ -1109,7 +1161,7 @@ __global__ void __launch_bounds__(THREADS, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))
                     tab[slot] = 0u;
                     const uint32_t cnt = wv & P::kCntMask;
                     if (wv != 0u && cnt >= thr) {
-                        const unsigned long long key = rank_key(cnt, table_docid<LOG>(wv, slot));
+                        const unsigned long long key = rank_key(cnt, table_docid<LOG>(wv, slot, rot));
                         if (key < s_kth) kbuf[atomicAdd(&s_ncand, 1u)] = key;
                     }
                     __syncthreads();
