@@ -564,6 +564,10 @@ template <int STAGES, uint32_t STAGE_U4, int SKLOG> constexpr size_t find_smem_b
 template <int GW, int RG, int PW, int STAGES, uint32_t STAGE_U4, int SKLOG>
 __global__ void __launch_bounds__((2 * GW + RG * kSkResolverWarps + PW) * 32, 1) search_find_kernel(BatchArgs a, uint32_t cls) {
     static_assert(RG >= 1 && RG <= 3 && STAGES >= 2 && STAGES <= 5 && SKLOG >= 13 && SKLOG <= 15, "barrier ids, sketch size");
+    // Consecutive tenants of a stage must be taken by the same counter group and the same resolver group: the groups wait
+    // on per-stage primitives (the parity of `full`, the "counted" barrier) that cannot tell one use of the stage from the
+    // next, so a group that laps the other one (a slow copy behind cold TLBs is enough) must not meet it there.
+    static_assert(STAGES % 2 == 0 && STAGES % RG == 0, "stage count: a multiple of the group counts");
     constexpr uint32_t kSketchBytes = 1u << SKLOG;            // one byte per counter
     constexpr uint32_t kSketchWords = kSketchBytes / 4;
     constexpr uint32_t kKeyShift = 32 - SKLOG;                // counter = h >> kKeyShift = word * 4 + byte
@@ -1468,9 +1472,9 @@ __global__ void __launch_bounds__(256) merge_packed_shards_kernel(const uint32_t
 // ------------------------------------------------------------------------------------------------
 // Warp split of the hot kernel: counter / resolver-group / producer warps (FPX_DEBUG_ABLATE bits 24..27 pick another
 // one for A/B runs).
-// Measured on C3 (tools/sweep.py, hot kernel per 100 K queries, profiles/r02/): 8/2/8 with four stages 1.120 ms,
-// five stages 1.145; 7/2/10 1.205; 6/3/8 1.200; 7/3/6 1.240; 9/2/6 1.161; 10/1/8 1.420; round-1 kernel 1.215.
-#define FPX_FIND_CONFIGS(X) X(0, 8, 2, 8, 4, 15) X(1, 8, 2, 8, 5, 15) X(2, 6, 3, 8, 5, 15) X(3, 9, 2, 6, 4, 15) X(4, 7, 2, 10, 4, 15)
+// Measured on C3 (tools/sweep.py, hot kernel per 100 K queries, profiles/r02/): 8+8 counter / 2x4 resolver / 8 producer
+// warps 1.120 ms; 9+9 / 2x4 / 6 1.161; 7+7 / 2x4 / 10 1.205; the round-1 kernel 1.215.
+#define FPX_FIND_CONFIGS(X) X(0, 8, 2, 8, 4, 15) X(1, 9, 2, 6, 4, 15) X(2, 7, 2, 10, 4, 15) X(3, 6, 2, 12, 4, 15)
 
 cudaError_t configure_kernels() {
     cudaError_t e;
@@ -1486,8 +1490,8 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     FPX_FIND_CONFIGS(X)
 #undef X
-    e = cudaFuncSetAttribute(search_find_kernel<8, 2, 8, 3, kStageLargeU4, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)find_smem_bytes<3, kStageLargeU4, 15>());
+    e = cudaFuncSetAttribute(search_find_kernel<8, 2, 8, 2, kStageLargeU4, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)find_smem_bytes<2, kStageLargeU4, 15>());
     return e;
 }
 
@@ -1522,7 +1526,7 @@ void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms) {
 #undef X
     default: break;
     }
-    search_find_kernel<8, 2, 8, 3, kStageLargeU4, 15><<<n_sms, 1024, find_smem_bytes<3, kStageLargeU4, 15>(), st>>>(a, kSketchLargeClass);
+    search_find_kernel<8, 2, 8, 2, kStageLargeU4, 15><<<n_sms, 1024, find_smem_bytes<2, kStageLargeU4, 15>(), st>>>(a, kSketchLargeClass);
 }
 
 void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms) {

@@ -61,7 +61,7 @@ struct WorkItem {
 //          in the staged rows (needs 2 <= min_score <= 128)
 //   1..3   exact shared-memory count table of 2^13 / 2^14 / 2^15 packed slots
 //   4      global-memory table: whatever the others cannot represent exactly
-//   5      sketch path with 48 KB stages (queries of up to 12288 padded postings)
+//   5      sketch path with 64 KB stages (queries of up to 16384 padded postings)
 constexpr int kNumClasses = 6;
 constexpr int kSketchClass = 0;
 constexpr int kWideClass = 4;
@@ -110,9 +110,8 @@ constexpr uint32_t kFastKbuf = 512;       // candidate buffer of the shared-memo
 constexpr uint32_t kWideKbuf = 2048;      // candidate buffer of the global-memory path
 constexpr uint32_t kMaxResults = 1024;    // FPX_MAX_RESULTS
 constexpr uint32_t kRowsChunk = 256;      // row descriptors staged per round
-constexpr uint32_t kStageU4 = 2000;       // sketch path: one query's padded rows must fit a 32000-byte stage (five of
-                                          // them and two 32 KB sketches fill the SM's shared memory) ...
-constexpr uint32_t kStageLargeU4 = 3072;  // ... or 48 KB in the large-stage class
+constexpr uint32_t kStageU4 = 2048;       // sketch path: one query's padded rows must fit a 32 KB stage (four of them) ...
+constexpr uint32_t kStageLargeU4 = 4096;  // ... or a 64 KB stage (two of them) in the large-stage class
 constexpr uint32_t kSketchMaxRows = 128;  // sketch path: row descriptors live in producer registers
 
 void launch_build_table(TermEntry *table, uint32_t log2cap, const uint32_t *terms, const uint32_t *lens,

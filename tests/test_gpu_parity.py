@@ -29,8 +29,11 @@ def _compare_batch(reader, ix, terms, offs, opts, k_stride, threads=8):
     bad = np.nonzero(cnt != oc)[0]
     assert len(bad) == 0, "count mismatch at queries %s: gpu %s oracle %s" % (bad[:5], cnt[bad[:5]], oc[bad[:5]])
     mask = np.arange(k_stride)[None, :] < cnt[:, None]
-    assert np.array_equal(np.where(mask, ids, 0), np.where(mask, oi, 0)), "ids differ"
-    assert np.array_equal(np.where(mask, sc, 0), np.where(mask, os_, 0)), "scores differ"
+    for name, got, want in (("ids", ids, oi), ("scores", sc, os_)):
+        diff = np.nonzero((np.where(mask, got, 0) != np.where(mask, want, 0)).any(axis=1))[0]
+        assert len(diff) == 0, "%s differ at %d queries, first %d: gpu ids %s scores %s | oracle ids %s scores %s" % (
+            name, len(diff), diff[0], ids[diff[0], :cnt[diff[0]]][:8], sc[diff[0], :cnt[diff[0]]][:8],
+            oi[diff[0], :cnt[diff[0]]][:8], os_[diff[0], :cnt[diff[0]]][:8])
     return ids, sc, cnt
 
 
@@ -521,7 +524,7 @@ def test_hot_kernel_variants_agree_with_the_oracle(ctx, c2):
     queries = [rng.integers(0, 4000, size=int(rng.integers(0, 120))).tolist() for _ in range(500)]
     t2, o2 = flat_queries(queries)
     try:
-        for variant in (1 << 24, 2 << 24, 3 << 24, 4 << 24):
+        for variant in (1 << 24, 2 << 24, 3 << 24):
             ctx.debug_set(variant)
             for opt in ((40, 5, 10), (40, 2, 0), (100, 3, 50), (512, 7, 10), (3, 4, 100)):
                 opts = np.tile(np.array(opt, dtype=np.uint32), (nq, 1))
