@@ -28,6 +28,18 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(pkg._ffi.EXPORTS)
 
 
+def test_zig_binding_names_only_exported_symbols():
+    """zig/fpx.zig (the binding a maintainer would add; it cannot be compiled here) must not drift from the library:
+    every `pub extern fn` it declares is declared in include/*.h and exported by libfpx.so."""
+    src = open(os.path.join(ROOT, "zig", "fpx.zig")).read()
+    names = set(re.findall(r"pub extern fn (fpx_[a-z0-9_]+)\(", src))
+    assert len(names) >= 25
+    L = C.CDLL(pkg._ffi.LIB_PATH)
+    declared = _declared()
+    for name in sorted(names):
+        assert name in declared and hasattr(L, name), name
+
+
 def test_abi_version_and_default_min_score():
     L = pkg.lib()
     assert L.fpx_abi_version() == 1
