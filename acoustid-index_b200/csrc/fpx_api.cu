@@ -851,7 +851,10 @@ fpx_status search_batch_host(fpx_snapshot *s, uint64_t n_queries, const uint32_t
         // every chunk costs a dozen kernel launches and a fill / drain of the persistent kernels (~0.05 ms), and the
         // copy engine feeds queries faster than the kernels answer them: a small first chunk so that the kernels start
         // early, then quickly growing ones
-        const uint64_t small = std::max<uint64_t>(1024, chunk / 16);
+        // (FPX_DEBUG_ABLATE bits 16..18: other first-chunk sizes / growth factors for A/B runs)
+        static const uint32_t kSchedDiv[8] = {16, 32, 32, 16, 64, 32, 64, 16}, kSchedGrow[8] = {4, 3, 2, 3, 3, 4, 4, 2};
+        const uint32_t sched = (ctx->debug >> 16) & 7u;
+        const uint64_t small = std::max<uint64_t>(1024, chunk / kSchedDiv[sched]);
         uint64_t q = 0, step = small;
         bounds.push_back(0);
         while (q < n_queries) {
@@ -864,7 +867,7 @@ fpx_status search_batch_host(fpx_snapshot *s, uint64_t n_queries, const uint32_t
             max_nt = std::max(max_nt, term_offsets[q1] - term_offsets[q]);
             q = q1;
             bounds.push_back(q);
-            step = std::min(chunk, step * 4);
+            step = std::min(chunk, step * kSchedGrow[sched]);
         }
     }
     const uint64_t n_chunks = bounds.size() - 1;

@@ -91,13 +91,13 @@ __device__ uint32_t make_item(const BatchArgs &a, uint32_t q, uint32_t rows_off,
     // fit one stage.  With a low floor and many postings too many counters reach it by chance: the expected
     // number of such counters is 32768 * P(Poisson(postings / 32768) >= min_score); the limits keep it <= 4
     // (kHotCap is 32; beyond it the query is re-queued, so this is a matter of speed only).
-    bool sketch_ok = a.use_sketch && o.min_score >= 2 && o.min_score <= 128 && total4 <= kStageLargeU4 &&
+    bool sketch_ok = a.use_sketch && o.min_score >= 2 && o.min_score <= 128 && total4 <= kStageU4 &&
                      k_eff <= kFastKbuf && n_rows <= kSketchMaxRows;
     if (o.min_score == 2 && postings > 512) sketch_ok = false;
     if (o.min_score == 3 && postings > 2900) sketch_ok = false;
     if (o.min_score == 4 && postings > 7600) sketch_ok = false;
     if (!sketch_ok) return exact_class_for(postings, k_eff);
-    return total4 <= kStageU4 ? (uint32_t)kSketchClass : (uint32_t)kSketchLargeClass;
+    return kSketchClass;
 }
 
 // Bin a prepared query (called by one thread).
@@ -507,9 +507,9 @@ constexpr int kSkResolverWarps = 4; // per resolver group
 constexpr int kSkResolvers = kSkResolverWarps * 32;
 
 // ------------------------------------------------------------------------------------------------
-// sketch path, "count, then find" (the hot kernel; classes kSketchClass and kSketchLargeClass).
+// sketch path, "count, then find" (the hot kernel; class kSketchClass).
 // One persistent CTA per SM, warps in three roles, hand-overs by named barriers (arrive / sync pairs; the TMA
-// completion is the only mbarrier), up to five queries in flight per SM:
+// completion is the only mbarrier), up to four queries in flight per SM:
 //   producers  TMA bulk copies (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) of the query's posting rows
 //              into a ring of shared-memory stages; all producer warps fill one stage at a time.
 //   counters   two groups, each with its own sketch of 32768 8-bit counters (four per 32-bit word), take the staged
@@ -544,8 +544,8 @@ constexpr uint32_t kFbCounters = 1, kFbGroup = 3, kFbStage = 6, kFbCounted = 11;
 
 struct FindMeta { // one per stage: what travels with the staged query
     WorkItem item;
-    uint32_t row_off[kSketchMaxRows]; // first docid of row r inside the stage
-    uint32_t row_len[kSketchMaxRows]; // postings in row r (without padding)
+    uint16_t row_off4[kSketchMaxRows]; // first 16-byte granule of row r inside the stage (a stage is <= 64 KB)
+    uint16_t row_len[kSketchMaxRows];  // postings in row r (without padding; the row fits the stage)
     uint32_t hot[kHotCap];            // counters that reached min_score: word * 4 + byte
     uint32_t n_hot, sum;              // sum: all bytes of the sketch after counting
 };
@@ -657,8 +657,8 @@ __global__ void __launch_bounds__((2 * GW + RG * kSkResolverWarps + PW) * 32, 1)
             for (int j = 0; j < kDesc; ++j) { // stage directory for the resolvers (d.z: the row's place, from prepare_kernel)
                 const uint32_t r = (uint32_t)kP * (lane + 32 * j) + p;
                 if (r < kSketchMaxRows) {
-                    meta[s].row_off[r] = d[j].z * 4u;
-                    meta[s].row_len[r] = d[j].y;
+                    meta[s].row_off4[r] = (uint16_t)d[j].z;
+                    meta[s].row_len[r] = (uint16_t)d[j].y;
                 }
             }
             if (p == 0 && lane == 0) meta[s].item = w;
@@ -719,7 +719,7 @@ __global__ void __launch_bounds__((2 * GW + RG * kSkResolverWarps + PW) * 32, 1)
                 // one append to a list, not a probe chain into a table.
                 const bool has_row = rtid < w.n_rows;
                 const uint32_t *row = reinterpret_cast<const uint32_t *>(stage + (size_t)s * STAGE_U4) +
-                                      (has_row ? m.row_off[rtid] : 0u);
+                                      (has_row ? 4u * m.row_off4[rtid] : 0u);
                 const uint32_t len = has_row ? m.row_len[rtid] : 0u;
 #pragma unroll 1
                 for (uint32_t c = 0; c < n_hot; ++c) {
@@ -948,7 +948,11 @@ template <int LOG> struct Packed {
 // hashing with an odd step derived from rem, so (slot, probe, rem) identifies d exactly.
 // `rot`: multi-pass queries split the key space by the top `rot` bits of hv (one key range per pass, see
 // search_smem_kernel), so those bits are the same for every docid of a pass: the key is rotated left by `rot` first.
-template <int LOG> __device__ __forceinline__ void table_insert(uint32_t *tab, uint32_t d, uint32_t *ovf, uint32_t rot = 0) {
+// PEEK: read the slot first and only CAS when it is empty.  A slot's tag never changes once set, so a stale read is
+// harmless; for queries whose docids repeat a lot (hot, capped rows share their low docids) most inserts find their
+// docid already there and become one load + one add instead of a CAS (half the atomic rate) + an add.
+template <int LOG, bool PEEK = false>
+__device__ __forceinline__ void table_insert(uint32_t *tab, uint32_t d, uint32_t *ovf, uint32_t rot = 0) {
     using P = Packed<LOG>;
     const uint32_t hv = __funnelshift_l(d * kMult, d * kMult, rot);
     const uint32_t rem = hv & P::kRemMask;
@@ -958,7 +962,8 @@ template <int LOG> __device__ __forceinline__ void table_insert(uint32_t *tab, u
 #pragma unroll 1
     for (uint32_t i = 0; i < 32; ++i) {
         const uint32_t tag = tagbase | (i << P::kCntBits);
-        const uint32_t old = atomicCAS(tab + s, 0u, tag | 1u);
+        uint32_t old = PEEK ? *const_cast<volatile uint32_t *>(tab + s) : 0u;
+        if (old == 0u) old = atomicCAS(tab + s, 0u, tag | 1u);
         if (old == 0u) return;
         if ((old & ~P::kCntMask) == tag) {
             const uint32_t prev = atomicAdd(tab + s, 1u);
@@ -999,8 +1004,15 @@ __global__ void __launch_bounds__(THREADS, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))
     constexpr uint32_t kRows = kSmemRowsChunk;
     unsigned long long *kbuf = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)P::kSlots * 4);
     uint4 *rows_s = reinterpret_cast<uint4 *>(smem_raw + (size_t)P::kSlots * 4 + kKbufCap * 8);
-    __shared__ uint32_t s_idx, s_ncand, s_ovf, s_count, s_qual;
+    __shared__ uint32_t s_idx, s_ncand, s_ovf, s_count, s_qual, s_bar, s_next;
     __shared__ uint32_t s_cur[kSmemRowsChunk]; // multi-pass: per row, the first granule of the next pass
+    // Histogram of the scores of a pass's qualifying docs, 256 bins (the last one: 255 or more).  It lives in the row
+    // descriptors' place, which is free between the insert phase and the next one; bin b sits at b + b / 32, so lane l of
+    // warp 0 walks its bins 8l .. 8l + 7 without bank conflicts.
+    constexpr uint32_t kHist = 256u, kHistPer = kHist / 32u;
+    static_assert((kHist + kHist / 32u) * 4u <= kSmemRowsChunk * 16u, "the histogram fits the row descriptors' place");
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(rows_s);
+    auto hbin = [](uint32_t b) { return b + (b >> 5); };
     __shared__ unsigned long long s_kth; // running threshold: only keys below it can still make the top k_eff
 
     constexpr int cls = LOG - 12;
@@ -1033,7 +1045,7 @@ __global__ void __launch_bounds__(THREADS, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))
         // contiguous piece of every row and each pass reads only its piece: the warp that owns a row keeps a cursor.
         uint32_t passes = 1, rot = 0;
         if (LOG == 15)
-            while ((unsigned long long)passes * 12288ull < w.postings && w.postings > 16384u) {
+            while ((unsigned long long)passes * 20480ull < w.postings && w.postings > 16384u) { // load <= 0.63 if all differ
                 passes <<= 1;
                 ++rot;
             }
@@ -1044,6 +1056,7 @@ __global__ void __launch_bounds__(THREADS, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))
                 const uint32_t nr = min(kRows, w.n_rows - r0);
                 __syncthreads();
                 for (uint32_t i = tid; i < nr; i += kThreads) rows_s[i] = rows[r0 + i];
+                if (tid == 0) s_next = 0u;
                 __syncthreads();
                 if (passes == 1) {
                     // a warp per posting row, 128-bit loads, two rows in flight; the tail of a row's last
@@ -1066,8 +1079,14 @@ __global__ void __launch_bounds__(THREADS, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))
                         }
                     }
                 } else {
+                    // Rows are handed out one at a time (a pass's pieces differ in length, and 100 rows over 32 warps
+                    // leave a quarter of the warps idle in the last round of a fixed split).
                     const uint32_t shift = 32 - rot;
-                    for (uint32_t r = warp; r < nr; r += kWarps) {
+                    for (;;) {
+                        uint32_t r = 0;
+                        if (lane == 0) r = atomicAdd(&s_next, 1u);
+                        r = __shfl_sync(0xFFFFFFFFu, r, 0);
+                        if (r >= nr) break;
                         const uint4 ra = rows_s[r];
                         const uint32_t na = (ra.y + 3) >> 2;
                         uint32_t g0 = 0; // first granule that can hold a posting of this pass
@@ -1095,7 +1114,7 @@ __global__ void __launch_bounds__(THREADS, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))
                             for (int e = 0; e < 4; ++e) {
                                 if (i >= na || 4 * i + e >= ra.y) continue;
                                 const uint32_t part = (d[e] * kMult) >> shift;
-                                if (part == pass) table_insert<LOG>(tab, d[e], &s_ovf, rot);
+                                if (part == pass) table_insert<LOG, true>(tab, d[e], &s_ovf, rot);
                                 past = past || part > pass;
                             }
                             const uint32_t pm = __ballot_sync(0xFFFFFFFFu, past);
@@ -1110,11 +1129,14 @@ __global__ void __launch_bounds__(THREADS, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))
             }
             __syncthreads();
             // scan + clear; candidates are docs with score >= max(min_score,1)  (common.zig:140-145) whose key
-            // can still make the top k_eff.  First count them ...
-            const unsigned long long kth = s_kth;
+            // can still make the top k_eff.  First a histogram of their scores ...
             // (skipped when the candidates of this pass fit for sure: at most postings / thr docs can reach thr)
+            unsigned long long kth = s_kth;
             const bool sure = passes == 1 && w.postings / thr <= kKbufCap;
-            uint32_t mine = 0;
+            if (!sure) {
+                for (uint32_t i = tid; i < kHist + kHist / 32u; i += kThreads) s_hist[i] = 0u;
+                __syncthreads();
+            }
             for (uint32_t i = tid; i < P::kSlots / 4 && !sure; i += kThreads) {
                 const uint4 wd = tab4[i];
                 if ((wd.x | wd.y | wd.z | wd.w) == 0u) continue;
@@ -1122,14 +1144,58 @@ __global__ void __launch_bounds__(THREADS, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const uint32_t cnt = ws[e] & P::kCntMask;
-                    if (ws[e] != 0u && cnt >= thr && rank_key(cnt, table_docid<LOG>(ws[e], i * 4 + e, rot)) < kth) ++mine;
+                    if (ws[e] != 0u && cnt >= thr && rank_key(cnt, table_docid<LOG>(ws[e], i * 4 + e, rot)) < kth)
+                        atomicAdd(&s_hist[hbin(min(cnt, kHist - 1u))], 1u);
                 }
             }
-            if (mine) atomicAdd(&s_qual, mine);
             __syncthreads();
-            const uint32_t qual = s_qual, have = s_ncand;
+            // ... from which one warp derives the bar of this pass: only the k_eff best of a pass can reach the final top
+            // k_eff, so with more qualifying docs than that the pass keeps the scores >= bar, bar = the largest score
+            // that still leaves k_eff of them (hot, capped rows share their low docids: a Zipf query has thousands of
+            // docs above the floor, and ranking them all was most of such a query's time)
+            if (warp == 0 && !sure) {
+                uint32_t loc = 0;
+                for (uint32_t j = 0; j < kHistPer; ++j) loc += s_hist[hbin(lane * kHistPer + j)];
+                uint32_t suf = loc; // docs with a score in my bins or above
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_down_sync(0xFFFFFFFFu, suf, o);
+                    if (lane + o < 32) suf += y;
+                }
+                uint32_t bar = thr, qual = __shfl_sync(0xFFFFFFFFu, suf, 0);
+                if (qual > k_eff) {
+                    const uint32_t at = 31u - __clz(__ballot_sync(0xFFFFFFFFu, suf >= k_eff)); // lane 0 always votes
+                    uint32_t acc = suf - loc, j = kHistPer;
+                    if (lane == at)
+                        while (j-- > 0u) {
+                            acc += s_hist[hbin(lane * kHistPer + j)];
+                            if (acc >= k_eff) break;
+                        }
+                    bar = max(thr, __shfl_sync(0xFFFFFFFFu, lane * kHistPer + j, at));
+                    qual = __shfl_sync(0xFFFFFFFFu, acc, at);
+                }
+                if (lane == 0) {
+                    s_qual = qual;
+                    s_bar = bar;
+                }
+            }
             __syncthreads();
-            if (tid == 0) s_qual = 0;
+            const uint32_t qual = sure ? 0u : s_qual, bar = sure ? thr : s_bar;
+            uint32_t have = s_ncand;
+            auto shrink = [&](uint32_t n) { // keep the k_eff best of kbuf[0..n) and raise the running threshold
+                group_sort_keys(g, kbuf, n, kKbufCap);
+                __syncthreads();
+                if (tid == 0) {
+                    s_ncand = min(n, k_eff);
+                    if (n >= k_eff && k_eff > 0) s_kth = kbuf[k_eff - 1];
+                }
+                __syncthreads();
+            };
+            if (have + qual > kKbufCap && have > k_eff) { // earlier passes' candidates are in the way
+                shrink(have);
+                have = s_ncand;
+                kth = s_kth;
+            }
             if (have + qual <= kKbufCap) {
                 // ... the usual case: they all fit
                 for (uint32_t i = tid; i < P::kSlots / 4; i += kThreads) {
@@ -1140,31 +1206,22 @@ __global__ void __launch_bounds__(THREADS, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const uint32_t cnt = ws[e] & P::kCntMask;
-                        if (ws[e] != 0u && cnt >= thr) {
+                        if (ws[e] != 0u && cnt >= bar) {
                             const unsigned long long key = rank_key(cnt, table_docid<LOG>(ws[e], i * 4 + e, rot));
                             if (key < kth) kbuf[atomicAdd(&s_ncand, 1u)] = key;
                         }
                     }
                 }
             } else {
-                // ... many candidates (hot, capped rows share their low docids): one slot per thread and round;
-                // whenever another round might not fit, keep the k_eff best and raise the bar
-                auto shrink = [&](uint32_t n) {
-                    group_sort_keys(g, kbuf, n, kKbufCap);
-                    __syncthreads();
-                    if (tid == 0) {
-                        s_ncand = min(n, k_eff);
-                        if (n >= k_eff && k_eff > 0) s_kth = kbuf[k_eff - 1];
-                    }
-                    __syncthreads();
-                };
+                // ... more docs tie at the bar than the buffer holds: one slot per thread and round; whenever another
+                // round might not fit, keep the k_eff best and raise the running threshold
                 if (have + kThreads > kKbufCap) shrink(have);
                 for (uint32_t base = 0; base < P::kSlots; base += kThreads) {
                     const uint32_t slot = base + tid;
                     const uint32_t wv = tab[slot];
                     tab[slot] = 0u;
                     const uint32_t cnt = wv & P::kCntMask;
-                    if (wv != 0u && cnt >= thr) {
+                    if (wv != 0u && cnt >= bar) {
                         const unsigned long long key = rank_key(cnt, table_docid<LOG>(wv, slot, rot));
                         if (key < s_kth) kbuf[atomicAdd(&s_ncand, 1u)] = key;
                     }
@@ -1474,7 +1531,8 @@ __global__ void __launch_bounds__(256) merge_packed_shards_kernel(const uint32_t
 // one for A/B runs).
 // Measured on C3 (tools/sweep.py, hot kernel per 100 K queries, profiles/r02/): 8+8 counter / 2x4 resolver / 8 producer
 // warps 1.120 ms; 9+9 / 2x4 / 6 1.161; 7+7 / 2x4 / 10 1.205; the round-1 kernel 1.215.
-#define FPX_FIND_CONFIGS(X) X(0, 8, 2, 8, 4, 15) X(1, 9, 2, 6, 4, 15) X(2, 7, 2, 10, 4, 15) X(3, 6, 2, 12, 4, 15)
+// (config 2: experiment only, 32 KB stages for workloads whose queries fit them)
+#define FPX_FIND_CONFIGS(X) X(0, 8, 2, 8, 4, 15, kStageU4) X(1, 9, 2, 6, 4, 15, kStageU4) X(2, 8, 2, 8, 4, 15, 2048u) X(3, 7, 2, 10, 4, 15, kStageU4)
 
 cudaError_t configure_kernels() {
     cudaError_t e;
@@ -1484,14 +1542,12 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(search_smem_kernel<15, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for<15, 1024>());
     if (e != cudaSuccess) return e;
-#define X(I, GW, RG, PW, ST, SK)                                                                                      \
-    e = cudaFuncSetAttribute(search_find_kernel<GW, RG, PW, ST, kStageU4, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                             (int)find_smem_bytes<ST, kStageU4, SK>());                                               \
+#define X(I, GW, RG, PW, ST, SK, SU4)                                                                                 \
+    e = cudaFuncSetAttribute(search_find_kernel<GW, RG, PW, ST, SU4, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)find_smem_bytes<ST, SU4, SK>());                                                    \
     if (e != cudaSuccess) return e;
     FPX_FIND_CONFIGS(X)
 #undef X
-    e = cudaFuncSetAttribute(search_find_kernel<8, 2, 8, 2, kStageLargeU4, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)find_smem_bytes<2, kStageLargeU4, 15>());
     return e;
 }
 
@@ -1517,16 +1573,15 @@ void launch_prepare_long(const BatchArgs &a, cudaStream_t st, int n_sms) {
 
 void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms) {
     switch ((a.debug >> 24) & 15u) {
-#define X(I, GW, RG, PW, ST, SK)                                                                                      \
+#define X(I, GW, RG, PW, ST, SK, SU4)                                                                                 \
     case I:                                                                                                           \
-        search_find_kernel<GW, RG, PW, ST, kStageU4, SK>                                                              \
-            <<<n_sms, (2 * GW + 4 * RG + PW) * 32, find_smem_bytes<ST, kStageU4, SK>(), st>>>(a, kSketchClass);       \
+        search_find_kernel<GW, RG, PW, ST, SU4, SK>                                                                   \
+            <<<n_sms, (2 * GW + 4 * RG + PW) * 32, find_smem_bytes<ST, SU4, SK>(), st>>>(a, kSketchClass);            \
         break;
         FPX_FIND_CONFIGS(X)
 #undef X
     default: break;
     }
-    search_find_kernel<8, 2, 8, 2, kStageLargeU4, 15><<<n_sms, 1024, find_smem_bytes<2, kStageLargeU4, 15>(), st>>>(a, kSketchLargeClass);
 }
 
 void launch_search_class(const BatchArgs &a, int cls, cudaStream_t st, int n_sms) {

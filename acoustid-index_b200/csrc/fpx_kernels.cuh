@@ -57,15 +57,13 @@ struct WorkItem {
 };
 
 // Work classes.
-//   0      sketch path: TMA-staged rows (<= 32 KB per query), u8 count sketch, hot counters resolved exactly
-//          in the staged rows (needs 2 <= min_score <= 128)
+//   0      sketch path: TMA-staged rows (<= 40832 bytes = 10208 padded postings per query), u8 count sketch, hot
+//          counters resolved exactly in the staged rows (needs 2 <= min_score <= 128)
 //   1..3   exact shared-memory count table of 2^13 / 2^14 / 2^15 packed slots
 //   4      global-memory table: whatever the others cannot represent exactly
-//   5      sketch path with 64 KB stages (queries of up to 16384 padded postings)
-constexpr int kNumClasses = 6;
+constexpr int kNumClasses = 5;
 constexpr int kSketchClass = 0;
 constexpr int kWideClass = 4;
-constexpr int kSketchLargeClass = 5;
 
 struct BatchCounters {
     uint32_t qcount[kNumClasses];
@@ -110,8 +108,8 @@ constexpr uint32_t kFastKbuf = 512;       // candidate buffer of the shared-memo
 constexpr uint32_t kWideKbuf = 2048;      // candidate buffer of the global-memory path
 constexpr uint32_t kMaxResults = 1024;    // FPX_MAX_RESULTS
 constexpr uint32_t kRowsChunk = 256;      // row descriptors staged per round
-constexpr uint32_t kStageU4 = 2048;       // sketch path: one query's padded rows must fit a 32 KB stage (four of them) ...
-constexpr uint32_t kStageLargeU4 = 4096;  // ... or a 64 KB stage (two of them) in the large-stage class
+constexpr uint32_t kStageU4 = 2552;       // sketch path: one query's padded rows must fit a 40832-byte stage (four of them and
+                                          // the two 32 KB sketches are all the shared memory of an SM)
 constexpr uint32_t kSketchMaxRows = 128;  // sketch path: row descriptors live in producer registers
 
 void launch_build_table(TermEntry *table, uint32_t log2cap, const uint32_t *terms, const uint32_t *lens,

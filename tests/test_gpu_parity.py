@@ -540,8 +540,8 @@ def test_hot_kernel_variants_agree_with_the_oracle(ctx, c2):
 
 
 def test_c2_queries_stay_on_the_sketch_path(ctx, c2):
-    """100-term C2 queries (~9.6 K padded postings, more than one 32 KB stage) are answered by the large-stage
-    instance of the hot kernel, not by the exact count-table kernels."""
+    """100-term C2 queries (~9.7 K padded postings, 39 KB) fit a 40832-byte stage of the hot kernel and are answered
+    there, not by the exact count-table kernels."""
     syn, seg, snap, ix = c2
     terms, _ = syn.queries(4000, 100, seed=99)
     nq, T = terms.shape

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Small large-stage-class workload for compute-sanitizer runs: 120-term queries on 100 K docs x 120 hashes (rows of ~92
+"""Small workload of queries that almost fill a stage of the hot kernel, for compute-sanitizer runs: 120-term queries on 100 K docs x 120 hashes (rows of ~92
 postings, ~2800 granules per query), checked against the oracle.   python tools/race_large.py [n_queries] [repeats]"""
 import os, sys
 import numpy as np

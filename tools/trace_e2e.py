@@ -25,18 +25,23 @@ def step():
     reader.search_batch_packed_ptr(nq, h[0].data_ptr(), h[1].data_ptr(), h[2].data_ptr(), K, h[3].data_ptr(), h[4].data_ptr(), nq * K)
 
 
-for ch in [int(x) for x in (sys.argv[1:] or ["65536"])]:
+TRACE = os.environ.get("TRACE", "1") == "1"
+for arg in (sys.argv[1:] or ["131072"]):  # chunk[:schedule variant] (FPX debug bits 16..18, see search_batch_host)
+    ch, _, sv = arg.partition(":")
+    ch, sv = int(ch), int(sv or 0) << 16
     ctx.set_chunk_queries(ch)
+    ctx.debug_set(sv)
     for _ in range(3):
         step()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(10):
+    for _ in range(20):
         step()
     torch.cuda.synchronize()
-    ms = (time.perf_counter() - t0) / 10 * 1e3
-    print("chunk %6d: %.3f ms per call, %.1fM q/s" % (ch, ms, nq / ms / 1e3), flush=True)
-    ctx.debug_set(2048)
-    step()
+    ms = (time.perf_counter() - t0) / 20 * 1e3
+    print("chunk %6d sched %d: %.3f ms per call, %.1fM q/s" % (ch, sv >> 16, ms, nq / ms / 1e3), flush=True)
+    if TRACE:
+        ctx.debug_set(2048 | sv)
+        step()
     ctx.debug_set(0)
-    print("---- chunk", ch, flush=True)
+    print("---- chunk", arg, flush=True)
