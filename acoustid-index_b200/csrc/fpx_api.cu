@@ -1293,10 +1293,10 @@ fpx_status fpx_profile_read(fpx_ctx *ctx, fpx_profile *out) {
         ctx->prof.overflow_requeues = ds.overflow_requeues;
         if (ctx->debug & 512u) { // phase timers of CTA 0 (clock cycles per own query, from the start of the role's iteration)
             auto per = [&](int slot, int n_slot) { return (double)ds.dbg[slot] / (double)(ds.dbg[n_slot] ? ds.dbg[n_slot] : 1); };
-            std::fprintf(stderr, "[fpx dbg] producers: wait_stage %.0f iter %.0f (%llu) | counter group 0: wait_full %.0f +count %.0f "
-                                 "+readback %.0f (%llu) | resolver group 0: wait_counted %.0f +find %.0f end %.0f (%llu)\n",
-                         per(0, 2), per(1, 2), ds.dbg[2], per(7, 10), per(8, 10), per(9, 10), ds.dbg[10], per(3, 6), per(11, 6),
-                         per(5, 6), ds.dbg[6]);
+            std::fprintf(stderr, "[fpx dbg] producers: wait_stage %.0f iter %.0f (%llu) | counter group 0: wait_full %.0f (parked warp %.0f) "
+                                 "+count %.0f +group %.0f +readback %.0f (%llu) | resolver group 0: wait_counted %.0f +find %.0f end %.0f (%llu)\n",
+                         per(0, 2), per(1, 2), ds.dbg[2], per(7, 10), per(12, 10), per(8, 10), per(13, 10), per(9, 10), ds.dbg[10],
+                         per(3, 6), per(11, 6), per(5, 6), ds.dbg[6]);
         }
     }
     *out = ctx->prof;

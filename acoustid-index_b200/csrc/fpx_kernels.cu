@@ -561,7 +561,12 @@ template <int STAGES, uint32_t STAGE_U4, int SKLOG> constexpr size_t find_smem_b
     return 2 * ((size_t)1 << SKLOG) + (size_t)STAGES * STAGE_U4 * 16;
 }
 
-template <int GW, int RG, int PW, int STAGES, uint32_t STAGE_U4, int SKLOG>
+// TIMED: the instance whose phase timers (FPX_DEBUG_ABLATE bit 9) also see the barrier waits (settle() below).  This kernel
+// is sensitive to the instruction schedule far beyond what the instruction counts suggest: the never-taken branch of a
+// settle() per hand-over costs the default instance 6 %, and compiling the clock reads of the plain timers OUT of it costs
+// 11 % (measured, profiles/r02/INDEX.md): they are compiler barriers that keep the loads of the next queries' work items,
+// descriptors and sketch bias ahead of the hand-overs.  So the default instance keeps the clock reads and has no settle().
+template <int GW, int RG, int PW, int STAGES, uint32_t STAGE_U4, int SKLOG, bool TIMED = false>
 __global__ void __launch_bounds__((2 * GW + RG * kSkResolverWarps + PW) * 32, 1) search_find_kernel(BatchArgs a, uint32_t cls) {
     static_assert(RG >= 1 && RG <= 3 && STAGES >= 2 && STAGES <= 5 && SKLOG >= 13 && SKLOG <= 15, "barrier ids, sketch size");
     // Consecutive tenants of a stage must be taken by the same counter group and the same resolver group: the groups wait
@@ -590,6 +595,16 @@ __global__ void __launch_bounds__((2 * GW + RG * kSkResolverWarps + PW) * 32, 1)
     const bool timed = (a.debug & 512u) && blockIdx.x == 0 && a.stats != nullptr;
     auto tick = [&](int slot, long long t0) {
         if (timed) atomicAdd(&a.stats->dbg[slot], (unsigned long long)(clock64() - t0));
+    };
+    // bar.sync does not block at issue but at the next instruction that consumes memory: a timer read right after it
+    // would miss the wait, so the timed instance touches shared memory first
+    auto settle = [&]() {
+        if constexpr (TIMED) {
+            if (timed) {
+                uint32_t x;
+                asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(x) : "r"(smem_u32(&full[0])) : "memory");
+            }
+        }
     };
     if (count == 0u) return;
 
@@ -647,6 +662,7 @@ __global__ void __launch_bounds__((2 * GW + RG * kSkResolverWarps + PW) * 32, 1)
             const long long tp0 = clock64();
             if (it >= (uint32_t)STAGES) // the resolvers released the previous tenant of this stage: us + their warp 0
                 named_sync(kFbStage + s, 32 * kP + 32);
+            settle();
             if (p == 0 && lane == 0) tick(0, tp0);
             uint32_t mine = 0;
 #pragma unroll
@@ -704,6 +720,7 @@ __global__ void __launch_bounds__((2 * GW + RG * kSkResolverWarps + PW) * 32, 1)
             FindMeta &m = meta[s];
             const long long tr0 = clock64();
             named_sync(kFbCounted + s, kGroup + kSkResolvers); // a counter group has counted query it and read its sketch back
+            settle();
             if (gidx == 0 && rtid == 0) tick(3, tr0);
             const WorkItem w = m.item;
             const uint32_t n_hot = (a.debug & 2u) ? 0u : m.n_hot;
@@ -778,6 +795,7 @@ __global__ void __launch_bounds__((2 * GW + RG * kSkResolverWarps + PW) * 32, 1)
                 }
             }
             R.sync(); // everyone is done with the stage; the findings are complete
+            settle();
             if (gidx == 0 && rtid == 0) tick(11, tr0);
             if (rwarp == 0) {
                 if (lane == 0) m.n_hot = m.sum = 0u;      // for the stage's next tenant
@@ -848,8 +866,8 @@ __global__ void __launch_bounds__((2 * GW + RG * kSkResolverWarps + PW) * 32, 1)
         if (idx >= count) break;
         const uint32_t s = it % STAGES;
         const unsigned long long idx2 = idx + 2ull * gridDim.x;
-        const uint32_t ms2 = idx2 < count ? items[idx2].min_score : 2u;
-        const long long tc0 = clock64();
+        const uint32_t ms2 = idx2 < count ? items[idx2].min_score : 2u; // from DRAM; needed at the read-back, issued here
+        const long long tc0 = clock64(); // (also a compiler barrier: the load above stays above the wait below)
         if (gwarp == 0) { // one warp polls the TMA completion, the others park on the named barrier
             if (lane == 0) {
                 mbar_wait(&full[s], (it / STAGES) & 1, 0);
@@ -858,6 +876,9 @@ __global__ void __launch_bounds__((2 * GW + RG * kSkResolverWarps + PW) * 32, 1)
             __syncwarp();
         }
         named_sync(kFbCounters + g, kGroup);
+        settle();
+        if constexpr (TIMED)
+            if (g == 0 && gtid == 32) tick(12, tc0); // a warp that parks on the barrier while warp 0 polls
         FindMeta &m = meta[s];
         const uint32_t total4 = m.item.total4;
         const uint4 *sg = stage + (size_t)s * STAGE_U4;
@@ -884,6 +905,9 @@ __global__ void __launch_bounds__((2 * GW + RG * kSkResolverWarps + PW) * 32, 1)
         }
         if (g == 0 && gtid == 0) tick(8, tc0);
         named_sync(kFbCounters + g, kGroup); // every warp of the group is done counting query it
+        settle();
+        if constexpr (TIMED)
+            if (g == 0 && gtid == 0) tick(13, tc0);
         {
             const uint32_t b2 = (0x80u - ms2) * 0x01010101u;
             const uint4 clear4 = make_uint4(b2, b2, b2, b2);
@@ -1531,8 +1555,7 @@ __global__ void __launch_bounds__(256) merge_packed_shards_kernel(const uint32_t
 // one for A/B runs).
 // Measured on C3 (tools/sweep.py, hot kernel per 100 K queries, profiles/r02/): 8+8 counter / 2x4 resolver / 8 producer
 // warps 1.120 ms; 9+9 / 2x4 / 6 1.161; 7+7 / 2x4 / 10 1.205; the round-1 kernel 1.215.
-// (config 2: experiment only, 32 KB stages for workloads whose queries fit them)
-#define FPX_FIND_CONFIGS(X) X(0, 8, 2, 8, 4, 15, kStageU4) X(1, 9, 2, 6, 4, 15, kStageU4) X(2, 8, 2, 8, 4, 15, 2048u) X(3, 7, 2, 10, 4, 15, kStageU4)
+#define FPX_FIND_CONFIGS(X) X(0, 8, 2, 8, 4, 15, kStageU4) X(1, 9, 2, 6, 4, 15, kStageU4) X(2, 7, 2, 10, 4, 15, kStageU4) X(3, 6, 2, 12, 4, 15, kStageU4)
 
 cudaError_t configure_kernels() {
     cudaError_t e;
@@ -1548,6 +1571,8 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     FPX_FIND_CONFIGS(X)
 #undef X
+    e = cudaFuncSetAttribute(search_find_kernel<8, 2, 8, 4, kStageU4, 15, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)find_smem_bytes<4, kStageU4, 15>());
     return e;
 }
 
@@ -1572,6 +1597,10 @@ void launch_prepare_long(const BatchArgs &a, cudaStream_t st, int n_sms) {
 }
 
 void launch_search_sketch(const BatchArgs &a, cudaStream_t st, int n_sms) {
+    if (a.debug & 512u) { // the default configuration with phase timers that see the barrier waits
+        search_find_kernel<8, 2, 8, 4, kStageU4, 15, true><<<n_sms, 1024, find_smem_bytes<4, kStageU4, 15>(), st>>>(a, kSketchClass);
+        return;
+    }
     switch ((a.debug >> 24) & 15u) {
 #define X(I, GW, RG, PW, ST, SK, SU4)                                                                                 \
     case I:                                                                                                           \
