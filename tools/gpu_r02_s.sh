@@ -1,0 +1,6 @@
+#!/bin/bash
+# round 2, session S: stages handed back through an mbarrier per stage (producer warps no longer in lockstep)
+mkdir -p gpurun_out
+V=0,0x2000000,0x3000000,0x4000000,0x5000000,0x1000000,0,0x2000000
+timeout 400 python tools/sweep.py --workload c3 --steps 8 --variants $V --check 0x2000000,0x3000000,0x4000000,0x5000000,0x1000000 > gpurun_out/sweep_c3.log 2>&1; grep -E "variant|rror" gpurun_out/sweep_c3.log | tail -9
+timeout 200 python tools/sweep.py --workload c2 --steps 8 --variants $V --check 0x2000000,0x3000000,0x4000000,0x5000000,0x1000000 > gpurun_out/sweep_c2.log 2>&1; grep -E "variant|rror" gpurun_out/sweep_c2.log | tail -9
