@@ -1297,6 +1297,8 @@ fpx_status fpx_profile_read(fpx_ctx *ctx, fpx_profile *out) {
                                  "+count %.0f +group %.0f +readback %.0f (%llu) | resolver group 0: wait_counted %.0f +find %.0f end %.0f (%llu)\n",
                          per(0, 2), per(1, 2), ds.dbg[2], per(7, 10), per(12, 10), per(8, 10), per(13, 10), per(9, 10), ds.dbg[10],
                          per(3, 6), per(11, 6), per(5, 6), ds.dbg[6]);
+            std::fprintf(stderr, "[fpx dbg] producer warp 0: issuing its copies %.0f | last copy issued -> stage complete as seen by counter group 0 "
+                                 "(includes the group's own lateness) %.0f\n", per(14, 2), per(15, 10));
         }
     }
     *out = ctx->prof;

@@ -587,6 +587,7 @@ __global__ void __launch_bounds__((2 * GW + RG * kSkResolverWarps + PW) * 32, 1)
     __shared__ uint64_t full[STAGES]; // TMA completion; every other hand-over is a named barrier
     __shared__ FindMeta meta[STAGES];
     __shared__ FindState fs[RG];
+    __shared__ long long t_issued[TIMED ? STAGES : 1]; // TIMED: when producer warp 0 had issued its last copy of the stage's tenant
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t count = a.counters->qcount[cls];
@@ -682,10 +683,18 @@ __global__ void __launch_bounds__((2 * GW + RG * kSkResolverWarps + PW) * 32, 1)
             __syncwarp();
             if (lane == 0) mbar_expect_tx(&full[s], mine * 16u); // expect_tx precedes my copies (release)
             __syncwarp();
+            long long ti0 = 0;
+            if constexpr (TIMED) ti0 = clock64();
             if (!(a.debug & 8u)) {
 #pragma unroll
                 for (int j = 0; j < kDesc; ++j)
                     if (d[j].y) bulk_g2s(dst + d[j].z, docids4 + d[j].x, ((d[j].y + 3) >> 2) * 16u, &full[s]);
+            }
+            if constexpr (TIMED) {
+                if (p == 0 && lane == 0) {
+                    tick(14, ti0); // issuing my share of the query's copies
+                    t_issued[s] = clock64();
+                }
             }
             have = have1;
             have1 = have2;
@@ -872,6 +881,8 @@ __global__ void __launch_bounds__((2 * GW + RG * kSkResolverWarps + PW) * 32, 1)
             if (lane == 0) {
                 mbar_wait(&full[s], (it / STAGES) & 1, 0);
                 if (g == 0) tick(7, tc0);
+                if constexpr (TIMED)
+                    if (g == 0) tick(15, t_issued[s]); // from producer warp 0's last copy to the stage being complete (0 if it was)
             }
             __syncwarp();
         }
