@@ -1217,6 +1217,7 @@ __global__ void __launch_bounds__(THREADS, (LOG == 13 ? 4 : (LOG == 14 ? 3 : 1))
             __syncthreads();
             const uint32_t qual = sure ? 0u : s_qual, bar = sure ? thr : s_bar;
             uint32_t have = s_ncand;
+            __syncthreads(); // everyone has read `have` before the first thread appends (or the branches below could differ)
             auto shrink = [&](uint32_t n) { // keep the k_eff best of kbuf[0..n) and raise the running threshold
                 group_sort_keys(g, kbuf, n, kKbufCap);
                 __syncthreads();

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Small workload of queries that almost fill a stage of the hot kernel, for compute-sanitizer runs: 120-term queries on 100 K docs x 120 hashes (rows of ~92
-postings, ~2800 granules per query), checked against the oracle.   python tools/race_large.py [n_queries] [repeats]"""
+"""Small workload of queries that almost fill a stage of the hot kernel, for compute-sanitizer runs: 105-term queries on 100 K docs x 120 hashes (rows of ~92
+postings, ~2450 of a stage's 2552 granules per query), checked against the oracle.   python tools/race_large.py [n_queries] [repeats]"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -18,9 +18,9 @@ ctx = pkg.Context(device=0, profile=True)
 snap = pkg.swap_snapshot(ctx, [seg])
 ix = OracleIndex()
 ix.adopt_file_segment(1, 0, seg.block_size, seg.blocks, seg.num_blocks, seg.block_index, seg.doc_ids, seg.doc_alive)
-terms, _ = syn.queries(nq, 120, seed=77)
-offs = np.arange(nq + 1, dtype=np.uint64) * 120
-opts = pkg.synth.http_opts(nq, 120)
+terms, _ = syn.queries(nq, 105, seed=77)
+offs = np.arange(nq + 1, dtype=np.uint64) * 105
+opts = pkg.synth.http_opts(nq, 105)
 oi, os_, oc, _ = ix.search_batch(terms.reshape(-1), offs, opts, 40, n_threads=8)
 mask = np.arange(40)[None, :] < oc[:, None]
 bad = 0
