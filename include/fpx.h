@@ -310,8 +310,13 @@ fpx_status fpx_set_chunk_queries(fpx_ctx *ctx, uint32_t chunk_queries);
 fpx_status fpx_set_profile(fpx_ctx *ctx, int enabled);
 fpx_status fpx_profile_reset(fpx_ctx *ctx);
 fpx_status fpx_profile_read(fpx_ctx *ctx, fpx_profile *out);
-/* Profiling only: kernel variant / ablation bits (same meaning as the FPX_DEBUG_ABLATE environment variable;
- * results are wrong while ablation bits are set). */
+/* Profiling only: kernel variant / ablation bits (same meaning as the FPX_DEBUG_ABLATE environment variable).
+ *   ablations of the hot kernel, WRONG RESULTS, timing only: bit 0 no counting, 1 no recount, 3 no row copies, 4 no sketch
+ *     clear
+ *   measurements, results unchanged: bit 9 the hot kernel's instance with phase timers (printed by fpx_profile_read),
+ *     bit 11 per-chunk timeline of every host-buffer call on stderr, bit 12 packed result path even for pinned output
+ *     arrays, bits 16..18 chunk schedule of the host-buffer call, bits 24..27 warp split of the hot kernel
+ *     (csrc/fpx_kernels.cu FPX_FIND_CONFIGS) */
 fpx_status fpx_debug_set(fpx_ctx *ctx, uint32_t bits);
 
 #ifdef __cplusplus
