@@ -1,3 +1,4 @@
 #!/bin/bash
+# how much of prepare_kernel's time is the directory's size?  c3's row lengths and queries on a quarter / half of its terms
 mkdir -p gpurun_out
-timeout 300 python tools/sweep.py --workload c3 --steps 8 --variants 0,0x100000,0x200000,0 --check 0x100000,0x200000 > gpurun_out/sweep_c3_prep.log 2>&1; grep -E "variant|rror" gpurun_out/sweep_c3_prep.log | tail -8
+for wl in c3q c3h; do timeout 300 python tools/sweep.py --workload $wl --steps 8 --variants 0,0 > gpurun_out/sweep_$wl.log 2>&1; grep -E "variant|snapshot:|rror" gpurun_out/sweep_$wl.log | tail -3; done
