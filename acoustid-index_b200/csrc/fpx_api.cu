@@ -814,9 +814,31 @@ struct PackedOut { // results as {count per query, (id, score) pairs back to bac
     uint64_t n_pairs;  // needed
 };
 
+fpx_status search_batch_host_impl(fpx_snapshot *s, uint64_t n_queries, const uint32_t *terms, const uint64_t *term_offsets,
+                                  const fpx_search_opts *opts, uint32_t k_stride, uint32_t *out_ids, uint32_t *out_scores,
+                                  uint32_t *out_counts, PackedOut *packed, uint32_t timeout_ms);
+
+// No exception crosses the C ABI: a failed host allocation inside the batch driver (chunk tables, helper threads) becomes
+// FPX_OUT_OF_MEMORY, after the device has drained whatever the call had already enqueued (it may write the caller's
+// arrays).  The call's workspace is not returned to the pool in that case.
 fpx_status search_batch_host(fpx_snapshot *s, uint64_t n_queries, const uint32_t *terms, const uint64_t *term_offsets,
                              const fpx_search_opts *opts, uint32_t k_stride, uint32_t *out_ids, uint32_t *out_scores,
                              uint32_t *out_counts, PackedOut *packed, uint32_t timeout_ms = 0) {
+    try {
+        return search_batch_host_impl(s, n_queries, terms, term_offsets, opts, k_stride, out_ids, out_scores, out_counts, packed,
+                                      timeout_ms);
+    } catch (const std::bad_alloc &) {
+        cudaDeviceSynchronize();
+        return set_error(FPX_OUT_OF_MEMORY, "host allocation in the batch driver");
+    } catch (const std::exception &ex) {
+        cudaDeviceSynchronize();
+        return set_error(FPX_OUT_OF_MEMORY, std::string("batch driver: ") + ex.what());
+    }
+}
+
+fpx_status search_batch_host_impl(fpx_snapshot *s, uint64_t n_queries, const uint32_t *terms, const uint64_t *term_offsets,
+                                  const fpx_search_opts *opts, uint32_t k_stride, uint32_t *out_ids, uint32_t *out_scores,
+                                  uint32_t *out_counts, PackedOut *packed, uint32_t timeout_ms) {
     if (!s) return set_error(FPX_INVALID_ARGUMENT, "null snapshot");
     if (n_queries == 0) return FPX_OK;
     if (!term_offsets || !opts || !out_counts || (!packed && k_stride && (!out_ids || !out_scores)))
