@@ -33,11 +33,11 @@ def test_zig_binding_names_only_exported_symbols():
     every `pub extern fn` it declares is declared in include/*.h and exported by libfpx.so."""
     src = open(os.path.join(ROOT, "zig", "fpx.zig")).read()
     names = set(re.findall(r"pub extern fn (fpx_[a-z0-9_]+)\(", src))
-    assert len(names) >= 25
     L = C.CDLL(pkg._ffi.LIB_PATH)
     declared = _declared()
     for name in sorted(names):
         assert name in declared and hasattr(L, name), name
+    assert names == declared, "zig/fpx.zig binds every entry point of include/*.h: %s" % sorted(declared ^ names)
 
 
 def test_abi_version_and_default_min_score():

@@ -47,6 +47,46 @@ pub const SearchOpts = extern struct { max_results: u32, min_score: u32, min_sco
 
 pub const BatcherConfig = extern struct { max_batch: u32 = 0, max_wait_us: u32 = 100 };
 pub const SegmentInfo = extern struct { commit_id: u64, merges: u64, version: u64, has_version: u32, reserved: u32 };
+pub const SegmentBuf = opaque {};
+pub const BatcherStats = extern struct { batches: u64, queries: u64, max_batch_seen: u64, timeouts: u64 };
+pub const SnapshotInfo = extern struct {
+    n_segments: u64,
+    n_terms: u64,
+    n_postings: u64,
+    n_postings_total: u64,
+    n_dropped_unreachable: u64,
+    n_dropped_superseded: u64,
+    n_dropped_out_of_range: u64,
+    device_bytes: u64,
+    max_row_len: u64,
+    pad_id: u32,
+    table_log2: u32,
+    doc_lo: u32,
+    doc_hi: u32,
+};
+pub const CsrView = extern struct { n_terms: u64, terms: ?[*]const u32, row_offsets: ?[*]const u64, docids: ?[*]const u32 };
+pub const WireSearchRequest = extern struct { query: ?[*]u32, n_terms: u64, timeout: u32, limit: u32, has_min_score: u32, min_score: u32, score_pct: u32 };
+pub const Profile = extern struct {
+    prepare_ms: f64,
+    prepare_launches: u64,
+    sketch_ms: f64,
+    sketch_launches: u64,
+    search_ms: f64,
+    search_launches: u64,
+    wide_ms: f64,
+    wide_launches: u64,
+    h2d_ms: f64,
+    d2h_ms: f64,
+    queries: u64,
+    unique_terms: u64,
+    postings: u64,
+    results: u64,
+    sketch_queries: u64,
+    wide_queries: u64,
+    overflow_requeues: u64,
+    h2d_bytes: u64,
+    d2h_bytes: u64,
+};
 
 pub extern fn fpx_abi_version() u32;
 pub extern fn fpx_last_error_message() [*:0]const u8;
@@ -70,13 +110,21 @@ pub extern fn fpx_search_batch(s: *Snapshot, n_queries: u64, terms: [*]const u32
 pub extern fn fpx_search_batch_timeout(s: *Snapshot, n_queries: u64, terms: [*]const u32, term_offsets: [*]const u64, opts: [*]const SearchOpts, k_stride: u32, out_ids: [*]u32, out_scores: [*]u32, out_counts: [*]u32, timeout_ms: u32) Status;
 /// results as the reference returns them: a list per query (counts + (id, score) pairs back to back)
 pub extern fn fpx_search_batch_packed(s: *Snapshot, n_queries: u64, terms: [*]const u32, term_offsets: [*]const u64, opts: [*]const SearchOpts, k_stride: u32, out_counts: [*]u32, out_pairs: [*]u32, capacity_pairs: u64, out_n_pairs: *u64) Status;
-// device-resident variants (fpx_search_batch_device, fpx_search_batch_device_async, fpx_pack_results_device,
-// fpx_merge_packed_shards_device) take CUDA device pointers and a cudaStream_t: for hosts that own GPU buffers
+// device-resident variants: every pointer is a CUDA device pointer, `cuda_stream` a cudaStream_t (null = the legacy default
+// stream); for hosts that own GPU buffers.  `_async` never waits for the device; what the kernels reject comes back
+// through the status word in device memory.
+pub extern fn fpx_search_batch_device_async(s: *Snapshot, n_queries: u64, term_base: u64, n_terms_total: u64, d_terms: ?*const anyopaque, d_term_offsets: ?*const anyopaque, d_opts: ?*const anyopaque, k_stride: u32, d_out_ids: ?*anyopaque, d_out_scores: ?*anyopaque, d_out_counts: ?*anyopaque, d_status: ?*anyopaque, cuda_stream: ?*anyopaque) Status;
+pub extern fn fpx_search_batch_device(s: *Snapshot, n_queries: u64, d_terms: ?*const anyopaque, d_term_offsets: ?*const anyopaque, d_opts: ?*const anyopaque, k_stride: u32, d_out_ids: ?*anyopaque, d_out_scores: ?*anyopaque, d_out_counts: ?*anyopaque, cuda_stream: ?*anyopaque) Status;
+// docid-range sharded corpus (one shard per GPU): pack a shard's lists, merge the gathered lists (device and host forms)
+pub extern fn fpx_pack_results_device(n_queries: u64, k_stride: u32, d_ids: ?*const anyopaque, d_scores: ?*const anyopaque, d_counts: ?*const anyopaque, d_packed: ?*anyopaque, capacity_pairs: u32, cuda_stream: ?*anyopaque) Status;
+pub extern fn fpx_merge_packed_shards_device(n_shards: u32, n_queries: u64, d_packed: ?*const anyopaque, shard_stride_words: u64, d_opts: ?*const anyopaque, k_stride: u32, d_out_ids: ?*anyopaque, d_out_scores: ?*anyopaque, d_out_counts: ?*anyopaque, cuda_stream: ?*anyopaque) Status;
+pub extern fn fpx_merge_shard_results(n_shards: u32, n_queries: u64, k_stride: u32, ids: [*]const u32, scores: [*]const u32, counts: [*]const u32, opts: [*]const SearchOpts, out_ids: [*]u32, out_scores: [*]u32, out_counts: [*]u32) Status;
 
 // ---- the single-query seam of MultiIndex.search (MultiIndex.zig:287-330)
 pub extern fn fpx_batcher_create(ctx: *Ctx, cfg: ?*const BatcherConfig, out: *?*Batcher) Status;
 pub extern fn fpx_batcher_set_snapshot(b: *Batcher, s: ?*Snapshot) Status;
 pub extern fn fpx_batcher_search(b: *Batcher, terms: [*]const u32, n_terms: u64, opts: *const SearchOpts, timeout_ms: u32, out_ids: [*]u32, out_scores: [*]u32, capacity: u32, out_count: *u32) Status;
+pub extern fn fpx_batcher_get_stats(b: *Batcher, out: *BatcherStats) Status;
 pub extern fn fpx_batcher_destroy(b: *Batcher) void;
 
 // ---- segment files for a search-only process (filefmt.zig:209-285, manifest.zig:17-39)
@@ -84,6 +132,45 @@ pub extern fn fpx_segment_file_read(path: [*:0]const u8, out: *?*SegmentFile) St
 pub extern fn fpx_segment_file_view(f: *SegmentFile, seg: *FileSegmentDesc, info: *SegmentInfo) Status;
 pub extern fn fpx_segment_file_close(f: *SegmentFile) void;
 pub extern fn fpx_manifest_parse(data: [*]const u8, size: u64, out: [*]SegmentInfo, capacity: u64, out_n: *u64) Status;
+pub extern fn fpx_segment_file_parse(data: [*]const u8, size: u64, out: *?*SegmentFile) Status;
+pub extern fn fpx_segment_file_num_items(f: *const SegmentFile) u64;
+pub extern fn fpx_segment_file_metadata_count(f: *const SegmentFile) u64;
+pub extern fn fpx_segment_file_metadata_get(f: *const SegmentFile, i: u64, key: *[*]const u8, key_len: *u64, value: *[*]const u8, value_len: *u64) Status;
+pub extern fn fpx_segment_file_serialize(seg: *const FileSegmentDesc, info: *const SegmentInfo, out: *?[*]u8, out_size: *u64) Status;
+pub extern fn fpx_bytes_free(p: ?[*]u8) void;
+pub extern fn fpx_segment_file_name(commit_id: u64, merges: u64, buf: [*]u8, cap: u64) i32;
+pub extern fn fpx_crc64_xz(data: [*]const u8, size: u64) u64;
+
+// ---- the block codec by itself (block.zig:438-567 / filefmt.zig:94-138): writer and single-block reader
+pub extern fn fpx_segment_write(items: [*]const u64, n_items: u64, min_doc_id: u32, block_size: u32, threads: u32, out: *?*SegmentBuf) Status;
+pub extern fn fpx_segment_buf_blocks(b: *const SegmentBuf) [*]const u8;
+pub extern fn fpx_segment_buf_block_index(b: *const SegmentBuf) [*]const u32;
+pub extern fn fpx_segment_buf_num_blocks(b: *const SegmentBuf) u64;
+pub extern fn fpx_segment_buf_num_items(b: *const SegmentBuf) u64;
+pub extern fn fpx_segment_buf_block_size(b: *const SegmentBuf) u32;
+pub extern fn fpx_segment_buf_free(b: *SegmentBuf) void;
+pub extern fn fpx_block_decode(block: [*]const u8, block_size: u32, min_doc_id: u32, out_hashes: [*]u32, out_docids: [*]u32) i32;
+
+// ---- snapshot introspection (tests, accounting) and the host-side CSR view of a builder
+pub extern fn fpx_snapshot_compile(b: *Builder) Status;
+pub extern fn fpx_snapshot_csr(b: *Builder, out: *CsrView) Status;
+pub extern fn fpx_snapshot_get_info(s: *const Snapshot, out: *SnapshotInfo) Status;
+pub extern fn fpx_snapshot_read_row(s: *const Snapshot, term: u32, out_docids: [*]u32, capacity: u64, out_len: *u64) Status;
+pub extern fn fpx_snapshot_row_lengths(s: *const Snapshot, terms: [*]const u32, n: u64, out_lengths: [*]u32) Status;
+
+// ---- wire codecs of the search endpoint (api.zig:14-72, server.zig:84-142, legacy.zig:185-210, 286-296)
+pub extern fn fpx_wire_decode_search_request(format: u32, data: [*]const u8, size: u64, out: *WireSearchRequest) Status;
+pub extern fn fpx_wire_encode_search_response(format: u32, ids: [*]const u32, scores: [*]const u32, n: u32, out: *?[*]u8, out_size: *u64) Status;
+pub extern fn fpx_legacy_parse_fingerprint(text: [*]const u8, len: u64, out_terms: *?[*]u32, out_n: *u64) Status;
+pub extern fn fpx_legacy_format_results(ids: [*]const u32, scores: [*]const u32, n: u32, out: *?[*]u8, out_size: *u64) Status;
+pub extern fn fpx_wire_free(p: ?*anyopaque) void;
+
+// ---- tuning and profiling
+pub extern fn fpx_set_chunk_queries(ctx: *Ctx, chunk_queries: u32) Status;
+pub extern fn fpx_set_profile(ctx: *Ctx, enabled: c_int) Status;
+pub extern fn fpx_profile_reset(ctx: *Ctx) Status;
+pub extern fn fpx_profile_read(ctx: *Ctx, out: *Profile) Status;
+pub extern fn fpx_debug_set(ctx: *Ctx, bits: u32) Status;
 
 pub fn toError(st: Status) anyerror!void {
     return switch (st) {
