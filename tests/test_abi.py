@@ -2,6 +2,7 @@
 import ctypes as C
 import os
 import re
+import subprocess
 
 import pytest
 
@@ -72,3 +73,31 @@ def test_product_never_touches_the_oracle():
                 assert "liboracle" not in txt and "fpindex_oracle" not in txt and "_oracle" not in txt, f
     out = os.popen("ldd '%s'" % pkg._ffi.LIB_PATH).read()
     assert "oracle" not in out
+
+
+def _build_c_example(tmp_path):
+    """tests/c_abi/example.c compiled as strict C99 against include/*.h and linked with libfpx.so."""
+    exe = os.path.join(str(tmp_path), "fpx_example")
+    pkg_dir = os.path.dirname(pkg._ffi.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c_abi", "example.c"), "-L", pkg_dir, "-lfpx", "-Wl,-rpath," + pkg_dir, "-o", exe]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    return exe
+
+
+def test_headers_are_c_and_a_c_host_links(tmp_path):
+    """The boundary is a C ABI: a C99 translation unit includes both headers, links, writes a segment with the library's
+    block writer and gets as far as fpx_init.  Without a device that returns FPX_BACKEND_UNAVAILABLE (exit 77: the caller
+    keeps its CPU path — there is no CPU fallback inside the library); with one, the query is answered (exit 0)."""
+    run = subprocess.run([_build_c_example(tmp_path)], capture_output=True, text=True)
+    assert run.returncode in (0, 77), (run.returncode, run.stdout, run.stderr)
+    if run.returncode == 77:
+        assert "no CUDA device" in run.stderr
+
+
+@pytest.mark.gpu
+def test_c_host_answers_a_query_on_the_gpu(tmp_path):
+    run = subprocess.run([_build_c_example(tmp_path)], capture_output=True, text=True)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    assert "results: 1, first (id 8, score 20)" in run.stdout
